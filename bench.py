@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GKR prover hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one GKR proof (gkr_prove through the C ABI) of the synthetic layered add/mul circuit of
+BASELINE.json config 3: 2^20 gates/layer x 16 layers, BN254 Fr, MiMC7 transcript on the host.
+  value : ms per proof with circuit + witness already resident in HBM (device time, CUDA events on the
+          prover's stream, max over ranks).  N > 1: every rank proves one independent proof of the same
+          shape (batch distribution, no data-path collective) -> weak scaling, value = ms per proof
+          amortised over the job (max-rank time / N).
+  e2e   : the same metric through the public host API with HOST buffers: pinned input layer -> H2D ->
+          on-device circuit evaluation -> proof -> Proof arrays back on the host.
+Extra objects: roofline (dominant kernel class, per-launch CUDA events inside the library),
+cpu_baseline (dense CPU oracle port on a bounded sample), sumcheck (standalone 3-table product
+sumcheck, Melem/s + HBM roofline fraction), clocks.
+--impl reference times the CPU oracle port of the reference algorithm (the Rust reference cannot be built
+here: no toolchain) on the same config, each step a bounded sample.
+Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "gkr_prove_ms"
+UNIT = "ms"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _workload_name(k, layers):
+    return f"synthetic layered add/mul circuit, 2^{k} gates/layer x {layers} layers, BN254 Fr, MiMC7-91 transcript"
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# --------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "no samples"}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the dense oracle port on a bounded sample
+# --------------------------------------------------------------------------------------------------
+def cpu_sample_ms(k: int, layers: int, sample_layers: int, seed: int = 1):
+    """ms for a full `layers`-layer proof, extrapolated from proving the first `sample_layers` layers
+    (all layers have the same shape and cost) with the dense CPU oracle on all host threads."""
+    from gkr_b200 import synthetic as syn
+    from oracle import oracle as orc
+    sl = min(sample_layers, layers)
+    circ = syn.layered_circuit(seed, k, sl)
+    inputs = syn.input_values(seed, k)
+    ol = [orc.DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in circ]
+    vals = orc.evaluate_circuit(ol, inputs.view(np.uint8).reshape(-1, 32))
+    t0 = time.perf_counter()
+    orc.gkr_prove(ol, vals)
+    dt = time.perf_counter() - t0
+    return dt * 1e3 * (layers / sl), orc.num_threads(), f"{sl} of {layers} layers of the same circuit, scaled x{layers / sl:g}"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    k, layers = args.k, args.layers
+    sample_layers = 1 if k >= 20 else 2
+    for _ in range(args.warmup):
+        cpu_sample_ms(k, layers, sample_layers)
+    vals = []
+    cores, sample = 0, ""
+    for _ in range(args.steps):
+        ms, cores, sample = cpu_sample_ms(k, layers, sample_layers)
+        vals.append(ms)
+    ms = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32x8 (BN254 Fr, 254-bit integers)", "data": "synthetic",
+        "config": {"workload": _workload_name(k, layers), "k": k, "layers": layers},
+        "cpu_baseline": {"value": ms, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "dense CPU oracle (oracle/gkr_dense.c, OpenMP); the Rust reference cannot be built here "
+                                 "and its term-list algorithm is O(4^k) per round (infeasible at this size)"},
+        "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import gkr_b200
+    from gkr_b200 import synthetic as syn
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; gkr_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    hbm_peak, peak_src = _peaks()
+    k, layers = args.k, args.layers
+    pv = gkr_b200.Prover(local)
+    ext = torch.cuda.ExternalStream(pv.stream, device=torch.device("cuda", local))
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+
+    seed = 1 + rank
+    circ_layers = syn.layered_circuit(seed, k, layers)
+    inputs_np = syn.input_values(seed, k)
+    pinned = torch.empty(inputs_np.shape, dtype=torch.int32, pin_memory=True)
+    pinned_np = pinned.numpy().view(np.uint32)
+    pinned_np[...] = inputs_np
+    circuit = pv.circuit(circ_layers)
+    witness = pv.witness_eval(circuit, pinned_np)
+
+    def step_resident():
+        ptr = pv.prove_raw(circuit, witness)
+        pv.free_raw(ptr)
+
+    def step_e2e():
+        w = pv.witness_eval(circuit, pinned_np)
+        ptr = pv.prove_raw(circuit, w)
+        pv.free_raw(ptr)
+        w.close()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        total_ms = 0.0
+        for _ in range(steps):
+            flush_l2()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            fn()
+            e1.record(ext)
+            e1.synchronize()
+            barrier()
+            total_ms += e0.elapsed_time(e1)
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    clocks = Clocks(local) if rank == 0 else None
+    pv.stats(reset=True)
+    total_ms = timed(step_resident, args.steps, args.warmup)
+    st = pv.stats(reset=True)
+    launches_timed = st["kernel_launches"] * args.steps // (args.steps + args.warmup)
+    e2e_ms = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    st2 = pv.stats(reset=True)
+    n_e2e = args.steps + max(1, args.warmup // 2)
+    clock_info = clocks.stop() if clocks else None
+
+    ms_per_step = total_ms / args.steps
+    value = ms_per_step / world                      # amortised ms per proof over the whole job
+    e2e_value = e2e_ms / args.steps / world
+
+    # ---- per-kernel-class device timing (library-side CUDA events around every launch) --------------
+    pv.profile(1)
+    step_resident()
+    prof = pv.profile(0)
+    classes = {n: d for n, d in prof.items() if d["launches"]}
+    dom = max(("gkr_round_fused", "gkr_round", "wiring", "line", "mobius", "eq"), key=lambda n: prof[n]["ms"])
+    d = prof[dom]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    achieved = d["algo_bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "launches": d["launches"], "avg_launch_us": 1e3 * d["ms"] / max(1, d["launches"]),
+                "algo_bytes_per_launch": d["algo_bytes"] / max(1, d["launches"]),
+                "note": "tables of this workload (3 x 32 MiB per phase) mostly fit the 126 MB L2; the HBM-bound "
+                        "measurement is the `sumcheck` object (tables larger than L2)",
+                "share_of_device_time": d["ms"] / max(1e-9, sum(x["ms"] for x in prof.values()))}
+
+    # ---- standalone product sumcheck (BASELINE.json config 4 at 1 GPU; tables larger than L2) ----------
+    sumcheck = None
+    if args.sumcheck_vars:
+        v = args.sumcheck_vars
+        N = 1 << v
+        tabs = [pv.dev_table_synth(seed, syn.TABLE_STREAM + t, N) for t in range(3)]
+
+        def step_sc():
+            pv.sumcheck_prod_raw(tabs, v)
+        sc_ms = timed(step_sc, args.steps, args.warmup) / args.steps
+        pv.profile(1)
+        step_sc()
+        sp = pv.profile(0)
+        algo = 32.0 * 3 * (4 * N - 6)
+        kern_ms = sp["prod3_round"]["ms"] + sp["prod3_round_fused"]["ms"]
+        kern_bytes = sp["prod3_round"]["algo_bytes"] + sp["prod3_round_fused"]["algo_bytes"]
+        sumcheck = {"n_vars": v, "tables": 3, "ms": sc_ms, "melem_s": N / (sc_ms * 1e-3) / 1e6 * world,
+                    "algo_bytes": algo, "gbs_whole_sumcheck": algo / (sc_ms * 1e-3) / 1e9,
+                    "frac_whole_sumcheck": algo / (sc_ms * 1e-3) / 1e9 / hbm_peak,
+                    "round_kernels": {"ms": kern_ms, "gbs": kern_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms else 0.0,
+                                      "frac": kern_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak if kern_ms else 0.0,
+                                      "first_round_ms": sp["prod3_round"]["ms"],
+                                      "first_round_gbs": sp["prod3_round"]["algo_bytes"] / (sp["prod3_round"]["ms"] * 1e-3) / 1e9
+                                      if sp["prod3_round"]["ms"] else 0.0},
+                    "l2": "inputs larger than L2 (3 x %d MiB)" % (N * 32 >> 20)}
+        for t in tabs:
+            t.close()
+
+    # ---- CPU baseline on rank 0, N = 1 only -----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            ms, cores, sample = cpu_sample_ms(k, layers, 1 if k >= 20 else 2)
+            cpu = {"value": ms, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                   "note": "dense CPU oracle (oracle/gkr_dense.c); the Rust reference cannot be built here"}
+        except Exception as e:  # the oracle is a checker, never a dependency of the measured path
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 (BN254 Fr, 254-bit integers)", "data": "synthetic",
+            "config": {"workload": _workload_name(k, layers), "k": k, "layers": layers,
+                       "parallelism": "1 proof per GPU" if world > 1 else "single GPU",
+                       "l2": "256 MiB flush between timed iterations; witness tables total %d MiB" % ((layers + 1) * (32 << k) >> 20),
+                       "timing": "CUDA events on the prover stream, per step, summed; max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st2["h2d_bytes"] // n_e2e,
+                    "d2h_bytes_per_step": st2["d2h_bytes"] // n_e2e,
+                    "note": "pinned input layer -> H2D -> device circuit evaluation -> gkr_prove -> Proof on host"},
+            "gpu_launches": int(launches_timed),
+            "roofline": roofline, "cpu_baseline": cpu, "sumcheck": sumcheck, "clocks": clock_info,
+            "kernel_classes": {n: {"launches": x["launches"], "ms": round(x["ms"], 4),
+                                   "gbs": round(x["algo_bytes"] / (x["ms"] * 1e-3) / 1e9, 1) if x["ms"] else None}
+                               for n, x in classes.items()},
+            "host": {"transcript_ms_per_step": 1e3 * st["transcript_seconds"] / (args.steps + args.warmup),
+                     "wait_ms_per_step": 1e3 * st["wait_seconds"] / (args.steps + args.warmup)},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--k", type=int, default=20, help="log2 gates per layer (BASELINE config 3: 20)")
+    ap.add_argument("--layers", type=int, default=16)
+    ap.add_argument("--sumcheck-vars", type=int, default=24, help="standalone 3-table sumcheck size (0 = skip)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

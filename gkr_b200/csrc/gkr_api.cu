@@ -1,0 +1,942 @@
+// C ABI (include/gkr_b200.h) + host driver of the GKR prover.
+//
+// Host driver == the per-layer loop of rust/src/gkr/prover.rs:6-96 and the round structure of
+// rust/src/gkr/sumcheck.rs:36-156, restated on dense device tables:
+//   per layer: eq(z_i,.) table -> phase-1 wiring sums (H, A over b) -> k rounds (fused fold+eval)
+//              -> W(u) -> eq(u,.) -> phase-2 wiring sums -> k rounds -> q_i line restriction
+//              -> r*_i, z_{i+1} on the host.
+// The transcript (MiMC7) and all vector bookkeeping stay on the host; every table operation is a CUDA
+// kernel (kernels.cu).  There is no CPU fallback: without a device every entry point fails.
+#include <immintrin.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <new>
+
+#include "runtime.cuh"
+#include "transcript.hpp"
+
+using namespace gkr;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+namespace gkr {
+static thread_local char g_err[512] = "";
+void set_last_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+}  // namespace gkr
+
+extern "C" const char *gkr_last_error(void) { return g_err; }
+extern "C" const char *gkr_version(void) { return "gkr_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+int gkr_ctx::wait_slot(uint32_t s, const HostSlot **out) {
+    const double t0 = now_seconds();
+    volatile HostSlot *slot = slots_host + (s % kSlots);
+    uint64_t spins = 0;
+    while (slot->seq != s) {
+        _mm_pause();
+        if ((++spins & 0xFFFFF) == 0) {
+            cudaError_t e = cudaStreamQuery(stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) {
+                set_last_error("stream error while waiting for a round result: %s", cudaGetErrorString(e));
+                return GKR_ERR_CUDA;
+            }
+            if (e == cudaSuccess && slot->seq != s) {
+                // stream drained: give the mapped write a last chance to land, then fail loudly
+                cudaStreamSynchronize(stream);
+                if (slot->seq != s) {
+                    set_last_error("round result %u never arrived (slot holds %u)", s, (unsigned)slot->seq);
+                    return GKR_ERR_INTERNAL;
+                }
+            }
+            if (now_seconds() - t0 > 120.0) {
+                set_last_error("timed out waiting for round result %u", s);
+                return GKR_ERR_INTERNAL;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    *out = const_cast<const HostSlot *>(slot);
+    stats.wait_seconds += now_seconds() - t0;
+    return GKR_OK;
+}
+
+extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
+    if (!out) return GKR_ERR_INVALID;
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        set_last_error("no CUDA device available (%s); gkr_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        cudaGetLastError();
+        return GKR_ERR_CUDA;
+    }
+    if (device < 0 || device >= n_dev) {
+        set_last_error("device %d out of range (%d devices)", device, n_dev);
+        return GKR_ERR_INVALID;
+    }
+    std::unique_ptr<gkr_ctx> ctx(new (std::nothrow) gkr_ctx());
+    if (!ctx) return GKR_ERR_OOM;
+    ctx->device = device;
+    GKR_TRY(ctx->bind());
+    GKR_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->slots_host, sizeof(HostSlot) * gkr_ctx::kSlots, cudaHostAllocMapped));
+    std::memset((void *)ctx->slots_host, 0, sizeof(HostSlot) * gkr_ctx::kSlots);
+    GKR_CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->slots_dev, (void *)ctx->slots_host, 0));
+    ctx->pinned_elems = 4096;
+    GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->pinned, sizeof(gkr_fr) * ctx->pinned_elems, cudaHostAllocDefault));
+    ctx->ws.max_blocks = device_sm_count() * 4;
+    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->ws.partials, sizeof(Fr) * 6 * (size_t)ctx->ws.max_blocks));
+    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->ws.counter, sizeof(unsigned int)));
+    GKR_CUDA_TRY(cudaMemsetAsync(ctx->ws.counter, 0, sizeof(unsigned int), ctx->stream));
+    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->words, sizeof(unsigned int) * 8));
+    GKR_CUDA_TRY(cudaMemsetAsync(ctx->words, 0, sizeof(unsigned int) * 8, ctx->stream));
+    GKR_CUDA_TRY(cudaEventCreate(&ctx->ev0));
+    GKR_CUDA_TRY(cudaEventCreate(&ctx->ev1));
+    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = ctx.release();
+    return GKR_OK;
+}
+
+extern "C" void gkr_ctx_destroy(gkr_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (DevBuf *b : {&ctx->eqz, &ctx->equ, &ctx->eq_scratch, &ctx->H, &ctx->A, &ctx->foldA, &ctx->foldB, &ctx->lineA,
+                      &ctx->lineB, &ctx->mob, &ctx->misc, &ctx->stage})
+        b->release();
+    if (ctx->ws.partials) cudaFree(ctx->ws.partials);
+    if (ctx->ws.counter) cudaFree(ctx->ws.counter);
+    if (ctx->words) cudaFree(ctx->words);
+    if (ctx->slots_host) cudaFreeHost((void *)ctx->slots_host);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" void *gkr_ctx_stream(gkr_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int gkr_ctx_sync(gkr_ctx *ctx) {
+    if (!ctx) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GKR_OK;
+}
+
+extern "C" int gkr_ctx_stats(gkr_ctx *ctx, gkr_stats *out, int reset) {
+    if (!ctx) return GKR_ERR_INVALID;
+    if (out) *out = ctx->stats;
+    if (reset) ctx->stats = gkr_stats{};
+    return GKR_OK;
+}
+extern "C" int gkr_ctx_profile(gkr_ctx *ctx, int enable, gkr_profile *out) {
+    if (!ctx) return GKR_ERR_INVALID;
+    if (out) *out = ctx->prof;
+    if (enable >= 0) {
+        ctx->profiling = enable != 0;
+        ctx->prof = gkr_profile{};
+    }
+    return GKR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// transcript
+// ------------------------------------------------------------------------------------------------
+static int challenge_for(gkr_ctx *ctx, const gkr_transcript *t, const HFr *msg, uint32_t n, HFr *r_out) {
+    const double t0 = now_seconds();
+    int rc = GKR_OK;
+    if (t && t->challenge) {
+        gkr_fr buf[8], r;
+        for (uint32_t i = 0; i < n; ++i) hfr_to_canonical(&buf[i], msg[i]);
+        if (t->challenge(t->user, buf, n, &r) != 0) {
+            set_last_error("transcript callback failed");
+            rc = GKR_ERR_TRANSCRIPT;
+        } else if (!hfr_from_canonical(r_out, &r)) {
+            set_last_error("transcript callback returned a value >= p");
+            rc = GKR_ERR_RANGE;
+        }
+    } else {
+        *r_out = mimc7_multi_hash(msg, n, hfr_zero());
+    }
+    ctx->stats.transcript_seconds += now_seconds() - t0;
+    return rc;
+}
+
+extern "C" int gkr_mimc7_multi_hash(const gkr_fr *msg, uint32_t n, const gkr_fr *key, gkr_fr *out) {
+    if ((!msg && n) || !key || !out) return GKR_ERR_INVALID;
+    HFr k;
+    if (!hfr_from_canonical(&k, key)) return GKR_ERR_RANGE;
+    std::vector<HFr> m(n);
+    for (uint32_t i = 0; i < n; ++i)
+        if (!hfr_from_canonical(&m[i], &msg[i])) return GKR_ERR_RANGE;
+    hfr_to_canonical(out, mimc7_multi_hash(m.data(), n, k));
+    return GKR_OK;
+}
+extern "C" int gkr_mimc7_hash(const gkr_fr *x, const gkr_fr *key, gkr_fr *out) {
+    if (!x || !key || !out) return GKR_ERR_INVALID;
+    HFr a, k;
+    if (!hfr_from_canonical(&a, x) || !hfr_from_canonical(&k, key)) return GKR_ERR_RANGE;
+    hfr_to_canonical(out, mimc7_hash(a, k));
+    return GKR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+// upload canonical host values and convert to Montgomery on the device; fails on values >= p
+static int upload_table(gkr_ctx *ctx, const gkr_fr *host, uint64_t n, Fr *dev_out) {
+    GKR_TRY(ctx->stage.ensure(n * sizeof(Fr)));
+    GKR_CUDA_TRY(cudaMemcpyAsync(ctx->stage.ptr, host, n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += n * sizeof(Fr);
+    ctx->begin_launch();
+    launch_to_mont(ctx->stage.as<Fr>(), dev_out, n, ctx->words, ctx->stream);
+    ctx->end_launch(KC_OTHER, 64.0 * n);
+    GKR_TRY(ctx->check_launch("to_mont"));
+    unsigned int flag = 0;
+    GKR_CUDA_TRY(cudaMemcpyAsync(&flag, ctx->words, sizeof flag, cudaMemcpyDeviceToHost, ctx->stream));
+    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (flag) {
+        cudaMemsetAsync(ctx->words, 0, sizeof(unsigned int), ctx->stream);
+        set_last_error("a field element >= p was supplied");
+        return GKR_ERR_RANGE;
+    }
+    return GKR_OK;
+}
+// Montgomery device table -> canonical host values
+static int download_table(gkr_ctx *ctx, const Fr *dev, uint64_t n, gkr_fr *host) {
+    GKR_TRY(ctx->stage.ensure(n * sizeof(Fr)));
+    ctx->begin_launch();
+    launch_from_mont(dev, ctx->stage.as<Fr>(), n, ctx->stream);
+    ctx->end_launch(KC_OTHER, 64.0 * n);
+    GKR_TRY(ctx->check_launch("from_mont"));
+    GKR_CUDA_TRY(cudaMemcpyAsync(host, ctx->stage.ptr, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += n * sizeof(Fr);
+    return GKR_OK;
+}
+static int eq_table_dev(gkr_ctx *ctx, const HFr *z, uint32_t k, Fr *out) {
+    if (k > 32) return GKR_ERR_INVALID;
+    FrVec zv;
+    std::memset(&zv, 0, sizeof zv);
+    for (uint32_t j = 0; j < k; ++j) zv.v[j] = to_dev(z[j]);
+    GKR_TRY(ctx->eq_scratch.ensure(sizeof(Fr) * 2 * ((size_t)1 << ((k + 1) / 2 + 1))));
+    ctx->begin_launch();
+    launch_eq_table(zv, k, out, ctx->eq_scratch.as<Fr>(), ctx->stream);
+    ctx->end_launch(KC_EQ, 32.0 * (double)((uint64_t)1 << k), k <= 8 ? 1 : 3);
+    return ctx->check_launch("eq_table");
+}
+// values -> Moebius coefficients (in place) + support; waits for the result
+static int mobius_support(gkr_ctx *ctx, Fr *table, uint32_t k, uint32_t *dep_mask, uint32_t *max_deg, bool *any) {
+    const uint64_t n = (uint64_t)1 << k;
+    ctx->begin_launch();
+    launch_mobius(table, k, ctx->stream);
+    ctx->end_launch(KC_MOBIUS, 64.0 * n * (k > 10 ? 1 + (k - 10) : 1), k > 10 ? 1 + (int)(k - 10) : 1);
+    GKR_TRY(ctx->check_launch("mobius"));
+    const uint32_t s = ctx->next_seq();
+    ctx->begin_launch();
+    launch_coef_support(table, n, ctx->words + 4, ctx->slot_dev(s), s, ctx->stream);
+    ctx->end_launch(KC_MOBIUS, 32.0 * n, 2);
+    GKR_TRY(ctx->check_launch("coef_support"));
+    const HostSlot *slot;
+    GKR_TRY(ctx->wait_slot(s, &slot));
+    *dep_mask = slot->aux[0];
+    *max_deg = slot->aux[1];
+    if (any) *any = slot->aux[2] != 0;
+    return GKR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// circuit
+// ------------------------------------------------------------------------------------------------
+struct LayerDev {
+    uint32_t k_out = 0, k_in = 0, n_gates = 0;
+    uint8_t *type = nullptr;
+    uint32_t *left = nullptr, *right = nullptr;
+    uint32_t *rowptr1 = nullptr, *gate1 = nullptr, *other1 = nullptr;   // CSR by left operand
+    uint32_t *rowptr2 = nullptr, *gate2 = nullptr, *other2 = nullptr;   // CSR by right operand
+};
+struct gkr_circuit {
+    int device = 0;
+    std::vector<LayerDev> layers;
+    std::vector<uint32_t> k;      // k_0 .. k_depth
+    uint32_t max_k = 0;
+};
+
+// stable counting sort of the gates of one layer by `key` -> CSR rows
+static void build_csr(uint32_t n_rows, uint32_t n_gates, const uint32_t *key, const uint32_t *other, const uint8_t *type,
+                      std::vector<uint32_t> &rowptr, std::vector<uint32_t> &gate, std::vector<uint32_t> &oth) {
+    rowptr.assign((size_t)n_rows + 1, 0);
+    for (uint32_t g = 0; g < n_gates; ++g) rowptr[key[g] + 1]++;
+    for (uint32_t r = 0; r < n_rows; ++r) rowptr[r + 1] += rowptr[r];
+    std::vector<uint32_t> cursor(rowptr.begin(), rowptr.end() - 1);
+    gate.resize(n_gates);
+    oth.resize(n_gates);
+    for (uint32_t g = 0; g < n_gates; ++g) {
+        const uint32_t pos = cursor[key[g]]++;
+        gate[pos] = g;
+        oth[pos] = other[g] | ((uint32_t)type[g] << 31);
+    }
+}
+
+template <typename T>
+static int dev_copy(gkr_ctx *ctx, T **dst, const T *src, size_t n) {
+    GKR_CUDA_TRY(cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T)));
+    GKR_CUDA_TRY(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += n * sizeof(T);
+    return GKR_OK;
+}
+
+extern "C" void gkr_circuit_destroy(gkr_circuit *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (LayerDev &L : c->layers)
+        for (void *p : {(void *)L.type, (void *)L.left, (void *)L.right, (void *)L.rowptr1, (void *)L.gate1,
+                        (void *)L.other1, (void *)L.rowptr2, (void *)L.gate2, (void *)L.other2})
+            if (p) cudaFree(p);
+    delete c;
+}
+
+extern "C" int gkr_circuit_create(gkr_ctx *ctx, uint32_t n_layers, const gkr_layer_desc *layers, gkr_circuit **out) {
+    if (!ctx || !layers || !out || n_layers == 0) {
+        set_last_error("gkr_circuit_create: null argument or zero layers");
+        return GKR_ERR_INVALID;
+    }
+    *out = nullptr;
+    GKR_TRY(ctx->bind());
+    for (uint32_t i = 0; i < n_layers; ++i) {
+        const gkr_layer_desc &d = layers[i];
+        if (d.k_in == 0) {
+            set_last_error("layer %u: k_in = 0 is unsupported (the reference underflows v-1, sumcheck.rs:49)", i);
+            return GKR_ERR_INVALID;
+        }
+        if (d.k_in > 30 || d.k_out > 30) {
+            set_last_error("layer %u: k_out=%u / k_in=%u exceeds 30", i, d.k_out, d.k_in);
+            return GKR_ERR_INVALID;
+        }
+        if (d.n_gates == 0 || d.n_gates > ((uint32_t)1 << d.k_out) || !d.type || !d.left || !d.right) {
+            set_last_error("layer %u: n_gates=%u must be in 1..2^k_out and arrays non-null", i, d.n_gates);
+            return GKR_ERR_INVALID;
+        }
+        if (i + 1 < n_layers && layers[i + 1].k_out != d.k_in) {
+            set_last_error("layer %u: k_in=%u != k_out=%u of layer %u", i, d.k_in, layers[i + 1].k_out, i + 1);
+            return GKR_ERR_INVALID;
+        }
+        const uint32_t lim = (uint32_t)1 << d.k_in;
+        for (uint32_t g = 0; g < d.n_gates; ++g)
+            if (d.left[g] >= lim || d.right[g] >= lim || d.type[g] > 1) {
+                set_last_error("layer %u gate %u: operand/type out of range", i, g);
+                return GKR_ERR_INVALID;
+            }
+    }
+    std::unique_ptr<gkr_circuit, void (*)(gkr_circuit *)> c(new (std::nothrow) gkr_circuit(), gkr_circuit_destroy);
+    if (!c) return GKR_ERR_OOM;
+    c->device = ctx->device;
+    c->layers.resize(n_layers);
+    c->k.push_back(layers[0].k_out);
+    std::vector<uint32_t> rowptr, gate, oth;
+    for (uint32_t i = 0; i < n_layers; ++i) {
+        const gkr_layer_desc &d = layers[i];
+        LayerDev &L = c->layers[i];
+        L.k_out = d.k_out; L.k_in = d.k_in; L.n_gates = d.n_gates;
+        c->k.push_back(d.k_in);
+        c->max_k = std::max(c->max_k, std::max(d.k_in, d.k_out));
+        GKR_TRY(dev_copy(ctx, &L.type, d.type, d.n_gates));
+        GKR_TRY(dev_copy(ctx, &L.left, d.left, d.n_gates));
+        GKR_TRY(dev_copy(ctx, &L.right, d.right, d.n_gates));
+        const uint32_t rows = (uint32_t)1 << d.k_in;
+        build_csr(rows, d.n_gates, d.left, d.right, d.type, rowptr, gate, oth);
+        GKR_TRY(dev_copy(ctx, &L.rowptr1, rowptr.data(), rowptr.size()));
+        GKR_TRY(dev_copy(ctx, &L.gate1, gate.data(), gate.size()));
+        GKR_TRY(dev_copy(ctx, &L.other1, oth.data(), oth.size()));
+        GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // host vectors are reused below
+        build_csr(rows, d.n_gates, d.right, d.left, d.type, rowptr, gate, oth);
+        GKR_TRY(dev_copy(ctx, &L.rowptr2, rowptr.data(), rowptr.size()));
+        GKR_TRY(dev_copy(ctx, &L.gate2, gate.data(), gate.size()));
+        GKR_TRY(dev_copy(ctx, &L.other2, oth.data(), oth.size()));
+        GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = c.release();
+    return GKR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// witness
+// ------------------------------------------------------------------------------------------------
+struct gkr_witness {
+    int device = 0;
+    std::vector<Fr *> vals;       // Montgomery tables, layer 0 .. depth
+    std::vector<uint32_t> k;
+};
+extern "C" void gkr_witness_destroy(gkr_witness *w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    for (Fr *p : w->vals)
+        if (p) cudaFree(p);
+    delete w;
+}
+static int witness_alloc(gkr_ctx *ctx, const gkr_circuit *c, std::unique_ptr<gkr_witness, void (*)(gkr_witness *)> &w) {
+    w.reset(new (std::nothrow) gkr_witness());
+    if (!w) return GKR_ERR_OOM;
+    w->device = ctx->device;
+    w->k = c->k;
+    w->vals.assign(c->k.size(), nullptr);
+    for (size_t i = 0; i < c->k.size(); ++i) {
+        cudaError_t e = cudaMalloc((void **)&w->vals[i], sizeof(Fr) << c->k[i]);
+        if (e != cudaSuccess) {
+            set_last_error("cudaMalloc of witness layer %zu failed: %s", i, cudaGetErrorString(e));
+            cudaGetLastError();
+            return e == cudaErrorMemoryAllocation ? GKR_ERR_OOM : GKR_ERR_CUDA;
+        }
+    }
+    return GKR_OK;
+}
+extern "C" int gkr_witness_create(gkr_ctx *ctx, const gkr_circuit *c, const gkr_fr *const *layer_values,
+                                  gkr_witness **out) {
+    if (!ctx || !c || !layer_values || !out) return GKR_ERR_INVALID;
+    *out = nullptr;
+    GKR_TRY(ctx->bind());
+    std::unique_ptr<gkr_witness, void (*)(gkr_witness *)> w(nullptr, gkr_witness_destroy);
+    GKR_TRY(witness_alloc(ctx, c, w));
+    for (size_t i = 0; i < c->k.size(); ++i) {
+        if (!layer_values[i]) return GKR_ERR_INVALID;
+        GKR_TRY(upload_table(ctx, layer_values[i], (uint64_t)1 << c->k[i], w->vals[i]));
+    }
+    *out = w.release();
+    return GKR_OK;
+}
+extern "C" int gkr_witness_eval(gkr_ctx *ctx, const gkr_circuit *c, const gkr_fr *input_values, gkr_witness **out) {
+    if (!ctx || !c || !input_values || !out) return GKR_ERR_INVALID;
+    *out = nullptr;
+    GKR_TRY(ctx->bind());
+    std::unique_ptr<gkr_witness, void (*)(gkr_witness *)> w(nullptr, gkr_witness_destroy);
+    GKR_TRY(witness_alloc(ctx, c, w));
+    const size_t n = c->layers.size();
+    GKR_TRY(upload_table(ctx, input_values, (uint64_t)1 << c->k[n], w->vals[n]));
+    for (size_t i = n; i-- > 0;) {
+        const LayerDev &L = c->layers[i];
+        ctx->begin_launch();
+        launch_layer_eval(L.type, L.left, L.right, w->vals[i + 1], w->vals[i], L.n_gates, (uint64_t)1 << L.k_out,
+                          ctx->stream);
+        ctx->end_launch(KC_OTHER, 96.0 * L.n_gates);
+        GKR_TRY(ctx->check_launch("layer_eval"));
+    }
+    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    *out = w.release();
+    return GKR_OK;
+}
+extern "C" int gkr_witness_layer(gkr_ctx *ctx, const gkr_witness *w, uint32_t layer, gkr_fr *out) {
+    if (!ctx || !w || !out || layer >= w->vals.size()) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    return download_table(ctx, w->vals[layer], (uint64_t)1 << w->k[layer], out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// proof container
+// ------------------------------------------------------------------------------------------------
+struct ProofHolder {
+    gkr_proof pub{};
+    std::vector<uint32_t> k, q_len;
+    std::vector<uint64_t> round_off, q_off, z_off;
+    std::vector<uint8_t> msg_len;
+    std::vector<gkr_fr> msgs, chal, q, z, r, d_coef, input_coef;
+    void finish() {
+        pub.k = k.data(); pub.round_off = round_off.data(); pub.msg_len = msg_len.data();
+        pub.msgs = msgs.data(); pub.chal = chal.data(); pub.q_off = q_off.data(); pub.q_len = q_len.data();
+        pub.q = q.data(); pub.z_off = z_off.data(); pub.z = z.data(); pub.r = r.data();
+        pub.d_coef = d_coef.data(); pub.d_len = d_coef.size();
+        pub.input_coef = input_coef.data(); pub.input_len = input_coef.size();
+    }
+};
+extern "C" void gkr_proof_free(gkr_proof *p) {
+    if (!p) return;
+    delete reinterpret_cast<ProofHolder *>(p);   // pub is the first member
+}
+
+// ------------------------------------------------------------------------------------------------
+// one phase of the per-layer sumcheck: k rounds over (H, W, A), first table size N = 2^k
+// ------------------------------------------------------------------------------------------------
+struct PhaseIO {
+    const Fr *H, *W, *A;       // size N inputs (never written)
+    uint32_t k;
+    uint32_t dep_mask;         // which variables W depends on (bit k-1-j <-> variable j+1)
+    HFr *challenges;           // out: k challenges
+    gkr_fr *msgs;              // out: [k][3]
+    uint8_t *msg_len;          // out: [k]
+    gkr_fr *chal_out;          // out: [k] canonical
+    const Fr *W_last;          // out: device pointer to the size-2 W table of the last round
+};
+
+static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *last_hash) {
+    const uint32_t k = io.k;
+    const uint64_t N = (uint64_t)1 << k;
+    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 2, 2)));
+    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 4, 2)));
+    const Fr *Hc = io.H, *Wc = io.W, *Ac = io.A;
+    uint64_t n = N;                                   // size of the current tables
+    HFr r = hfr_zero();
+    for (uint32_t j = 0; j < k; ++j) {
+        const uint32_t s = ctx->next_seq();
+        ctx->begin_launch();
+        if (j == 0) {
+            launch_gkr_round(false, Hc, Wc, Ac, nullptr, nullptr, nullptr, to_dev(r), n / 2, ctx->ws, ctx->slot_dev(s), s,
+                             ctx->stream);
+            ctx->end_launch(KC_ROUND, 96.0 * n);
+        } else {
+            // fold the size-n tables with r_{j} into size n/2 and evaluate round j+1 on them
+            DevBuf &dst = (j & 1) ? ctx->foldA : ctx->foldB;
+            const uint64_t half = n / 2;
+            Fr *Ho = dst.as<Fr>(), *Wo = Ho + half, *Ao = Wo + half;
+            launch_gkr_round(true, Hc, Wc, Ac, Ho, Wo, Ao, to_dev(r), half / 2, ctx->ws, ctx->slot_dev(s), s, ctx->stream);
+            ctx->end_launch(KC_ROUND_FUSED, 96.0 * n + 96.0 * half);
+            Hc = Ho; Wc = Wo; Ac = Ao;
+            n = half;
+        }
+        GKR_TRY(ctx->check_launch("gkr_round"));
+        const HostSlot *slot;
+        GKR_TRY(ctx->wait_slot(s, &slot));
+        HFr x0, x1, x2;
+        if (!hfr_from_canonical(&x0, &slot->v[0]) || !hfr_from_canonical(&x1, &slot->v[1]) ||
+            !hfr_from_canonical(&x2, &slot->v[2])) {
+            set_last_error("device published a non-canonical round value");
+            return GKR_ERR_INTERNAL;
+        }
+        // message: descending coefficients [c2, c1, c0] or [c1, c0] when W does not depend on x_{j+1}
+        const HFr c1 = hfr_sub(hfr_sub(x1, x0), x2);
+        const bool dep = (io.dep_mask >> (k - 1 - j)) & 1u;
+        HFr msg[3];
+        uint32_t len;
+        if (dep) { msg[0] = x2; msg[1] = c1; msg[2] = x0; len = 3; }
+        else { msg[0] = c1; msg[1] = x0; len = 2; }
+        std::memset(&io.msgs[3 * j], 0, 3 * sizeof(gkr_fr));
+        for (uint32_t i = 0; i < len; ++i) hfr_to_canonical(&io.msgs[3 * j + i], msg[i]);
+        io.msg_len[j] = (uint8_t)len;
+        GKR_TRY(challenge_for(ctx, t, msg, len, &r));
+        io.challenges[j] = r;
+        hfr_to_canonical(&io.chal_out[j], r);
+        *last_hash = r;
+    }
+    io.W_last = Wc;
+    // keep r_k for the caller's final fold
+    return GKR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prove
+// ------------------------------------------------------------------------------------------------
+extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *w, const gkr_transcript *t,
+                         gkr_proof **out) {
+    if (!ctx || !c || !w || !out) return GKR_ERR_INVALID;
+    *out = nullptr;
+    if (w->k != c->k || c->device != ctx->device || w->device != ctx->device) {
+        set_last_error("gkr_prove: witness/circuit/context mismatch");
+        return GKR_ERR_INVALID;
+    }
+    GKR_TRY(ctx->bind());
+    const uint32_t n_layers = (uint32_t)c->layers.size();
+    std::unique_ptr<ProofHolder> P(new (std::nothrow) ProofHolder());
+    if (!P) return GKR_ERR_OOM;
+    P->pub.n_layers = n_layers;
+    P->pub.depth = n_layers + 1;
+    P->k = c->k;
+    P->round_off.assign(n_layers + 1, 0);
+    P->q_off.assign(n_layers + 1, 0);
+    P->z_off.assign(n_layers + 2, 0);
+    for (uint32_t i = 0; i < n_layers; ++i) {
+        P->round_off[i + 1] = P->round_off[i] + 2ull * c->k[i + 1];
+        P->q_off[i + 1] = P->q_off[i] + c->k[i + 1] + 1;
+    }
+    for (uint32_t i = 0; i <= n_layers; ++i) P->z_off[i + 1] = P->z_off[i] + c->k[i];
+    P->pub.n_rounds = P->round_off[n_layers];
+    P->msg_len.assign(P->pub.n_rounds, 0);
+    P->msgs.assign(P->pub.n_rounds * 3, gkr_fr{});
+    P->chal.assign(P->pub.n_rounds, gkr_fr{});
+    P->q.assign(P->q_off[n_layers], gkr_fr{});
+    P->q_len.assign(n_layers, 0);
+    P->z.assign(std::max<uint64_t>(P->z_off[n_layers + 1], 1), gkr_fr{});
+    P->r.assign(n_layers, gkr_fr{});
+
+    const uint64_t Nmax = (uint64_t)1 << c->max_k;
+    GKR_TRY(ctx->H.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->A.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->eqz.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->equ.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->lineA.ensure(sizeof(Fr) * std::max<uint64_t>(Nmax, 64)));
+    GKR_TRY(ctx->lineB.ensure(sizeof(Fr) * std::max<uint64_t>(Nmax, 64)));
+    GKR_TRY(ctx->mob.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
+
+    // d and input_func as dense monomial tables (prover.rs:88,93; get_multi_ext, poly.rs:502-536)
+    for (int which = 0; which < 2; ++which) {
+        const uint32_t layer = which == 0 ? 0 : n_layers;
+        const uint32_t k = c->k[layer];
+        const uint64_t n = (uint64_t)1 << k;
+        std::vector<gkr_fr> &dst = which == 0 ? P->d_coef : P->input_coef;
+        dst.assign(n, gkr_fr{});
+        GKR_CUDA_TRY(cudaMemcpyAsync(ctx->mob.ptr, w->vals[layer], n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->begin_launch();
+        launch_mobius(ctx->mob.as<Fr>(), k, ctx->stream);
+        ctx->end_launch(KC_MOBIUS, 64.0 * n * (k > 10 ? 1 + (k - 10) : 1), k > 10 ? 1 + (int)(k - 10) : 1);
+        GKR_TRY(ctx->check_launch("mobius"));
+        GKR_TRY(download_table(ctx, ctx->mob.as<Fr>(), n, dst.data()));
+    }
+
+    // z_0 = 0 (prover.rs:16-21)
+    std::vector<HFr> z(c->k[0], hfr_zero());
+    std::vector<HFr> rs;
+    std::vector<gkr_fr> qbuf;
+
+    for (uint32_t li = 0; li < n_layers; ++li) {
+        const LayerDev &L = c->layers[li];
+        const uint32_t k = L.k_in;
+        const uint64_t N = (uint64_t)1 << k;
+        const Fr *W = w->vals[li + 1];
+        Fr *H = ctx->H.as<Fr>(), *A = ctx->A.as<Fr>();
+        Fr *wu = ctx->misc.as<Fr>();
+
+        // static shape of W_{i+1}: non-zero top coefficient => depends on every variable, degree k
+        const uint32_t s_alt = ctx->next_seq();
+        ctx->begin_launch();
+        launch_alt_sum(W, N, ctx->ws, ctx->slot_dev(s_alt), s_alt, ctx->stream);
+        ctx->end_launch(KC_MOBIUS, 32.0 * N);
+        GKR_TRY(ctx->check_launch("alt_sum"));
+
+        GKR_TRY(eq_table_dev(ctx, z.data(), L.k_out, ctx->eqz.as<Fr>()));
+        ctx->begin_launch();
+        launch_wiring_phase1(L.rowptr1, L.gate1, L.other1, ctx->eqz.as<Fr>(), W, H, A, N, ctx->stream);
+        ctx->end_launch(KC_WIRING, 76.0 * L.n_gates + 64.0 * N);
+        GKR_TRY(ctx->check_launch("wiring_phase1"));
+
+        uint32_t dep_mask = (uint32_t)(N - 1), max_deg = k;
+        {
+            const HostSlot *slot;
+            GKR_TRY(ctx->wait_slot(s_alt, &slot));
+            if (slot->aux[1] == 0) {
+                // degenerate W: exact shape from the full Moebius transform
+                GKR_CUDA_TRY(cudaMemcpyAsync(ctx->mob.ptr, W, N * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+                GKR_TRY(mobius_support(ctx, ctx->mob.as<Fr>(), k, &dep_mask, &max_deg, nullptr));
+            }
+        }
+
+        rs.assign(2 * k, hfr_zero());
+        HFr last_hash = hfr_zero();
+        const uint64_t ro = P->round_off[li];
+
+        // ---- phase 1: variables b ----
+        PhaseIO io{};
+        io.H = H; io.W = W; io.A = A; io.k = k; io.dep_mask = dep_mask;
+        io.challenges = rs.data();
+        io.msgs = &P->msgs[3 * ro]; io.msg_len = &P->msg_len[ro]; io.chal_out = &P->chal[ro];
+        GKR_TRY(run_phase(ctx, t, io, &last_hash));
+        // W(u): fold the last size-2 W table with r_k
+        ctx->begin_launch();
+        launch_fold(io.W_last, wu, to_dev(rs[k - 1]), 1, ctx->stream);
+        ctx->end_launch(KC_OTHER, 96.0);
+        GKR_TRY(ctx->check_launch("fold"));
+
+        // ---- phase 2: variables c ----
+        GKR_TRY(eq_table_dev(ctx, rs.data(), k, ctx->equ.as<Fr>()));
+        ctx->begin_launch();
+        launch_wiring_phase2(L.rowptr2, L.gate2, L.other2, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu, H, A, N, ctx->stream);
+        ctx->end_launch(KC_WIRING, 76.0 * L.n_gates + 64.0 * N);
+        GKR_TRY(ctx->check_launch("wiring_phase2"));
+        io.challenges = rs.data() + k;
+        io.msgs = &P->msgs[3 * (ro + k)]; io.msg_len = &P->msg_len[ro + k]; io.chal_out = &P->chal[ro + k];
+        GKR_TRY(run_phase(ctx, t, io, &last_hash));
+
+        // ---- q_i = W restricted to the line b* -> c* (poly.rs:469-500), static length 1 + max_deg ----
+        {
+            const Fr *cur = W;
+            uint64_t cnt = N;
+            for (uint32_t j = 0; j < k; ++j) {
+                Fr *nxt = (j & 1) ? ctx->lineB.as<Fr>() : ctx->lineA.as<Fr>();
+                const HFr g = hfr_sub(rs[k + j], rs[j]);
+                ctx->begin_launch();
+                launch_line_fold(cur, nxt, cnt, j, to_dev(rs[j]), to_dev(g), ctx->stream);
+                ctx->end_launch(KC_LINE, 32.0 * (double)(cnt * (j + 1)) + 32.0 * (double)(cnt / 2 * (j + 2)));
+                GKR_TRY(ctx->check_launch("line_fold"));
+                cur = nxt;
+                cnt /= 2;
+            }
+            qbuf.assign(k + 1, gkr_fr{});
+            GKR_TRY(download_table(ctx, cur, k + 1, qbuf.data()));     // ascending coefficients
+            const uint32_t len = max_deg + 1;
+            for (uint32_t d = len; d <= k; ++d) {
+                bool zero = true;
+                for (int l = 0; l < 8; ++l) zero &= qbuf[d].l[l] == 0;
+                if (!zero) {
+                    set_last_error("layer %u: q has degree above the static bound", li);
+                    return GKR_ERR_INTERNAL;
+                }
+            }
+            for (uint32_t d = 0; d < len; ++d) P->q[P->q_off[li] + d] = qbuf[len - 1 - d];
+            P->q_len[li] = len;
+        }
+
+        // ---- r*_i = hash of the last message (prover.rs:74-78); z_{i+1} = b* + r*(c* - b*) (poly.rs:538-551) ----
+        hfr_to_canonical(&P->r[li], last_hash);
+        std::vector<HFr> znext(k);
+        for (uint32_t j = 0; j < k; ++j) znext[j] = hfr_add(rs[j], hfr_mul(hfr_sub(rs[k + j], rs[j]), last_hash));
+        for (uint32_t j = 0; j < k; ++j) hfr_to_canonical(&P->z[P->z_off[li + 1] + j], znext[j]);
+        z.swap(znext);
+    }
+    // z_0 entries are zero already
+    P->finish();
+    *out = &P.release()->pub;
+    return GKR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone product sumcheck (BASELINE.json config 4)
+// ------------------------------------------------------------------------------------------------
+extern "C" int gkr_dev_table_synth(gkr_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t n, void **out) {
+    if (!ctx || !out || n == 0) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    Fr *p = nullptr;
+    cudaError_t e = cudaMalloc((void **)&p, n * sizeof(Fr));
+    if (e != cudaSuccess) {
+        set_last_error("cudaMalloc(%llu elements) failed: %s", (unsigned long long)n, cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? GKR_ERR_OOM : GKR_ERR_CUDA;
+    }
+    ctx->begin_launch();
+    launch_synth_values(seed, stream, 0, n, p, ctx->stream);
+    ctx->end_launch(KC_OTHER, 32.0 * n);
+    int rc = ctx->check_launch("synth_values");
+    if (rc == GKR_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = GKR_ERR_CUDA;
+    if (rc != GKR_OK) { cudaFree(p); return rc; }
+    *out = p;
+    return GKR_OK;
+}
+extern "C" int gkr_dev_table_upload(gkr_ctx *ctx, const gkr_fr *host, uint64_t n, void **out) {
+    if (!ctx || !out || !host || n == 0) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    Fr *p = nullptr;
+    GKR_CUDA_TRY(cudaMalloc((void **)&p, n * sizeof(Fr)));
+    int rc = upload_table(ctx, host, n, p);
+    if (rc != GKR_OK) { cudaFree(p); return rc; }
+    *out = p;
+    return GKR_OK;
+}
+extern "C" int gkr_dev_table_download(gkr_ctx *ctx, const void *dev, uint64_t n, gkr_fr *host_out) {
+    if (!ctx || !dev || !host_out) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    return download_table(ctx, static_cast<const Fr *>(dev), n, host_out);
+}
+extern "C" void gkr_dev_table_free(gkr_ctx *ctx, void *dev) {
+    if (!ctx || !dev) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(dev);
+}
+
+extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_vars, const void *const *tables,
+                                 int on_device, const gkr_transcript *t, gkr_fr *msgs, uint8_t *msg_len, gkr_fr *chal,
+                                 gkr_fr *final_vals) {
+    if (!ctx || !tables || !msgs || !msg_len || !chal) return GKR_ERR_INVALID;
+    if (n_tables != 3) {
+        set_last_error("gkr_sumcheck_prod: only products of 3 tables are implemented (got %u)", n_tables);
+        return GKR_ERR_INVALID;
+    }
+    if (n_vars < 2 || n_vars > 32) {
+        set_last_error("gkr_sumcheck_prod: n_vars=%u outside 2..32 (v=1 is broken in the reference, sumcheck.rs:167)", n_vars);
+        return GKR_ERR_INVALID;
+    }
+    GKR_TRY(ctx->bind());
+    const uint64_t N = (uint64_t)1 << n_vars;
+    const Fr *T[3];
+    Fr *owned[3] = {nullptr, nullptr, nullptr};
+    struct Cleanup {
+        Fr **p;
+        ~Cleanup() { for (int i = 0; i < 3; ++i) if (p[i]) cudaFree(p[i]); }
+    } cleanup{owned};
+    for (int i = 0; i < 3; ++i) {
+        if (!tables[i]) return GKR_ERR_INVALID;
+        if (on_device) {
+            T[i] = static_cast<const Fr *>(tables[i]);
+        } else {
+            GKR_CUDA_TRY(cudaMalloc((void **)&owned[i], N * sizeof(Fr)));
+            GKR_TRY(upload_table(ctx, static_cast<const gkr_fr *>(tables[i]), N, owned[i]));
+            T[i] = owned[i];
+        }
+    }
+    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 2, 2)));
+    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 4, 2)));
+    const HFr inv2 = hfr_inv(hfr_from_u64(2));
+    const Fr *Ac = T[0], *Bc = T[1], *Cc = T[2];
+    uint64_t n = N;
+    HFr r = hfr_zero();
+    for (uint32_t j = 0; j < n_vars; ++j) {
+        const uint32_t s = ctx->next_seq();
+        ctx->begin_launch();
+        if (j == 0) {
+            launch_prod3_round(false, Ac, Bc, Cc, nullptr, nullptr, nullptr, to_dev(r), n / 2, ctx->ws, ctx->slot_dev(s), s,
+                               ctx->stream);
+            ctx->end_launch(KC_PROD3, 96.0 * n);
+        } else {
+            DevBuf &dst = (j & 1) ? ctx->foldA : ctx->foldB;
+            const uint64_t half = n / 2;
+            Fr *Ao = dst.as<Fr>(), *Bo = Ao + half, *Co = Bo + half;
+            launch_prod3_round(true, Ac, Bc, Cc, Ao, Bo, Co, to_dev(r), half / 2, ctx->ws, ctx->slot_dev(s), s, ctx->stream);
+            ctx->end_launch(KC_PROD3_FUSED, 96.0 * n + 96.0 * half);
+            Ac = Ao; Bc = Bo; Cc = Co;
+            n = half;
+        }
+        GKR_TRY(ctx->check_launch("prod3_round"));
+        const HostSlot *slot;
+        GKR_TRY(ctx->wait_slot(s, &slot));
+        HFr g0, g1, gm, ginf;
+        if (!hfr_from_canonical(&g0, &slot->v[0]) || !hfr_from_canonical(&g1, &slot->v[1]) ||
+            !hfr_from_canonical(&gm, &slot->v[2]) || !hfr_from_canonical(&ginf, &slot->v[3]))
+            return GKR_ERR_INTERNAL;
+        // g(X) = c3 X^3 + c2 X^2 + c1 X + c0 from g(0), g(1), g(-1), c3
+        const HFr c0 = g0, c3 = ginf;
+        const HFr c2 = hfr_sub(hfr_mul(hfr_add(g1, gm), inv2), c0);
+        const HFr c1 = hfr_sub(hfr_mul(hfr_sub(g1, gm), inv2), c3);
+        const HFr desc[4] = {c3, c2, c1, c0};
+        uint32_t len;
+        HFr lo[3], hi[3];
+        const bool last = (j + 1 == n_vars);
+        if (!last) {
+            // add_poly drops zero-sum terms (poly.rs:324-327): leading zeros are stripped
+            uint32_t lead = 0;
+            while (lead < 3 && hfr_is_zero(desc[lead])) ++lead;
+            len = 4 - lead;
+        } else {
+            // final round: static length 1 + #tables that depend on the last variable (sumcheck.rs:206-207)
+            const Fr *ptrs[6] = {Ac, Ac + 1, Bc, Bc + 1, Cc, Cc + 1};
+            const uint32_t s2 = ctx->next_seq();
+            ctx->begin_launch();
+            launch_publish(ptrs, 6, ctx->slot_dev(s2), s2, ctx->stream);
+            ctx->end_launch(KC_OTHER, 192.0);
+            GKR_TRY(ctx->check_launch("publish"));
+            const HostSlot *fs;
+            GKR_TRY(ctx->wait_slot(s2, &fs));
+            for (int i = 0; i < 3; ++i)
+                if (!hfr_from_canonical(&lo[i], &fs->v[2 * i]) || !hfr_from_canonical(&hi[i], &fs->v[2 * i + 1]))
+                    return GKR_ERR_INTERNAL;
+            bool all_nonzero = true;
+            uint32_t deps = 0;
+            for (int i = 0; i < 3; ++i) {
+                bool dep = !hfr_eq(lo[i], hi[i]);
+                bool nonzero = !(hfr_is_zero(lo[i]) && hfr_is_zero(hi[i]));
+                if (!dep || !nonzero) {
+                    // ambiguous from the folded values alone: decide exactly on the original table
+                    const uint32_t s3 = ctx->next_seq();
+                    ctx->begin_launch();
+                    launch_table_flags(T[i], N, ctx->words + 4, ctx->slot_dev(s3), s3, ctx->stream);
+                    ctx->end_launch(KC_OTHER, 32.0 * N, 2);
+                    GKR_TRY(ctx->check_launch("table_flags"));
+                    const HostSlot *fl;
+                    GKR_TRY(ctx->wait_slot(s3, &fl));
+                    dep = fl->aux[0] != 0;
+                    nonzero = fl->aux[1] != 0;
+                }
+                deps += dep ? 1u : 0u;
+                all_nonzero = all_nonzero && nonzero;
+            }
+            len = all_nonzero ? 1 + deps : 1;
+        }
+        gkr_fr *m = &msgs[4 * (size_t)j];
+        std::memset(m, 0, 4 * sizeof(gkr_fr));
+        const HFr *src = desc + (4 - len);
+        for (uint32_t i = 0; i < len; ++i) hfr_to_canonical(&m[i], src[i]);
+        msg_len[j] = (uint8_t)len;
+        GKR_TRY(challenge_for(ctx, t, src, len, &r));
+        hfr_to_canonical(&chal[j], r);
+        if (last && final_vals)
+            for (int i = 0; i < 3; ++i) hfr_to_canonical(&final_vals[i], hfr_add(lo[i], hfr_mul(r, hfr_sub(hi[i], lo[i]))));
+    }
+    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return GKR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// building blocks
+// ------------------------------------------------------------------------------------------------
+namespace gkr {
+__global__ void k_binop(int op, const Fr *a, const Fr *b, Fr *out, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const Fr x = a[i], y = b[i];
+        out[i] = op == 0 ? fr_add(x, y) : op == 1 ? fr_sub(x, y) : fr_mul(x, y);
+    }
+}
+}  // namespace gkr
+
+extern "C" int gkr_fr_binop(gkr_ctx *ctx, int op, const gkr_fr *a, const gkr_fr *b, gkr_fr *out, uint64_t n) {
+    if (!ctx || !a || !b || !out || op < 0 || op > 2) return GKR_ERR_INVALID;
+    if (n == 0) return GKR_OK;
+    GKR_TRY(ctx->bind());
+    GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
+    DevBuf da, db;
+    struct Rel { DevBuf &a, &b; ~Rel() { a.release(); b.release(); } } rel{da, db};
+    GKR_TRY(da.ensure(n * sizeof(Fr)));
+    GKR_TRY(db.ensure(n * sizeof(Fr)));
+    GKR_TRY(upload_table(ctx, a, n, da.as<Fr>()));
+    GKR_TRY(upload_table(ctx, b, n, db.as<Fr>()));
+    ctx->begin_launch();
+    k_binop<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 1184), 256, 0, ctx->stream>>>(op, da.as<Fr>(), db.as<Fr>(), da.as<Fr>(), n);
+    ctx->end_launch(KC_OTHER, 96.0 * n);
+    GKR_TRY(ctx->check_launch("binop"));
+    return download_table(ctx, da.as<Fr>(), n, out);
+}
+
+extern "C" int gkr_eq_table(gkr_ctx *ctx, const gkr_fr *z, uint32_t k, gkr_fr *out) {
+    if (!ctx || (!z && k) || !out || k > 30) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    std::vector<HFr> zz(k);
+    for (uint32_t j = 0; j < k; ++j)
+        if (!hfr_from_canonical(&zz[j], &z[j])) return GKR_ERR_RANGE;
+    GKR_TRY(ctx->eqz.ensure(sizeof(Fr) << k));
+    GKR_TRY(eq_table_dev(ctx, zz.data(), k, ctx->eqz.as<Fr>()));
+    return download_table(ctx, ctx->eqz.as<Fr>(), (uint64_t)1 << k, out);
+}
+
+extern "C" int gkr_mobius(gkr_ctx *ctx, const gkr_fr *values, uint32_t k, gkr_fr *coef_out, uint32_t *dep_mask,
+                          uint32_t *max_deg) {
+    if (!ctx || !values || !coef_out || k > 30) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    const uint64_t n = (uint64_t)1 << k;
+    GKR_TRY(ctx->mob.ensure(sizeof(Fr) * n));
+    GKR_TRY(upload_table(ctx, values, n, ctx->mob.as<Fr>()));
+    uint32_t m = 0, d = 0;
+    GKR_TRY(mobius_support(ctx, ctx->mob.as<Fr>(), k, &m, &d, nullptr));
+    if (dep_mask) *dep_mask = m;
+    if (max_deg) *max_deg = d;
+    return download_table(ctx, ctx->mob.as<Fr>(), n, coef_out);
+}
+
+extern "C" int gkr_line_restrict(gkr_ctx *ctx, const gkr_fr *values, uint32_t k, const gkr_fr *b, const gkr_fr *c,
+                                 gkr_fr *coef_ascending) {
+    if (!ctx || !values || !b || !c || !coef_ascending || k == 0 || k > 30) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    const uint64_t n = (uint64_t)1 << k;
+    GKR_TRY(ctx->mob.ensure(sizeof(Fr) * n));
+    GKR_TRY(ctx->lineA.ensure(sizeof(Fr) * std::max<uint64_t>(n, 64)));
+    GKR_TRY(ctx->lineB.ensure(sizeof(Fr) * std::max<uint64_t>(n, 64)));
+    GKR_TRY(upload_table(ctx, values, n, ctx->mob.as<Fr>()));
+    const Fr *cur = ctx->mob.as<Fr>();
+    uint64_t cnt = n;
+    for (uint32_t j = 0; j < k; ++j) {
+        HFr bj, cj;
+        if (!hfr_from_canonical(&bj, &b[j]) || !hfr_from_canonical(&cj, &c[j])) return GKR_ERR_RANGE;
+        Fr *nxt = (j & 1) ? ctx->lineB.as<Fr>() : ctx->lineA.as<Fr>();
+        ctx->begin_launch();
+        launch_line_fold(cur, nxt, cnt, j, to_dev(bj), to_dev(hfr_sub(cj, bj)), ctx->stream);
+        ctx->end_launch(KC_LINE, 32.0 * (double)(cnt * (j + 1)) + 32.0 * (double)(cnt / 2 * (j + 2)));
+        GKR_TRY(ctx->check_launch("line_fold"));
+        cur = nxt;
+        cnt /= 2;
+    }
+    return download_table(ctx, cur, k + 1, coef_ascending);
+}

@@ -1,0 +1,134 @@
+// Host-side BN254 Fr (4 x 64-bit limbs, Montgomery form) for the serial parts of the prover that the
+// north star keeps on the CPU: the Fiat-Shamir transcript (MiMC7), challenge bookkeeping, message
+// assembly, z_{i+1} = l(b*, c*, r*) (rust/src/gkr/poly.rs:538-551) and the interpolation of the
+// degree-3 messages.  Bulk table arithmetic never runs here -- it has no CPU fallback.
+// The Montgomery representation (R = 2^256) is bit-identical to the device one (fr.cuh), so values
+// move between the two with a plain 32-byte copy.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+namespace gkr {
+
+struct HFr {
+    uint64_t l[4];
+};
+
+namespace hf {
+using u128 = unsigned __int128;
+constexpr uint64_t P[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+constexpr uint64_t RR[4] = {0x1bb8e645ae216da7ULL, 0x53fe3ab1e35c59e3ULL, 0x8c49833d53bb8085ULL, 0x0216d0b17f4e44a5ULL};
+constexpr uint64_t ONE[4] = {0xac96341c4ffffffbULL, 0x36fc76959f60cd29ULL, 0x666ea36f7879462eULL, 0x0e0a77c19a07df2fULL};
+constexpr uint64_t NINV = 0xc2e1f593efffffffULL;
+
+inline bool geq_p(const uint64_t a[4]) {
+    for (int i = 3; i >= 0; --i) {
+        if (a[i] != P[i]) return a[i] > P[i];
+    }
+    return true;
+}
+inline void sub_p(uint64_t a[4]) {
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+        u128 d = (u128)a[i] - P[i] - borrow;
+        a[i] = (uint64_t)d;
+        borrow = (uint64_t)(d >> 64) & 1;
+    }
+}
+}  // namespace hf
+
+inline HFr hfr_zero() { return HFr{{0, 0, 0, 0}}; }
+inline HFr hfr_one() { return HFr{{hf::ONE[0], hf::ONE[1], hf::ONE[2], hf::ONE[3]}}; }
+inline bool hfr_is_zero(const HFr &a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
+inline bool hfr_eq(const HFr &a, const HFr &b) { return std::memcmp(a.l, b.l, 32) == 0; }
+
+inline HFr hfr_add(const HFr &a, const HFr &b) {
+    HFr r;
+    uint64_t carry = 0;
+    for (int i = 0; i < 4; ++i) {
+        hf::u128 s = (hf::u128)a.l[i] + b.l[i] + carry;
+        r.l[i] = (uint64_t)s;
+        carry = (uint64_t)(s >> 64);
+    }
+    if (hf::geq_p(r.l)) hf::sub_p(r.l);
+    return r;
+}
+inline HFr hfr_sub(const HFr &a, const HFr &b) {
+    HFr r;
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+        hf::u128 d = (hf::u128)a.l[i] - b.l[i] - borrow;
+        r.l[i] = (uint64_t)d;
+        borrow = (uint64_t)(d >> 64) & 1;
+    }
+    if (borrow) {
+        uint64_t carry = 0;
+        for (int i = 0; i < 4; ++i) {
+            hf::u128 s = (hf::u128)r.l[i] + hf::P[i] + carry;
+            r.l[i] = (uint64_t)s;
+            carry = (uint64_t)(s >> 64);
+        }
+    }
+    return r;
+}
+inline HFr hfr_neg(const HFr &a) { return hfr_sub(hfr_zero(), a); }
+
+// Montgomery product: product scanning into an 8-limb buffer, then 4 reduction sweeps
+inline HFr hfr_mul(const HFr &a, const HFr &b) {
+    using hf::u128;
+    uint64_t t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 4; ++j) {
+            u128 cur = (u128)a.l[i] * b.l[j] + t[i + j] + carry;
+            t[i + j] = (uint64_t)cur;
+            carry = (uint64_t)(cur >> 64);
+        }
+        t[i + 4] = carry;
+    }
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t m = t[i] * hf::NINV;
+        uint64_t carry = 0;
+        for (int j = 0; j < 4; ++j) {
+            u128 cur = (u128)m * hf::P[j] + t[i + j] + carry;
+            t[i + j] = (uint64_t)cur;
+            carry = (uint64_t)(cur >> 64);
+        }
+        for (int j = i + 4; carry && j < 9; ++j) {
+            u128 cur = (u128)t[j] + carry;
+            t[j] = (uint64_t)cur;
+            carry = (uint64_t)(cur >> 64);
+        }
+    }
+    HFr r{{t[4], t[5], t[6], t[7]}};
+    if (t[8] || hf::geq_p(r.l)) hf::sub_p(r.l);
+    return r;
+}
+inline HFr hfr_sqr(const HFr &a) { return hfr_mul(a, a); }
+
+// canonical 32-byte little-endian value <-> Montgomery.  from_canonical returns false if value >= p.
+inline bool hfr_from_canonical(HFr *out, const void *bytes32) {
+    HFr c;
+    std::memcpy(c.l, bytes32, 32);
+    if (hf::geq_p(c.l)) return false;
+    *out = hfr_mul(c, HFr{{hf::RR[0], hf::RR[1], hf::RR[2], hf::RR[3]}});
+    return true;
+}
+inline void hfr_to_canonical(void *bytes32, const HFr &a) {
+    HFr c = hfr_mul(a, HFr{{1, 0, 0, 0}});
+    std::memcpy(bytes32, c.l, 32);
+}
+inline HFr hfr_from_u64(uint64_t v) { return hfr_mul(HFr{{v, 0, 0, 0}}, HFr{{hf::RR[0], hf::RR[1], hf::RR[2], hf::RR[3]}}); }
+
+// a^(p-2)
+inline HFr hfr_inv(const HFr &a) {
+    uint64_t e[4] = {hf::P[0] - 2, hf::P[1], hf::P[2], hf::P[3]};
+    HFr acc = hfr_one();
+    for (int i = 255; i >= 0; --i) {
+        acc = hfr_sqr(acc);
+        if ((e[i / 64] >> (i % 64)) & 1) acc = hfr_mul(acc, a);
+    }
+    return acc;
+}
+
+}  // namespace gkr

@@ -1,0 +1,576 @@
+// sm_100a kernels of the GKR prover hot path.  Integer pipe + HBM only: no tensor cores.
+// Tables are arrays of 32-byte Montgomery elements; every table access is a pair of 128-bit loads.
+// Reductions: per-thread accumulators -> warp shuffles -> shared-memory tree -> per-CTA partials ->
+// last CTA (ticket) sums the partials and publishes canonical values to a device-mapped host slot.
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+
+namespace gkr {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// ------------------------------------------------------------------------------------------------
+// 128-bit table access
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fr ld_fr(const Fr *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = __ldg(q), hi = __ldg(q + 1);
+    Fr r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+// coherent (L2) load for data written earlier in the same kernel by other CTAs
+__device__ __forceinline__ Fr ld_fr_cg(const Fr *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
+    Fr r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+__device__ __forceinline__ void st_fr(Fr *p, const Fr &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+// lo + r * (hi - lo)
+__device__ __forceinline__ Fr fold2(const Fr &lo, const Fr &hi, const Fr &r) {
+    return fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fr warp_sum(Fr v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], off);
+        v = fr_add(v, o);
+    }
+    return v;
+}
+
+// Sum K accumulators over the CTA; result valid in thread 0.
+template <int K>
+__device__ __forceinline__ void block_sum(Fr (&acc)[K], Fr (*smem)[kWarps]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        Fr w = warp_sum(acc[j]);
+        if (lane == 0) smem[j][warp] = w;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            Fr v = lane < kWarps ? smem[j][lane] : fr_zero();
+            acc[j] = warp_sum(v);
+        }
+    }
+    __syncthreads();
+}
+
+// Grid-wide sum of K accumulators; the last CTA to arrive publishes the canonical totals.
+template <int K>
+__device__ __forceinline__ void grid_sum_publish(Fr (&acc)[K], Fr *partials, unsigned int *counter,
+                                                 HostSlot *slot, uint32_t seq, uint32_t aux0) {
+    __shared__ Fr red[K][kWarps];
+    __shared__ bool is_last;
+    block_sum<K>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) st_fr(&partials[(size_t)blockIdx.x * K + j], acc[j]);
+        __threadfence();
+        unsigned int ticket = atomicAdd(counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = fr_zero();
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = fr_add(acc[j], ld_fr_cg(&partials[(size_t)b * K + j]));
+    }
+    block_sum<K>(acc, red);
+    if (threadIdx.x == 0) {
+        uint32_t nz = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            nz |= fr_is_zero(acc[j]) ? 0u : (1u << j);
+            st_fr(&slot->v[j], fr_from_mont(acc[j]));
+        }
+        slot->aux[0] = aux0;
+        slot->aux[1] = nz;
+        *counter = 0;
+        __threadfence_system();
+        slot->seq = seq;
+    }
+}
+
+static inline int grid_for(uint64_t work_items, int max_blocks) {
+    uint64_t b = (work_items + kThreads - 1) / kThreads;
+    if (b < 1) b = 1;
+    if (b > (uint64_t)max_blocks) b = (uint64_t)max_blocks;
+    return (int)b;
+}
+
+static int g_sm_count = 0;
+int device_sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+// grid for streaming (non-reducing) kernels: a multiple of the SM count, grid-stride loop inside
+static inline int stream_grid(uint64_t work_items) { return grid_for(work_items, device_sm_count() * 8); }
+
+// ------------------------------------------------------------------------------------------------
+// conversions / generators
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_to_mont(const Fr *__restrict__ in, Fr *__restrict__ out, uint64_t n,
+                                                      unsigned int *err_flag) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        Fr v = ld_fr(in + i);
+        if (!fr_is_canonical(v)) atomicOr(err_flag, 1u);
+        st_fr(out + i, fr_to_mont(v));
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_from_mont(const Fr *__restrict__ in, Fr *__restrict__ out, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        st_fr(out + i, fr_from_mont(ld_fr(in + i)));
+}
+void launch_to_mont(const Fr *in, Fr *out, uint64_t n, unsigned int *err_flag, cudaStream_t s) {
+    if (n == 0) return;
+    k_to_mont<<<stream_grid(n), kThreads, 0, s>>>(in, out, n, err_flag);
+}
+void launch_from_mont(const Fr *in, Fr *out, uint64_t n, cudaStream_t s) {
+    if (n == 0) return;
+    k_from_mont<<<stream_grid(n), kThreads, 0, s>>>(in, out, n);
+}
+
+// counter-based splitmix64 stream, same definition as the synthetic-workload generator of the bench
+// harness (gkr_b200/synthetic.py): word(seed,stream,idx,j) = mix(mix(mix(seed+G(stream+1))+G(idx+1))+G(j+1))
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(kThreads) k_synth_values(uint64_t seed, uint64_t stream_id, uint64_t first,
+                                                           uint64_t n, Fr *__restrict__ out) {
+    const uint64_t G = 0x9E3779B97F4A7C15ULL;
+    const uint64_t h0 = mix64(seed + G * (stream_id + 1));
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h1 = mix64(h0 + G * (first + i + 1));
+        Fr v;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint64_t w = mix64(h1 + G * (uint64_t)(j + 1));
+            if (j == 3) w &= 0x3FFFFFFFFFFFFFFFULL;
+            v.l[2 * j] = (uint32_t)w;
+            v.l[2 * j + 1] = (uint32_t)(w >> 32);
+        }
+        fr_cond_sub_p(v.l);                       // value < 2^254 < 2p
+        st_fr(out + i, fr_to_mont(v));
+    }
+}
+void launch_synth_values(uint64_t seed, uint64_t stream_id, uint64_t first, uint64_t n, Fr *out, cudaStream_t s) {
+    if (n == 0) return;
+    k_synth_values<<<stream_grid(n), kThreads, 0, s>>>(seed, stream_id, first, n, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward evaluation of one layer
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_layer_eval(const uint8_t *__restrict__ type,
+                                                         const uint32_t *__restrict__ left,
+                                                         const uint32_t *__restrict__ right, const Fr *__restrict__ in,
+                                                         Fr *__restrict__ out, uint32_t n_gates, uint64_t n_out) {
+    for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; g < n_out; g += (uint64_t)gridDim.x * blockDim.x) {
+        Fr v = fr_zero();
+        if (g < n_gates) {
+            Fr a = ld_fr(in + left[g]), b = ld_fr(in + right[g]);
+            v = type[g] ? fr_mul(a, b) : fr_add(a, b);
+        }
+        st_fr(out + g, v);
+    }
+}
+void launch_layer_eval(const uint8_t *type, const uint32_t *left, const uint32_t *right, const Fr *in, Fr *out,
+                       uint32_t n_gates, uint64_t n_out, cudaStream_t s) {
+    k_layer_eval<<<stream_grid(n_out), kThreads, 0, s>>>(type, left, right, in, out, n_gates, n_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// eq tables: split eq(z, idx) = eq(z_hi, idx >> k_lo) * eq(z_lo, idx & mask)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_eq_small(FrVec z, uint32_t first_var, uint32_t nv, Fr *__restrict__ out) {
+    const uint32_t n = 1u << nv;
+    const Fr one = fr_one();
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        Fr acc = one;
+        for (uint32_t j = 0; j < nv; ++j) {
+            const Fr zj = z.v[first_var + j];
+            const bool bit = (idx >> (nv - 1 - j)) & 1u;
+            acc = fr_mul(acc, bit ? zj : fr_sub(one, zj));
+        }
+        st_fr(out + idx, acc);
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_eq_expand(const Fr *__restrict__ hi, const Fr *__restrict__ lo,
+                                                        Fr *__restrict__ out, uint32_t k_lo, uint64_t n) {
+    const uint64_t mask = ((uint64_t)1 << k_lo) - 1;
+    for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x)
+        st_fr(out + idx, fr_mul(ld_fr(hi + (idx >> k_lo)), ld_fr(lo + (idx & mask))));
+}
+void launch_eq_table(const FrVec &z, uint32_t k, Fr *out, Fr *scratch, cudaStream_t s) {
+    if (k <= 8) {
+        k_eq_small<<<grid_for(1u << k, 64), kThreads, 0, s>>>(z, 0, k, out);
+        return;
+    }
+    const uint32_t k_hi = k / 2, k_lo = k - k_hi;
+    Fr *hi = scratch, *lo = scratch + ((size_t)1 << k_hi);
+    k_eq_small<<<grid_for(1u << k_hi, 148), kThreads, 0, s>>>(z, 0, k_hi, hi);
+    k_eq_small<<<grid_for(1u << k_lo, 148), kThreads, 0, s>>>(z, k_hi, k_lo, lo);
+    const uint64_t n = (uint64_t)1 << k;
+    k_eq_expand<<<stream_grid(n), kThreads, 0, s>>>(hi, lo, out, k_lo, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wiring-predicate sums, one thread per row of the CSR (deterministic, no atomics)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_wiring_phase1(const uint32_t *__restrict__ rowptr,
+                                                            const uint32_t *__restrict__ csr_gate,
+                                                            const uint32_t *__restrict__ csr_other,
+                                                            const Fr *__restrict__ eqz, const Fr *__restrict__ W,
+                                                            Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n) {
+    for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < n; b += (uint64_t)gridDim.x * blockDim.x) {
+        Fr h = fr_zero(), a = fr_zero();
+        const uint32_t e0 = rowptr[b], e1 = rowptr[b + 1];
+        for (uint32_t e = e0; e < e1; ++e) {
+            const uint32_t g = csr_gate[e], o = csr_other[e];
+            const Fr ez = ld_fr(eqz + g);
+            const Fr ew = fr_mul(ez, ld_fr(W + (o & 0x7fffffffu)));
+            if (o >> 31) {
+                h = fr_add(h, ew);                 // mult gate: eqz[g] * W[r_g] multiplies W(b)
+            } else {
+                h = fr_add(h, ez);                 // add gate: eqz[g] multiplies W(b)
+                a = fr_add(a, ew);                 //           eqz[g] * W[r_g] is the constant part
+            }
+        }
+        st_fr(H + b, h);
+        st_fr(A + b, a);
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_wiring_phase2(const uint32_t *__restrict__ rowptr,
+                                                            const uint32_t *__restrict__ csr_gate,
+                                                            const uint32_t *__restrict__ csr_other,
+                                                            const Fr *__restrict__ eqz, const Fr *__restrict__ equ,
+                                                            const Fr *__restrict__ wu_ptr, Fr *__restrict__ H,
+                                                            Fr *__restrict__ A, uint64_t n) {
+    const Fr wu = ld_fr(wu_ptr);
+    for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
+        Fr sa = fr_zero(), sm = fr_zero();
+        const uint32_t e0 = rowptr[c], e1 = rowptr[c + 1];
+        for (uint32_t e = e0; e < e1; ++e) {
+            const uint32_t g = csr_gate[e], o = csr_other[e];
+            const Fr t = fr_mul(ld_fr(eqz + g), ld_fr(equ + (o & 0x7fffffffu)));
+            if (o >> 31) sm = fr_add(sm, t); else sa = fr_add(sa, t);
+        }
+        // H2[c] = S_add + W(u) S_mul ;  A2[c] = W(u) S_add
+        Fr h = sa, a = fr_zero();
+        if (e1 > e0) {
+            h = fr_add(sa, fr_mul(wu, sm));
+            a = fr_mul(wu, sa);
+        }
+        st_fr(H + c, h);
+        st_fr(A + c, a);
+    }
+}
+void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, const Fr *eqz,
+                          const Fr *W, Fr *H, Fr *A, uint64_t n, cudaStream_t s) {
+    k_wiring_phase1<<<stream_grid(n), kThreads, 0, s>>>(rowptr, csr_gate, csr_other, eqz, W, H, A, n);
+}
+void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, const Fr *eqz,
+                          const Fr *equ, const Fr *wu, Fr *H, Fr *A, uint64_t n, cudaStream_t s) {
+    k_wiring_phase2<<<stream_grid(n), kThreads, 0, s>>>(rowptr, csr_gate, csr_other, eqz, equ, wu, H, A, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GKR sumcheck round, degree 2:  g(X) = sum_i (H_lo + X dH)(W_lo + X dW) + (A_lo + X dA)
+//   X0 = g(0) = sum H_lo W_lo + A_lo ;  X1 = g(1) = sum H_hi W_hi + A_hi ;  X2 = sum dH dW
+//   message = [X2, X1 - X0 - X2, X0]  (rust/src/gkr/sumcheck.rs:80-85,125-130 build the same coefficients)
+// FOLD: fold-by-r of the previous round fused with this round's evaluation (each table crosses HBM once)
+// ------------------------------------------------------------------------------------------------
+template <bool FOLD>
+__global__ void __launch_bounds__(kThreads) k_gkr_round(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+                                                        const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
+                                                        Fr *__restrict__ Wout, Fr *__restrict__ Aout, Fr r,
+                                                        uint64_t q, Fr *partials, unsigned int *counter,
+                                                        HostSlot *slot, uint32_t seq) {
+    Fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < q; i += (uint64_t)gridDim.x * blockDim.x) {
+        Fr wl, wh, hl, hh, al, ah;
+        if (FOLD) {
+            wl = fold2(ld_fr(Win + i), ld_fr(Win + i + 2 * q), r);
+            wh = fold2(ld_fr(Win + i + q), ld_fr(Win + i + 3 * q), r);
+            st_fr(Wout + i, wl);
+            st_fr(Wout + i + q, wh);
+            hl = fold2(ld_fr(Hin + i), ld_fr(Hin + i + 2 * q), r);
+            hh = fold2(ld_fr(Hin + i + q), ld_fr(Hin + i + 3 * q), r);
+            st_fr(Hout + i, hl);
+            st_fr(Hout + i + q, hh);
+            al = fold2(ld_fr(Ain + i), ld_fr(Ain + i + 2 * q), r);
+            ah = fold2(ld_fr(Ain + i + q), ld_fr(Ain + i + 3 * q), r);
+            st_fr(Aout + i, al);
+            st_fr(Aout + i + q, ah);
+        } else {
+            wl = ld_fr(Win + i); wh = ld_fr(Win + i + q);
+            hl = ld_fr(Hin + i); hh = ld_fr(Hin + i + q);
+            al = ld_fr(Ain + i); ah = ld_fr(Ain + i + q);
+        }
+        acc[0] = fr_add(acc[0], fr_add(fr_mul(hl, wl), al));
+        acc[1] = fr_add(acc[1], fr_add(fr_mul(hh, wh), ah));
+        acc[2] = fr_add(acc[2], fr_mul(fr_sub(hh, hl), fr_sub(wh, wl)));
+    }
+    grid_sum_publish<3>(acc, partials, counter, slot, seq, 0u);
+}
+void launch_gkr_round(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const Fr &r,
+                      uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    const int grid = grid_for(pairs, ws.max_blocks);
+    if (fold)
+        k_gkr_round<true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
+    else
+        k_gkr_round<false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
+}
+
+// ------------------------------------------------------------------------------------------------
+// product-of-three sumcheck round, degree 3 (generic prove_sumcheck, rust/src/gkr/sumcheck.rs:158-214):
+// publishes g(0), g(1), g(-1) and g(inf) = X^3 coefficient; the host interpolates the coefficients.
+// ------------------------------------------------------------------------------------------------
+template <bool FOLD>
+__global__ void __launch_bounds__(kThreads) k_prod3_round(const Fr *__restrict__ Ain, const Fr *__restrict__ Bin,
+                                                          const Fr *__restrict__ Cin, Fr *__restrict__ Aout,
+                                                          Fr *__restrict__ Bout, Fr *__restrict__ Cout, Fr r,
+                                                          uint64_t q, Fr *partials, unsigned int *counter,
+                                                          HostSlot *slot, uint32_t seq) {
+    Fr acc[4] = {fr_zero(), fr_zero(), fr_zero(), fr_zero()};
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < q; i += (uint64_t)gridDim.x * blockDim.x) {
+        Fr a0, a1, b0, b1, c0, c1;
+        if (FOLD) {
+            a0 = fold2(ld_fr(Ain + i), ld_fr(Ain + i + 2 * q), r);
+            a1 = fold2(ld_fr(Ain + i + q), ld_fr(Ain + i + 3 * q), r);
+            st_fr(Aout + i, a0);
+            st_fr(Aout + i + q, a1);
+            b0 = fold2(ld_fr(Bin + i), ld_fr(Bin + i + 2 * q), r);
+            b1 = fold2(ld_fr(Bin + i + q), ld_fr(Bin + i + 3 * q), r);
+            st_fr(Bout + i, b0);
+            st_fr(Bout + i + q, b1);
+            c0 = fold2(ld_fr(Cin + i), ld_fr(Cin + i + 2 * q), r);
+            c1 = fold2(ld_fr(Cin + i + q), ld_fr(Cin + i + 3 * q), r);
+            st_fr(Cout + i, c0);
+            st_fr(Cout + i + q, c1);
+        } else {
+            a0 = ld_fr(Ain + i); a1 = ld_fr(Ain + i + q);
+            b0 = ld_fr(Bin + i); b1 = ld_fr(Bin + i + q);
+            c0 = ld_fr(Cin + i); c1 = ld_fr(Cin + i + q);
+        }
+        acc[0] = fr_add(acc[0], fr_mul(fr_mul(a0, b0), c0));
+        acc[1] = fr_add(acc[1], fr_mul(fr_mul(a1, b1), c1));
+        const Fr da = fr_sub(a1, a0), db = fr_sub(b1, b0), dc = fr_sub(c1, c0);
+        acc[3] = fr_add(acc[3], fr_mul(fr_mul(da, db), dc));
+        // value at X = -1 : lo - d
+        acc[2] = fr_add(acc[2], fr_mul(fr_mul(fr_sub(a0, da), fr_sub(b0, db)), fr_sub(c0, dc)));
+    }
+    grid_sum_publish<4>(acc, partials, counter, slot, seq, 0u);
+}
+void launch_prod3_round(bool fold, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const Fr &r,
+                        uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    const int grid = grid_for(pairs, ws.max_blocks);
+    if (fold)
+        k_prod3_round<true><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq);
+    else
+        k_prod3_round<false><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq);
+}
+
+__global__ void __launch_bounds__(kThreads) k_fold(const Fr *__restrict__ in, Fr *__restrict__ out, Fr r, uint64_t half) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < half; i += (uint64_t)gridDim.x * blockDim.x)
+        st_fr(out + i, fold2(ld_fr(in + i), ld_fr(in + i + half), r));
+}
+void launch_fold(const Fr *in, Fr *out, const Fr &r, uint64_t half, cudaStream_t s) {
+    k_fold<<<stream_grid(half), kThreads, 0, s>>>(in, out, r, half);
+}
+
+struct Ptrs6 { const Fr *p[6]; };
+__global__ void k_publish(Ptrs6 ptrs, int count, HostSlot *slot, uint32_t seq) {
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < count; ++j) st_fr(&slot->v[j], fr_from_mont(ld_fr_cg(ptrs.p[j])));
+        __threadfence_system();
+        slot->seq = seq;
+    }
+}
+void launch_publish(const Fr *const *ptrs6, int count, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    Ptrs6 p;
+    for (int j = 0; j < 6; ++j) p.p[j] = j < count ? ptrs6[j] : nullptr;
+    k_publish<<<1, 32, 0, s>>>(p, count, slot, seq);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MLE shape
+// ------------------------------------------------------------------------------------------------
+// sum_idx (-1)^popcount(idx) W[idx] = +- coefficient of x_1...x_k.  Non-zero => W depends on every
+// variable and its max total degree is k, which fixes every static length of Appendix B.
+__global__ void __launch_bounds__(kThreads) k_alt_sum(const Fr *__restrict__ W, uint64_t n, Fr *partials,
+                                                      unsigned int *counter, HostSlot *slot, uint32_t seq) {
+    Fr acc[1] = {fr_zero()};
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const Fr v = ld_fr(W + i);
+        acc[0] = (__popcll(i) & 1) ? fr_sub(acc[0], v) : fr_add(acc[0], v);
+    }
+    grid_sum_publish<1>(acc, partials, counter, slot, seq, 0u);
+}
+void launch_alt_sum(const Fr *W, uint64_t n, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    k_alt_sum<<<grid_for(n, ws.max_blocks), kThreads, 0, s>>>(W, n, ws.partials, ws.counter, slot, seq);
+}
+
+// Moebius transform, low stages: a CTA owns 2^T contiguous entries in shared memory (limb-planar)
+constexpr int kMobTile = 10;
+__global__ void __launch_bounds__(kThreads) k_mobius_low(Fr *__restrict__ table, uint32_t stages) {
+    extern __shared__ uint32_t sm[];                 // [8][1 << stages]
+    const uint32_t tile = 1u << stages;
+    Fr *base = table + (size_t)blockIdx.x * tile;
+    for (uint32_t i = threadIdx.x; i < tile; i += blockDim.x) {
+        Fr v = ld_fr_cg(base + i);
+#pragma unroll
+        for (int l = 0; l < 8; ++l) sm[l * tile + i] = v.l[l];
+    }
+    __syncthreads();
+    for (uint32_t s = 0; s < stages; ++s) {
+        const uint32_t bit = 1u << s;
+        for (uint32_t t = threadIdx.x; t < tile / 2; t += blockDim.x) {
+            const uint32_t lo = ((t >> s) << (s + 1)) | (t & (bit - 1)), hi = lo | bit;
+            Fr a, b;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) { a.l[l] = sm[l * tile + lo]; b.l[l] = sm[l * tile + hi]; }
+            b = fr_sub(b, a);
+#pragma unroll
+            for (int l = 0; l < 8; ++l) sm[l * tile + hi] = b.l[l];
+        }
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < tile; i += blockDim.x) {
+        Fr v;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) v.l[l] = sm[l * tile + i];
+        st_fr(base + i, v);
+    }
+}
+// one high stage: c[i | bit] -= c[i] for i with the bit clear
+__global__ void __launch_bounds__(kThreads) k_mobius_stage(Fr *__restrict__ table, uint32_t s, uint64_t half) {
+    const uint64_t bit = (uint64_t)1 << s;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < half; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t lo = ((t >> s) << (s + 1)) | (t & (bit - 1)), hi = lo | bit;
+        st_fr(table + hi, fr_sub(ld_fr_cg(table + hi), ld_fr_cg(table + lo)));
+    }
+}
+void launch_mobius(Fr *table, uint32_t k, cudaStream_t s) {
+    if (k == 0) return;
+    const uint32_t low = k < (uint32_t)kMobTile ? k : (uint32_t)kMobTile;
+    const size_t smem = (size_t)32 << low;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_mobius_low, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMobTile);
+        attr_set = true;
+    }
+    k_mobius_low<<<(unsigned)(((uint64_t)1 << k) >> low), kThreads, smem, s>>>(table, low);
+    const uint64_t half = ((uint64_t)1 << k) / 2;
+    for (uint32_t st = low; st < k; ++st) k_mobius_stage<<<stream_grid(half), kThreads, 0, s>>>(table, st, half);
+}
+
+// support of the non-zero coefficients: OR of indices, max popcount, any non-zero
+__global__ void __launch_bounds__(kThreads) k_coef_support(const Fr *__restrict__ coef, uint64_t n, unsigned int *words) {
+    unsigned int m = 0, d = 0, any = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (!fr_is_zero(ld_fr(coef + i))) {
+            m |= (unsigned int)i;
+            d = max(d, (unsigned int)__popcll(i));
+            any = 1;
+        }
+    }
+    m = __reduce_or_sync(0xffffffffu, m);
+    d = __reduce_max_sync(0xffffffffu, d);
+    any = __reduce_or_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0 && any) {
+        atomicOr(&words[0], m);
+        atomicMax(&words[1], d);
+        atomicOr(&words[2], 1u);
+    }
+}
+// dependence on the last variable / any non-zero entry
+__global__ void __launch_bounds__(kThreads) k_table_flags(const Fr *__restrict__ T, uint64_t n, unsigned int *words) {
+    unsigned int dep = 0, any = 0;
+    const uint64_t pairs = n / 2;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+        const Fr a = ld_fr(T + 2 * i), b = ld_fr(T + 2 * i + 1);
+        dep |= fr_eq(a, b) ? 0u : 1u;
+        any |= (fr_is_zero(a) && fr_is_zero(b)) ? 0u : 1u;
+    }
+    dep = __reduce_or_sync(0xffffffffu, dep);
+    any = __reduce_or_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0) {
+        if (dep) atomicOr(&words[0], 1u);
+        if (any) atomicOr(&words[1], 1u);
+    }
+}
+__global__ void k_publish_words(unsigned int *words, HostSlot *slot, uint32_t seq) {
+    if (threadIdx.x == 0) {
+        slot->aux[0] = words[0];
+        slot->aux[1] = words[1];
+        slot->aux[2] = words[2];
+        words[0] = words[1] = words[2] = 0;
+        __threadfence_system();
+        slot->seq = seq;
+    }
+}
+void launch_coef_support(const Fr *coef, uint64_t n, unsigned int *words, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    k_coef_support<<<stream_grid(n), kThreads, 0, s>>>(coef, n, words);
+    k_publish_words<<<1, 32, 0, s>>>(words, slot, seq);
+}
+void launch_table_flags(const Fr *T, uint64_t n, unsigned int *words, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    k_table_flags<<<stream_grid(n / 2), kThreads, 0, s>>>(T, n, words);
+    k_publish_words<<<1, 32, 0, s>>>(words, slot, seq);
+}
+
+// ------------------------------------------------------------------------------------------------
+// line restriction: entries are polynomials in t (coefficient-major: coefficient d of entry e at
+// cur[d * cnt + e]); folding variable x_j := b_j + g_j t raises the degree by one:
+//   new(t) = lo(t) + (b + g t)(hi(t) - lo(t))
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_line_fold(const Fr *__restrict__ cur, Fr *__restrict__ nxt, uint64_t cnt,
+                                                        uint32_t deg, Fr b, Fr g) {
+    const uint64_t half = cnt / 2;
+    for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < half; e += (uint64_t)gridDim.x * blockDim.x) {
+        Fr carry = fr_zero();
+        for (uint32_t d = 0; d <= deg; ++d) {
+            const Fr lo = ld_fr(cur + (size_t)d * cnt + e), hi = ld_fr(cur + (size_t)d * cnt + e + half);
+            const Fr df = fr_sub(hi, lo);
+            st_fr(nxt + (size_t)d * half + e, fr_add(fr_add(lo, fr_mul(b, df)), carry));
+            carry = fr_mul(g, df);
+        }
+        st_fr(nxt + (size_t)(deg + 1) * half + e, carry);
+    }
+}
+void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const Fr &b, const Fr &g, cudaStream_t s) {
+    k_line_fold<<<stream_grid(cnt / 2), kThreads, 0, s>>>(cur, nxt, cnt, deg, b, g);
+}
+
+}  // namespace gkr

@@ -1,0 +1,88 @@
+// Host-callable launchers for the sm_100a kernels of the GKR prover hot path (kernels.cu).
+// Every launcher enqueues on the given stream and returns immediately; results that the host
+// transcript needs are published into a pinned, device-mapped HostSlot that the host spins on.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fr.cuh"
+
+namespace gkr {
+
+// One published result.  The last CTA of a reducing kernel writes the values (canonical form),
+// then `seq` with a system-scope fence in between; the host polls `seq`.
+struct alignas(256) HostSlot {
+    Fr v[6];
+    uint32_t aux[15];
+    volatile uint32_t seq;
+};
+static_assert(sizeof(HostSlot) == 256, "HostSlot layout");
+
+struct FrVec {            // up to 32 field elements passed by value as a kernel parameter
+    Fr v[32];
+};
+
+// Reduction workspace shared by all reducing kernels of one context (stream-ordered reuse).
+struct ReduceWs {
+    Fr *partials;         // [max_blocks * 6]
+    unsigned int *counter;
+    int max_blocks;
+};
+
+// ---- conversions / generators ------------------------------------------------------------------
+void launch_to_mont(const Fr *in, Fr *out, uint64_t n, unsigned int *err_flag, cudaStream_t s);
+void launch_from_mont(const Fr *in, Fr *out, uint64_t n, cudaStream_t s);
+void launch_synth_values(uint64_t seed, uint64_t stream_id, uint64_t first, uint64_t n, Fr *out_mont, cudaStream_t s);
+
+// ---- circuit evaluation (rust/src/convert.rs:812-830) -----------------------------------------
+void launch_layer_eval(const uint8_t *type, const uint32_t *left, const uint32_t *right, const Fr *in, Fr *out,
+                       uint32_t n_gates, uint64_t n_out, cudaStream_t s);
+
+// ---- eq tables (partial_eval_binary_form over z, rust/src/gkr/poly.rs:43-62) ---------------------
+// out[idx] = prod_j (bit_j(idx) ? z_j : 1 - z_j), j = 1..k MSB-first.  scratch: >= 2 * 2^ceil(k/2) Fr.
+void launch_eq_table(const FrVec &z_mont, uint32_t k, Fr *out, Fr *scratch, cudaStream_t s);
+
+// ---- wiring-predicate sums (implicit in rust/src/gkr/sumcheck.rs:49-78,97-124) ------------------
+// CSR by left operand: row b lists (gate, right|type<<31)
+void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
+                          const Fr *eqz, const Fr *W, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
+// CSR by right operand: row c lists (gate, left|type<<31); wu = W(u) on device
+void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
+                          const Fr *eqz, const Fr *equ, const Fr *wu, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
+
+// ---- sumcheck rounds --------------------------------------------------------------------------
+// GKR round (degree 2) on (H, W, A).  Publishes X0 = g(0), X1 = g(1), X2 = coefficient of X^2.
+// fold == false: tables have 2*pairs entries, no output tables.
+// fold == true : tables have 4*pairs entries; first folds them with r (writing 2*pairs entries to
+//                Hout/Wout/Aout), then evaluates the round polynomial of the folded tables -- one pass.
+void launch_gkr_round(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
+                      const Fr &r_mont, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
+                      cudaStream_t s);
+// product-of-3 round (degree 3).  Publishes g(0), g(1), g(-1), g(inf) (= X^3 coefficient).
+void launch_prod3_round(bool fold, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
+                        const Fr &r_mont, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
+                        cudaStream_t s);
+// plain fold out[i] = in[i] + r (in[i+half] - in[i])
+void launch_fold(const Fr *in, Fr *out, const Fr &r_mont, uint64_t half, cudaStream_t s);
+// publish up to 6 device values (Montgomery -> canonical) to a slot
+void launch_publish(const Fr *const *ptrs6, int count, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
+
+// ---- MLE shape: Moebius transform (get_multi_ext, rust/src/gkr/poly.rs:502-536) -------------------
+// alternating sum = top monomial coefficient (up to sign); aux[0] = 1 if it is non-zero
+void launch_alt_sum(const Fr *W, uint64_t n, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
+void launch_mobius(Fr *table, uint32_t k, cudaStream_t s);            // in place, values -> coefficients
+// aux[0] = OR of indices with non-zero coefficient, aux[1] = max popcount among them, aux[2] = any non-zero
+void launch_coef_support(const Fr *coef, uint64_t n, unsigned int *dev_words3, HostSlot *slot_dev, uint32_t seq,
+                         cudaStream_t s);
+// aux[0] = 1 if some T[2i] != T[2i+1] (dependence on the last variable), aux[1] = 1 if any entry non-zero
+void launch_table_flags(const Fr *T, uint64_t n, unsigned int *dev_words3, HostSlot *slot_dev, uint32_t seq,
+                        cudaStream_t s);
+
+// ---- line restriction (reduce_multiple_polynomial, rust/src/gkr/poly.rs:469-500) -----------------
+// one level: cnt entries with (deg+1) coefficients each (coefficient-major) -> cnt/2 entries with deg+2
+void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const Fr &b_mont, const Fr &g_mont,
+                      cudaStream_t s);
+
+int device_sm_count();
+
+}  // namespace gkr

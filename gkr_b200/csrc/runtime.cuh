@@ -1,0 +1,139 @@
+// Per-context runtime of the prover: one device, one stream, a ring of pinned device-mapped result
+// slots the host spins on, grow-only device workspaces, launch accounting and optional per-kernel
+// CUDA-event profiling.  Internal to the library (the public surface is include/gkr_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/gkr_b200.h"
+#include "host_field.hpp"
+#include "kernels.cuh"
+
+namespace gkr {
+
+void set_last_error(const char *fmt, ...);
+
+#define GKR_CUDA_TRY(expr)                                                                        \
+    do {                                                                                          \
+        cudaError_t err__ = (expr);                                                               \
+        if (err__ != cudaSuccess) {                                                               \
+            gkr::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+            return GKR_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define GKR_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != GKR_OK) return rc__; \
+    } while (0)
+
+enum KernelClass { KC_ROUND = 0, KC_ROUND_FUSED, KC_PROD3, KC_PROD3_FUSED, KC_WIRING, KC_EQ, KC_MOBIUS, KC_LINE, KC_OTHER };
+
+// grow-only device buffer
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return GKR_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e != cudaSuccess) {
+            set_last_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            cudaGetLastError();
+            return e == cudaErrorMemoryAllocation ? GKR_ERR_OOM : GKR_ERR_CUDA;
+        }
+        cap = bytes;
+        return GKR_OK;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const { return static_cast<T *>(ptr); }
+};
+
+inline double now_seconds() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+inline Fr to_dev(const HFr &h) {      // identical Montgomery representation: plain copy
+    Fr f;
+    std::memcpy(f.l, h.l, 32);
+    return f;
+}
+inline HFr to_host(const Fr &f) {
+    HFr h;
+    std::memcpy(h.l, f.l, 32);
+    return h;
+}
+
+}  // namespace gkr
+
+struct gkr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    static constexpr int kSlots = 64;
+    gkr::HostSlot *slots_host = nullptr;   // pinned + mapped
+    gkr::HostSlot *slots_dev = nullptr;
+    uint32_t seq = 0;
+    gkr::ReduceWs ws{};
+    unsigned int *words = nullptr;         // [8] device words: [0] range-error flag, [4..6] support/flags scratch
+    gkr_fr *pinned = nullptr;              // small pinned staging (q coefficients, flags)
+    size_t pinned_elems = 0;
+
+    // workspaces
+    gkr::DevBuf eqz, equ, eq_scratch, H, A, foldA, foldB, lineA, lineB, mob, misc, stage;
+
+    // accounting
+    gkr_stats stats{};
+    bool profiling = false;
+    gkr_profile prof{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    int bind() const {
+        cudaError_t e = cudaSetDevice(device);
+        if (e != cudaSuccess) {
+            gkr::set_last_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
+            return GKR_ERR_CUDA;
+        }
+        return GKR_OK;
+    }
+    // bracket one launch for accounting / profiling
+    void begin_launch() {
+        if (profiling) cudaEventRecord(ev0, stream);
+    }
+    void end_launch(gkr::KernelClass kc, double algo_bytes, int n_kernels = 1) {
+        stats.kernel_launches += (uint64_t)n_kernels;
+        if (profiling) {
+            cudaEventRecord(ev1, stream);
+            cudaEventSynchronize(ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev0, ev1);
+            prof.launches[kc] += (uint64_t)n_kernels;
+            prof.ms[kc] += ms;
+            prof.algo_bytes[kc] += algo_bytes;
+        }
+    }
+    uint32_t next_seq() { return ++seq; }
+    gkr::HostSlot *slot_dev(uint32_t s) const { return slots_dev + (s % kSlots); }
+    // spin until the slot for sequence number s has been published
+    int wait_slot(uint32_t s, const gkr::HostSlot **out);
+    int check_launch(const char *what) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            gkr::set_last_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+            return GKR_ERR_CUDA;
+        }
+        return GKR_OK;
+    }
+};

@@ -1,0 +1,170 @@
+/*
+ * gkr_b200 -- C ABI of the B200-native GKR prover hot path.
+ *
+ * Drop-in boundary for the reference's prover seam
+ *     prover::prove(&GKRCircuit<S>, &Input<S>) -> Proof<S>         rust/src/gkr/prover.rs:6-9
+ * called per sub-circuit from rayon workers at rust/src/aggregator.rs:352-355 and :413-416.
+ * The reference has no FFI; its seam passes sparse term lists (rust/src/gkr.rs:21-56) whose
+ * construction is a 3^k blow-up (get_multi_ext, rust/src/gkr/poly.rs:502-536).  The ABI therefore
+ * binds one step earlier, where the reference still holds dense data:
+ *     IntermediateLayer{node_types, operand_index}                  rust/src/convert.rs:103-106, consumed :704-777
+ *     w_values (dense layer values)                                 rust/src/convert.rs:793-831
+ * and returns every field of Proof<S> (rust/src/gkr.rs:8-19).  INTEGRATION.md shows the Rust
+ * (cc + bindgen) side a maintainer would add.
+ *
+ * Conventions
+ *  - gkr_fr is the canonical value, 32 bytes little-endian == Fr::to_repr() (sumcheck.rs:14-21,
+ *    file_utils.rs:20-24).  Montgomery form never crosses the boundary.  Inputs >= p are an error.
+ *  - Gate g of layer i is output index g; indices are MSB-first bit strings (convert.rs:721-728):
+ *    variable 1 of a layer is the most significant index bit.
+ *  - Every function returns 0 on success or a negative gkr_status; gkr_last_error() gives a
+ *    thread-local message.  Nothing unwinds or aborts across the boundary.
+ *  - There is NO CPU fallback: without a CUDA device every entry point that computes fails with
+ *    GKR_ERR_CUDA.
+ *  - A gkr_ctx is bound to one device + one stream and must not be used from two threads at once;
+ *    distinct contexts are fully concurrent (the reference proves sub-circuits concurrently,
+ *    aggregator.rs:353,414).  A gkr_circuit is immutable after creation.
+ */
+#ifndef GKR_B200_H
+#define GKR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint32_t l[8]; } gkr_fr;
+
+typedef enum {
+    GKR_OK = 0,
+    GKR_ERR_INVALID = -1,     /* bad argument / unsupported shape (e.g. k_in = 0: sumcheck.rs:49 underflows) */
+    GKR_ERR_CUDA = -2,        /* CUDA runtime error or no device */
+    GKR_ERR_OOM = -3,
+    GKR_ERR_RANGE = -4,       /* a field element >= p was supplied */
+    GKR_ERR_TRANSCRIPT = -5,  /* user transcript callback failed */
+    GKR_ERR_COMM = -6,        /* multi-GPU exchange failed */
+    GKR_ERR_INTERNAL = -7
+} gkr_status;
+
+typedef struct gkr_ctx gkr_ctx;
+typedef struct gkr_circuit gkr_circuit;
+typedef struct gkr_witness gkr_witness;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int gkr_ctx_create(int device, gkr_ctx **out);
+void gkr_ctx_destroy(gkr_ctx *ctx);
+/* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
+void *gkr_ctx_stream(gkr_ctx *ctx);
+/* block until all work enqueued by this context has finished */
+int gkr_ctx_sync(gkr_ctx *ctx);
+const char *gkr_last_error(void);
+const char *gkr_version(void);
+
+/* ---- Fiat-Shamir ------------------------------------------------------------------------------
+ * challenge(user, msg, n, r_out) must return 0 and write the challenge for the round message
+ * msg[0..n) (descending coefficients).  NULL transcript => built-in MiMC7, 91 rounds, key 0:
+ * r = multi_hash(msg, 0)   (mimc-rs; sumcheck.rs:83-85,128-130,151-153; prover.rs:74-78).
+ * Invoked once per round, synchronously, on the calling thread. */
+typedef struct {
+    void *user;
+    int (*challenge)(void *user, const gkr_fr *msg, uint32_t n, gkr_fr *r_out);
+} gkr_transcript;
+
+/* built-in transcript, exposed for hosts/tests: out = multi_hash(msg[0..n), key) ; hash(x, key) */
+int gkr_mimc7_multi_hash(const gkr_fr *msg, uint32_t n, const gkr_fr *key, gkr_fr *out);
+int gkr_mimc7_hash(const gkr_fr *x, const gkr_fr *key, gkr_fr *out);
+
+/* ---- circuit (replaces the add_i/mult_i/wire emission of convert.rs:704-777) ------------------- */
+typedef struct {
+    uint32_t k_out;           /* layer i has 2^k_out output slots (Layer.k, gkr.rs:36) */
+    uint32_t k_in;            /* k of layer i+1 (or input_k for the last layer); must be >= 1 */
+    uint32_t n_gates;         /* 1..2^k_out; slots >= n_gates are absent gates with value 0 */
+    const uint8_t *type;      /* 0 = Add, 1 = Mult (NodeType, convert.rs:815-826) */
+    const uint32_t *left;     /* operand_index.0, < 2^k_in */
+    const uint32_t *right;    /* operand_index.1, < 2^k_in */
+} gkr_layer_desc;
+
+/* layers[0] is the output layer; layers[i].k_in == layers[i+1].k_out.  Copies everything it needs
+ * (the caller may free its arrays on return) and builds the by-left / by-right CSR on the device. */
+int gkr_circuit_create(gkr_ctx *ctx, uint32_t n_layers, const gkr_layer_desc *layers, gkr_circuit **out);
+void gkr_circuit_destroy(gkr_circuit *c);
+
+/* ---- witness (replaces calculate_input, convert.rs:787-849) -------------------------------------- */
+/* all layer tables supplied by the host: layer_values[i] has 2^{k_i} elements, i = 0..n_layers */
+int gkr_witness_create(gkr_ctx *ctx, const gkr_circuit *c, const gkr_fr *const *layer_values, gkr_witness **out);
+/* only the input layer supplied (2^{input_k} elements); the layers are evaluated on the device */
+int gkr_witness_eval(gkr_ctx *ctx, const gkr_circuit *c, const gkr_fr *input_values, gkr_witness **out);
+/* copy layer i (canonical values) back to the host */
+int gkr_witness_layer(gkr_ctx *ctx, const gkr_witness *w, uint32_t layer, gkr_fr *out);
+void gkr_witness_destroy(gkr_witness *w);
+
+/* ---- proof == Proof<S> (gkr.rs:8-19), flat ------------------------------------------------------- */
+typedef struct {
+    uint32_t n_layers;         /* circuit.depth() */
+    uint32_t depth;            /* Proof.depth = n_layers + 1 (prover.rs:92) */
+    const uint32_t *k;         /* [n_layers+1]  Proof.k */
+    uint64_t n_rounds;         /* sum_i 2*k_{i+1} */
+    const uint64_t *round_off; /* [n_layers+1] prefix: rounds of layer i are round_off[i]..round_off[i+1] */
+    const uint8_t *msg_len;    /* [n_rounds] 2 or 3 */
+    const gkr_fr *msgs;        /* [n_rounds][3] sumcheck_proofs: descending coefficients, left aligned */
+    const gkr_fr *chal;        /* [n_rounds]    sumcheck_r */
+    const uint64_t *q_off;     /* [n_layers+1] prefix with stride k_{i+1}+1 */
+    const uint32_t *q_len;     /* [n_layers] */
+    const gkr_fr *q;           /* q[q_off[i] .. +q_len[i]) descending */
+    const uint64_t *z_off;     /* [n_layers+2] prefix: z_i has k_i elements */
+    const gkr_fr *z;
+    const gkr_fr *r;           /* [n_layers]  r*_i */
+    uint64_t d_len;            /* 2^{k_0} */
+    const gkr_fr *d_coef;      /* Proof.d as a dense monomial table: entry S multiplies prod_{j in S} x_j,
+                                  variable j <-> index bit k-j; zero entries are absent terms */
+    uint64_t input_len;        /* 2^{input_k} */
+    const gkr_fr *input_coef;  /* Proof.input_func, same encoding */
+} gkr_proof;
+
+int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *w, const gkr_transcript *t, gkr_proof **out);
+void gkr_proof_free(gkr_proof *p);
+
+/* ---- standalone sumcheck of a product of 3 multilinear tables (prove_sumcheck, sumcheck.rs:158-214) -
+ * tables: n_tables (= 3) pointers to 2^n_vars canonical elements in HOST memory (on_device = 0) or
+ * Montgomery-form DEVICE buffers created by gkr_dev_table_* (on_device = 1).
+ * msgs: [n_vars][4] descending left-aligned, msg_len[n_vars], chal[n_vars], final_vals[n_tables]. */
+int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_vars, const void *const *tables, int on_device,
+                      const gkr_transcript *t, gkr_fr *msgs, uint8_t *msg_len, gkr_fr *chal, gkr_fr *final_vals);
+
+/* device-resident tables for benchmarks at sizes that should not cross PCIe (BASELINE.json config 4) */
+int gkr_dev_table_synth(gkr_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t n, void **dev_table_out);
+int gkr_dev_table_upload(gkr_ctx *ctx, const gkr_fr *host_values, uint64_t n, void **dev_table_out);
+int gkr_dev_table_download(gkr_ctx *ctx, const void *dev_table, uint64_t n, gkr_fr *host_out);
+void gkr_dev_table_free(gkr_ctx *ctx, void *dev_table);
+
+/* ---- building blocks, exposed so that each kernel can be checked against the oracle --------------- */
+int gkr_fr_binop(gkr_ctx *ctx, int op /*0 add,1 sub,2 mul*/, const gkr_fr *a, const gkr_fr *b, gkr_fr *out, uint64_t n);
+int gkr_eq_table(gkr_ctx *ctx, const gkr_fr *z, uint32_t k, gkr_fr *out);
+int gkr_mobius(gkr_ctx *ctx, const gkr_fr *values, uint32_t k, gkr_fr *coef_out, uint32_t *dep_mask, uint32_t *max_deg);
+int gkr_line_restrict(gkr_ctx *ctx, const gkr_fr *values, uint32_t k, const gkr_fr *b, const gkr_fr *c,
+                      gkr_fr *coef_ascending /* k+1 */);
+
+/* ---- instrumentation ------------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t kernel_launches;  /* kernels launched by this context since creation / last reset */
+    uint64_t h2d_bytes, d2h_bytes;
+    double transcript_seconds; /* host time spent in the challenge callback / MiMC7 */
+    double wait_seconds;       /* host time spent waiting for round results */
+} gkr_stats;
+int gkr_ctx_stats(gkr_ctx *ctx, gkr_stats *out, int reset);
+/* per-kernel-class device timing (CUDA events around every launch; slows the prover down).
+ * classes: 0 gkr_round (no fold), 1 gkr_round fused fold, 2 prod3 round, 3 prod3 fused, 4 wiring,
+ * 5 eq, 6 mobius/alt-sum, 7 line, 8 other */
+#define GKR_N_KERNEL_CLASSES 9
+typedef struct {
+    uint64_t launches[GKR_N_KERNEL_CLASSES];
+    double ms[GKR_N_KERNEL_CLASSES];
+    double algo_bytes[GKR_N_KERNEL_CLASSES];   /* algorithmic bytes moved (reads + writes of table entries) */
+} gkr_profile;
+int gkr_ctx_profile(gkr_ctx *ctx, int enable, gkr_profile *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,23 @@
+// Test-only harness: runs the product's device field library (gkr_b200/csrc/fr.cuh) through its
+// portable host-emulation branch so that the composition logic (row chains, Montgomery reduction,
+// conditional subtraction) can be checked on a CPU against Python big integers.
+#include "../../gkr_b200/csrc/fr.cuh"
+#include <cstring>
+extern "C" int frh_binop(int op, const unsigned char *a, const unsigned char *b, unsigned char *out, unsigned long n) {
+    for (unsigned long i = 0; i < n; ++i) {
+        Fr x, y, r;
+        std::memcpy(x.l, a + 32 * i, 32);
+        std::memcpy(y.l, b + 32 * i, 32);
+        if (!fr_is_canonical(x) || !fr_is_canonical(y)) return -1;
+        Fr xm = fr_to_mont(x), ym = fr_to_mont(y);
+        switch (op) {
+            case 0: r = fr_add(xm, ym); break;
+            case 1: r = fr_sub(xm, ym); break;
+            case 2: r = fr_mul(xm, ym); break;
+            default: r = fr_neg(xm); break;
+        }
+        r = fr_from_mont(r);
+        std::memcpy(out + 32 * i, r.l, 32);
+    }
+    return 0;
+}

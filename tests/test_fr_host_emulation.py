@@ -1,0 +1,52 @@
+"""CPU check of the composition logic in gkr_b200/csrc/fr.cuh via its host-emulation branch
+(the PTX branch itself is checked on the GPU in tests/test_gpu_field.py)."""
+import ctypes as C
+import os
+import random
+import subprocess
+
+import numpy as np
+
+from oracle import oracle as orc
+
+P = orc.P
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _lib():
+    so = os.path.join(HERE, "csrc", "libfr_host_check.so")
+    src = os.path.join(HERE, "csrc", "fr_host_check.cpp")
+    hdr = os.path.join(HERE, "..", "gkr_b200", "csrc", "fr.cuh")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
+    return C.CDLL(so)
+
+
+def _edge_values():
+    vals = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, 2**32 - 1, 2**32, 2**64 - 1, 2**128, 2**253, 2**253 + 12345]
+    vals += [(1 << (32 * i)) - 1 for i in range(1, 8)] + [P - (1 << (32 * i)) for i in range(1, 8)]
+    return [v % P for v in vals]
+
+
+def test_host_emulation_matches_bigint():
+    lib = _lib()
+    rng = random.Random(1)
+    edge = _edge_values()
+    a = [x for x in edge for _ in edge] + [rng.randrange(P) for _ in range(3000)]
+    b = [y for _ in edge for y in edge] + [rng.randrange(P) for _ in range(3000)]
+    A, B = orc.to_bytes(a), orc.to_bytes(b)
+    for op, fn in ((0, lambda x, y: (x + y) % P), (1, lambda x, y: (x - y) % P), (2, lambda x, y: x * y % P),
+                   (3, lambda x, y: (-x) % P)):
+        out = np.zeros_like(A)
+        rc = lib.frh_binop(op, A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p),
+                           out.ctypes.data_as(C.c_void_p), C.c_ulong(len(a)))
+        assert rc == 0
+        assert orc.from_bytes(out) == [fn(x, y) for x, y in zip(a, b)]
+
+
+def test_noncanonical_rejected():
+    lib = _lib()
+    A = orc.to_bytes([P])
+    out = np.zeros_like(A)
+    assert lib.frh_binop(0, A.ctypes.data_as(C.c_void_p), A.ctypes.data_as(C.c_void_p),
+                         out.ctypes.data_as(C.c_void_p), C.c_ulong(1)) == -1

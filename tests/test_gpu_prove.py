@@ -1,0 +1,163 @@
+"""GPU parity tests proper: gkr_prove through the C ABI against the golden fixtures, the literal
+reference restatement (L0), the dense CPU oracle (L1) and the complete verifier -- bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+from gkr_b200 import synthetic as syn
+from gkr_b200.field import P, fr_to_ints, ints_to_fr
+from oracle import l0_reference as l0
+from oracle import oracle as orc
+from oracle import verifier
+from tests import golden_util as gu
+from tests.helpers import assert_same_dense, dense_layers, random_circuit, run_l0, run_l1
+
+pytestmark = pytest.mark.gpu
+GOLD = gu.load()
+
+
+@pytest.fixture(scope="module")
+def pv():
+    from gkr_b200 import Prover
+    return Prover(0)
+
+
+def _gpu_prove(pv, layers, inputs, challenge=None):
+    from gkr_b200 import DenseLayer
+    dl = dense_layers(layers)
+    c = pv.circuit([DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in dl])
+    w = pv.witness_eval(c, ints_to_fr(inputs))
+    return pv.prove(c, w, challenge)
+
+
+@pytest.mark.parametrize("case", GOLD["gkr"], ids=[c["name"] for c in GOLD["gkr"]])
+def test_golden(pv, case):
+    layers = gu.case_layers(case)
+    inputs = gu.I(case["input"])
+    proof = _gpu_prove(pv, layers, inputs)
+    gu.assert_dense_matches_golden(proof, gu.golden_proof_fields(case), case["name"])
+    ok, why = verifier.verify(layers, proof, input_values=inputs)
+    assert ok, why
+
+
+@pytest.mark.parametrize("ks", [[1, 2, 2], [2, 3, 2], [2, 2, 3, 1], [3, 4, 3], [0, 2, 2], [1, 1, 1], [4, 5, 4, 5]])
+@pytest.mark.parametrize("mode", ["mixed", "add", "mult"])
+def test_against_literal_reference_types(pv, ks, mode):
+    """reads like a reference test: build GKRCircuit/Input term lists, call prove(), compare with L0"""
+    import gkr_b200 as g
+    rng = random.Random(hash((tuple(ks), mode, 1)) & 0xFFFF)
+    layers = random_circuit(rng, ks, mode)
+    inputs = [rng.randrange(P) for _ in range(1 << ks[-1])]
+    ref_circ = l0.build_reference_circuit([(k_out, gates) for k_out, _, gates in layers], ks[-1])
+    ref_inp, _ = l0.calculate_input([(k_out, gates) for k_out, _, gates in layers], inputs)
+    want = l0.prove(ref_circ, ref_inp)
+    circ = g.GKRCircuit([g.Layer(L.k, L.add, L.mult, L.wire) for L in ref_circ.layer], ref_circ.input_k)
+    got = g.prove(circ, g.Input(ref_inp.w, ref_inp.d), prover=pv)
+    assert got.sumcheck_proofs == want.sumcheck_proofs
+    assert got.sumcheck_r == want.sumcheck_r
+    assert got.q == want.q and got.z == want.z and got.r == want.r
+    assert got.depth == want.depth and got.k == want.k
+    assert sorted(got.d) == sorted(want.d) and sorted(got.input_func) == sorted(want.input_func)
+
+
+@pytest.mark.parametrize("ks,full", [([5, 7, 6], True), ([8, 8, 8, 8], True), ([3, 9, 4, 10], False), ([10, 11, 12], True),
+                                     ([12, 12, 12], False)])
+def test_against_dense_oracle(pv, ks, full):
+    rng = random.Random(sum(ks) * 31 + len(ks))
+    layers = random_circuit(rng, ks, "mixed", full=full)
+    inputs = [rng.randrange(P) for _ in range(1 << ks[-1])]
+    want, _ = run_l1(layers, inputs)
+    got = _gpu_prove(pv, layers, inputs)
+    assert_same_dense(want, got)
+
+
+def test_degenerate_shapes_mid_size(pv):
+    """static length rules at a size where the alternating-sum shortcut and the Moebius fallback both matter"""
+    rng = random.Random(77)
+    k = 9
+    layers = random_circuit(rng, [6, k], "mixed")
+    a, b = rng.randrange(P), rng.randrange(P)
+    n = 1 << k
+    for inputs in ([5] * n, [0] * n, [a] * (n // 2) + [b] * (n // 2),
+                   [rng.randrange(P) if i % 8 == 0 else 0 for i in range(n)],
+                   [rng.randrange(P) for _ in range(n // 4)] * 4):
+        want, _ = run_l1(layers, inputs)
+        got = _gpu_prove(pv, layers, inputs)
+        assert_same_dense(want, got)
+
+
+def test_custom_transcript_callback(pv):
+    """the challenge callback (how a Rust host keeps mimc_rs) must see the same messages and drive the same proof"""
+    rng = random.Random(5)
+    layers = random_circuit(rng, [3, 4, 3], "mixed")
+    inputs = [rng.randrange(P) for _ in range(8)]
+    seen = []
+
+    def challenge(msg):
+        seen.append(list(msg))
+        return l0.multi_hash(msg, 0)
+    a = _gpu_prove(pv, layers, inputs, challenge)
+    b = _gpu_prove(pv, layers, inputs)
+    assert_same_dense(a, b)
+    assert seen == [m for layer in b.sumcheck_proofs for m in layer]
+    # a different transcript gives a different, still self-consistent, proof
+    c = _gpu_prove(pv, layers, inputs, lambda msg: (sum(msg) * 7 + 3) % P)
+    assert c.sumcheck_r != b.sumcheck_r
+    ok, why = verifier.verify(layers, c, input_values=inputs, check_hashes=False)
+    assert ok, why
+
+
+def test_config2_synthetic_2p16_x8(pv):
+    """BASELINE.json config 2: synthetic layered add/mul circuit, 2^16 gates/layer x 8 layers, bit-exact vs oracle"""
+    k, n_layers, seed = 16, 8, 1
+    layers = syn.layered_circuit(seed, k, n_layers)
+    inputs = syn.input_values(seed, k)
+    c = pv.circuit(layers)
+    w = pv.witness_eval(c, inputs)
+    got = pv.prove(c, w)
+    ol = [orc.DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in layers]
+    vals = orc.evaluate_circuit(ol, inputs.view(np.uint8).reshape(-1, 32))
+    want = orc.gkr_prove(ol, vals)
+    assert_same_dense(want, got)
+    # size-independent properties: every round message has full length, claims chain, hashes chain
+    for i in range(n_layers):
+        assert all(len(m) == 3 for m in got.sumcheck_proofs[i]) and len(got.q[i]) == k + 1
+        claim = None
+        for m, r in zip(got.sumcheck_proofs[i], got.sumcheck_r[i]):
+            if claim is not None:
+                assert (verifier.horner(m, 0) + verifier.horner(m, 1)) % P == claim
+            assert l0.multi_hash(m, 0) == r
+            claim = verifier.horner(m, r)
+
+
+@pytest.mark.parametrize("seed", [1])
+def test_config3_synthetic_2p20_x16(pv, seed):
+    """BASELINE.json config 3 at full size: 2^20 gates/layer x 16 layers, bit-exact vs the dense CPU oracle"""
+    k, n_layers = 20, 16
+    layers = syn.layered_circuit(seed, k, n_layers)
+    inputs = syn.input_values(seed, k)
+    c = pv.circuit(layers)
+    w = pv.witness_eval(c, inputs)
+    ptr = pv.prove_raw(c, w)
+    from gkr_b200.prover import _np_from
+    pc = ptr.contents
+    R = int(pc.n_rounds)
+    got_msgs = _np_from(pc.msgs, R * 3 * 8, np.uint32).reshape(R, 3, 8)
+    got_chal = _np_from(pc.chal, R * 8, np.uint32).reshape(R, 8)
+    got_q = _np_from(pc.q, int(_np_from(pc.q_off, n_layers + 1, np.uint64)[n_layers]) * 8, np.uint32).reshape(-1, 8)
+    got_z = _np_from(pc.z, (n_layers + 1) * k * 8, np.uint32).reshape(-1, 8)
+    got_r = _np_from(pc.r, n_layers * 8, np.uint32).reshape(-1, 8)
+    got_d = _np_from(pc.d_coef, int(pc.d_len) * 8, np.uint32).reshape(-1, 8)
+    got_in = _np_from(pc.input_coef, int(pc.input_len) * 8, np.uint32).reshape(-1, 8)
+    pv.free_raw(ptr)
+    ol = [orc.DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in layers]
+    vals = orc.evaluate_circuit(ol, inputs.view(np.uint8).reshape(-1, 32))
+    want = orc.gkr_prove(ol, vals)
+    flat_msgs = [m for layer in want.sumcheck_proofs for m in layer]
+    assert [fr_to_ints(got_msgs[j]) for j in range(R)] == flat_msgs
+    assert fr_to_ints(got_chal) == [r for layer in want.sumcheck_r for r in layer]
+    assert fr_to_ints(got_q) == [x for layer in want.q for x in layer]
+    assert fr_to_ints(got_z) == [x for zz in want.z for x in zz]
+    assert fr_to_ints(got_r) == want.r
+    assert fr_to_ints(got_d) == want.d_coef and fr_to_ints(got_in) == want.input_coef

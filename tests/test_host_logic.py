@@ -1,0 +1,55 @@
+"""Host-side mirror logic (no GPU): decoding the reference's term-list types into the dense boundary,
+term-list emission, synthetic generators."""
+import random
+
+import numpy as np
+
+from gkr_b200 import prover as gp
+from gkr_b200 import synthetic as syn
+from gkr_b200.field import P, fr_to_ints, ints_to_fr
+from oracle import l0_reference as l0
+from oracle import oracle as orc
+from tests.helpers import random_circuit
+
+
+def test_field_roundtrip():
+    vals = [0, 1, P - 1, 2**200 + 17]
+    assert fr_to_ints(ints_to_fr(vals)) == vals
+    a = ints_to_fr(vals)
+    assert fr_to_ints(gp.as_fr_array(a.view(np.uint8).reshape(-1, 32))) == vals
+
+
+def test_circuit_to_dense_inverts_reference_emission():
+    rng = random.Random(2)
+    for ks in ([2, 3, 2], [0, 2, 2], [3, 1, 2]):
+        layers = random_circuit(rng, ks, "mixed", full=(ks[0] != 2))
+        ref = l0.build_reference_circuit([(k_out, gates) for k_out, _, gates in layers], ks[-1])
+        circ = gp.GKRCircuit([gp.Layer(L.k, L.add, L.mult, L.wire) for L in ref.layer], ref.input_k)
+        dense = gp.circuit_to_dense(circ)
+        for (k_out, k_in, gates), D in zip(layers, dense):
+            assert (D.k_out, D.k_in) == (k_out, k_in)
+            assert [(int(t), int(l), int(r)) for t, l, r in zip(D.gtype, D.left, D.right)] == gates
+        assert circ.get_k_list() == ks
+
+
+def test_terms_to_values_inverts_get_multi_ext():
+    rng = random.Random(3)
+    for k in (1, 2, 4):
+        vals = [rng.randrange(P) if rng.random() < 0.7 else 0 for _ in range(1 << k)]
+        terms = l0.get_multi_ext(vals, k)
+        assert gp.terms_to_values(terms, k) == vals
+        coef, _, _ = orc.mobius(orc.to_bytes(vals), k)
+        emitted = gp.coef_table_to_terms(orc.from_bytes(coef), k)
+        assert sorted(emitted) == sorted(terms)
+    assert gp.coef_table_to_terms([7], 0) == []
+
+
+def test_synthetic_generators_match_oracle_definition():
+    for seed in (1, 3):
+        assert fr_to_ints(syn.values(seed, syn.INPUT_STREAM, 513)) == orc.from_bytes(orc.synth_values(seed, syn.INPUT_STREAM, 513))
+        assert fr_to_ints(syn.values(seed, syn.TABLE_STREAM + 1, 64, first=100)) == orc.from_bytes(
+            orc.synth_values(seed, syn.TABLE_STREAM + 1, 64, first=100))
+        g = syn.gates(seed, 2, 9, 7)
+        t, l, r = orc.synth_gates(seed, 2, 7, 512)
+        assert (g.gtype == t).all() and (g.left == l).all() and (g.right == r).all()
+    assert all(v < P for v in fr_to_ints(syn.values(9, 1, 2000)))
