@@ -62,11 +62,11 @@ class Profile(C.Structure):
 
 # every symbol include/gkr_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "gkr_ctx_create", "gkr_ctx_destroy", "gkr_ctx_stream", "gkr_ctx_sync", "gkr_last_error", "gkr_version", "gkr_mimc7_multi_hash", "gkr_mimc7_hash",
+    "gkr_ctx_create", "gkr_ctx_destroy", "gkr_ctx_stream", "gkr_ctx_sync", "gkr_ctx_set_option", "gkr_last_error", "gkr_version", "gkr_mimc7_multi_hash", "gkr_mimc7_hash",
     "gkr_circuit_create", "gkr_circuit_destroy", "gkr_witness_create", "gkr_witness_eval", "gkr_witness_layer",
     "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_sumcheck_prod", "gkr_dev_table_synth",
     "gkr_dev_table_upload", "gkr_dev_table_download", "gkr_dev_table_free", "gkr_fr_binop", "gkr_eq_table",
-    "gkr_mobius", "gkr_line_restrict", "gkr_ctx_stats", "gkr_ctx_profile",
+    "gkr_mobius", "gkr_line_restrict", "gkr_ctx_stats", "gkr_ctx_profile", "gkr_bench_field_mul",
 ]
 
 _LIB = None
@@ -98,6 +98,7 @@ def lib():
     L.gkr_ctx_stream.argtypes = [vp]
     L.gkr_ctx_stream.restype = vp
     L.gkr_ctx_sync.argtypes = [vp]
+    L.gkr_ctx_set_option.argtypes = [vp, C.c_char_p, i32]
     L.gkr_mimc7_multi_hash.argtypes = [vp, u32, vp, vp]
     L.gkr_mimc7_hash.argtypes = [vp, vp, vp]
     L.gkr_circuit_create.argtypes = [vp, u32, C.POINTER(LayerDesc), C.POINTER(vp)]
@@ -123,6 +124,7 @@ def lib():
     L.gkr_line_restrict.argtypes = [vp, vp, u32, vp, vp, vp]
     L.gkr_ctx_stats.argtypes = [vp, C.POINTER(Stats), i32]
     L.gkr_ctx_profile.argtypes = [vp, i32, C.POINTER(Profile)]
+    L.gkr_bench_field_mul.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_double)]
     _LIB = L
     return L
 

@@ -12,7 +12,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 
 #include "runtime.cuh"
@@ -30,6 +32,35 @@ void set_last_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
+}
+
+namespace {
+std::mutex g_pool_mu;
+std::multimap<size_t, void *> g_pool;
+}  // namespace
+void *pinned_get(size_t bytes) {
+    if (bytes == 0) bytes = 32;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = g_pool.find(bytes);
+        if (it != g_pool.end()) {
+            void *p = it->second;
+            g_pool.erase(it);
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void pinned_put(void *ptr, size_t bytes) {
+    if (!ptr) return;
+    if (bytes == 0) bytes = 32;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool.emplace(bytes, ptr);
 }
 }  // namespace gkr
 
@@ -90,7 +121,10 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     if (!ctx) return GKR_ERR_OOM;
     ctx->device = device;
     GKR_TRY(ctx->bind());
-    GKR_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    GKR_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    GKR_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+    GKR_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_lo));
     GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->slots_host, sizeof(HostSlot) * gkr_ctx::kSlots, cudaHostAllocMapped));
     std::memset((void *)ctx->slots_host, 0, sizeof(HostSlot) * gkr_ctx::kSlots);
     GKR_CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->slots_dev, (void *)ctx->slots_host, 0));
@@ -113,8 +147,9 @@ extern "C" void gkr_ctx_destroy(gkr_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->aux) cudaStreamSynchronize(ctx->aux);
     for (DevBuf *b : {&ctx->eqz, &ctx->equ, &ctx->eq_scratch, &ctx->H, &ctx->A, &ctx->foldA, &ctx->foldB, &ctx->lineA,
-                      &ctx->lineB, &ctx->mob, &ctx->misc, &ctx->stage})
+                      &ctx->lineB, &ctx->mob, &ctx->misc, &ctx->stage, &ctx->aux_mob, &ctx->aux_stage, &ctx->qdev})
         b->release();
     if (ctx->ws.partials) cudaFree(ctx->ws.partials);
     if (ctx->ws.counter) cudaFree(ctx->ws.counter);
@@ -124,7 +159,27 @@ extern "C" void gkr_ctx_destroy(gkr_ctx *ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
     delete ctx;
+}
+
+extern "C" int gkr_bench_field_mul(gkr_ctx *ctx, int ilp, int blocks_per_sm, int iters, double *mul_per_second) {
+    if (!ctx || !mul_per_second || blocks_per_sm < 1 || blocks_per_sm > 8 || iters < 1) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
+    *mul_per_second = run_mul_bench(ilp, blocks_per_sm, iters, ctx->misc.as<Fr>(), ctx->stream);
+    ctx->stats.kernel_launches += 2;
+    return ctx->check_launch("mul_bench");
+}
+
+extern "C" int gkr_ctx_set_option(gkr_ctx *ctx, const char *name, int value) {
+    if (!ctx || !name) return GKR_ERR_INVALID;
+    if (std::strcmp(name, "paranoid") == 0) {
+        ctx->paranoid = value != 0;
+        return GKR_OK;
+    }
+    set_last_error("unknown option '%s'", name);
+    return GKR_ERR_INVALID;
 }
 
 extern "C" void *gkr_ctx_stream(gkr_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
@@ -132,6 +187,7 @@ extern "C" int gkr_ctx_sync(gkr_ctx *ctx) {
     if (!ctx) return GKR_ERR_INVALID;
     GKR_TRY(ctx->bind());
     GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->aux));
     return GKR_OK;
 }
 
@@ -450,13 +506,20 @@ struct ProofHolder {
     std::vector<uint32_t> k, q_len;
     std::vector<uint64_t> round_off, q_off, z_off;
     std::vector<uint8_t> msg_len;
-    std::vector<gkr_fr> msgs, chal, q, z, r, d_coef, input_coef;
+    std::vector<gkr_fr> msgs, chal, q, z, r;
+    gkr_fr *d_coef = nullptr, *input_coef = nullptr, *q_stage = nullptr;     // pinned (pool)
+    size_t d_n = 0, input_n = 0, q_stage_n = 0;
+    ~ProofHolder() {
+        pinned_put(d_coef, d_n * sizeof(gkr_fr));
+        pinned_put(input_coef, input_n * sizeof(gkr_fr));
+        pinned_put(q_stage, q_stage_n * sizeof(gkr_fr));
+    }
     void finish() {
         pub.k = k.data(); pub.round_off = round_off.data(); pub.msg_len = msg_len.data();
         pub.msgs = msgs.data(); pub.chal = chal.data(); pub.q_off = q_off.data(); pub.q_len = q_len.data();
         pub.q = q.data(); pub.z_off = z_off.data(); pub.z = z.data(); pub.r = r.data();
-        pub.d_coef = d_coef.data(); pub.d_len = d_coef.size();
-        pub.input_coef = input_coef.data(); pub.input_len = input_coef.size();
+        pub.d_coef = d_coef; pub.d_len = d_n;
+        pub.input_coef = input_coef; pub.input_len = input_n;
     }
 };
 extern "C" void gkr_proof_free(gkr_proof *p) {
@@ -478,7 +541,10 @@ struct PhaseIO {
     const Fr *W_last;          // out: device pointer to the size-2 W table of the last round
 };
 
-static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *last_hash) {
+// claim: in = g_{prev}(r_prev) if known (nullptr => the first round also accumulates g(1) on the device);
+//        out = g_k(r_k), the claim the next phase starts from.
+static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *last_hash, const HFr *claim_in,
+                     HFr *claim_out) {
     const uint32_t k = io.k;
     const uint64_t N = (uint64_t)1 << k;
     GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 2, 2)));
@@ -486,19 +552,23 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
     const Fr *Hc = io.H, *Wc = io.W, *Ac = io.A;
     uint64_t n = N;                                   // size of the current tables
     HFr r = hfr_zero();
+    HFr claim = claim_in ? *claim_in : hfr_zero();
+    bool have_claim = claim_in != nullptr;
     for (uint32_t j = 0; j < k; ++j) {
         const uint32_t s = ctx->next_seq();
+        const bool full = !have_claim || ctx->paranoid;
         ctx->begin_launch();
         if (j == 0) {
-            launch_gkr_round(false, Hc, Wc, Ac, nullptr, nullptr, nullptr, to_dev(r), n / 2, ctx->ws, ctx->slot_dev(s), s,
-                             ctx->stream);
-            ctx->end_launch(KC_ROUND, 96.0 * n);
+            launch_gkr_round(false, full, Hc, Wc, Ac, nullptr, nullptr, nullptr, to_dev(r), n / 2, ctx->ws, ctx->slot_dev(s),
+                             s, ctx->stream);
+            ctx->end_launch(KC_ROUND, (full ? 96.0 : 80.0) * n);
         } else {
             // fold the size-n tables with r_{j} into size n/2 and evaluate round j+1 on them
             DevBuf &dst = (j & 1) ? ctx->foldA : ctx->foldB;
             const uint64_t half = n / 2;
             Fr *Ho = dst.as<Fr>(), *Wo = Ho + half, *Ao = Wo + half;
-            launch_gkr_round(true, Hc, Wc, Ac, Ho, Wo, Ao, to_dev(r), half / 2, ctx->ws, ctx->slot_dev(s), s, ctx->stream);
+            launch_gkr_round(true, full, Hc, Wc, Ac, Ho, Wo, Ao, to_dev(r), half / 2, ctx->ws, ctx->slot_dev(s), s,
+                             ctx->stream);
             ctx->end_launch(KC_ROUND_FUSED, 96.0 * n + 96.0 * half);
             Hc = Ho; Wc = Wo; Ac = Ao;
             n = half;
@@ -507,9 +577,15 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
         const HostSlot *slot;
         GKR_TRY(ctx->wait_slot(s, &slot));
         HFr x0, x1, x2;
-        if (!hfr_from_canonical(&x0, &slot->v[0]) || !hfr_from_canonical(&x1, &slot->v[1]) ||
-            !hfr_from_canonical(&x2, &slot->v[2])) {
+        if (!hfr_from_canonical(&x0, &slot->v[0]) || !hfr_from_canonical(&x2, &slot->v[1]) ||
+            (full && !hfr_from_canonical(&x1, &slot->v[2]))) {
             set_last_error("device published a non-canonical round value");
+            return GKR_ERR_INTERNAL;
+        }
+        if (!full) {
+            x1 = hfr_sub(claim, x0);                  // g(0) + g(1) = claim
+        } else if (have_claim && !hfr_eq(hfr_add(x0, x1), claim)) {
+            set_last_error("sumcheck claim mismatch at round %u: g(0)+g(1) != previous g(r)", j);
             return GKR_ERR_INTERNAL;
         }
         // message: descending coefficients [c2, c1, c0] or [c1, c0] when W does not depend on x_{j+1}
@@ -526,9 +602,11 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
         io.challenges[j] = r;
         hfr_to_canonical(&io.chal_out[j], r);
         *last_hash = r;
+        claim = hfr_add(hfr_mul(hfr_add(hfr_mul(x2, r), c1), r), x0);      // g(r), Horner
+        have_claim = true;
     }
     io.W_last = Wc;
-    // keep r_k for the caller's final fold
+    if (claim_out) *claim_out = claim;
     return GKR_OK;
 }
 
@@ -547,6 +625,11 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
     const uint32_t n_layers = (uint32_t)c->layers.size();
     std::unique_ptr<ProofHolder> P(new (std::nothrow) ProofHolder());
     if (!P) return GKR_ERR_OOM;
+    // whatever path leaves this function, no aux-stream copy may still target the proof's pinned tables
+    struct AuxDrain {
+        cudaStream_t st;
+        ~AuxDrain() { cudaStreamSynchronize(st); }
+    } aux_drain{ctx->aux};
     P->pub.n_layers = n_layers;
     P->pub.depth = n_layers + 1;
     P->k = c->k;
@@ -577,25 +660,39 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
     GKR_TRY(ctx->mob.ensure(sizeof(Fr) * Nmax));
     GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
 
-    // d and input_func as dense monomial tables (prover.rs:88,93; get_multi_ext, poly.rs:502-536)
+    // d and input_func as dense monomial tables (prover.rs:88,93; get_multi_ext, poly.rs:502-536):
+    // Moebius transform + D2H into pinned proof memory on the low-priority stream, overlapped with the rounds
+    GKR_TRY(ctx->aux_mob.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->aux_stage.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->qdev.ensure(sizeof(Fr) * (P->q_off[n_layers] + 1)));
+    P->q_stage_n = P->q_off[n_layers] + 1;
+    P->q_stage = static_cast<gkr_fr *>(pinned_get(P->q_stage_n * sizeof(gkr_fr)));
     for (int which = 0; which < 2; ++which) {
         const uint32_t layer = which == 0 ? 0 : n_layers;
         const uint32_t k = c->k[layer];
         const uint64_t n = (uint64_t)1 << k;
-        std::vector<gkr_fr> &dst = which == 0 ? P->d_coef : P->input_coef;
-        dst.assign(n, gkr_fr{});
-        GKR_CUDA_TRY(cudaMemcpyAsync(ctx->mob.ptr, w->vals[layer], n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-        ctx->begin_launch();
-        launch_mobius(ctx->mob.as<Fr>(), k, ctx->stream);
-        ctx->end_launch(KC_MOBIUS, 64.0 * n * (k > 10 ? 1 + (k - 10) : 1), k > 10 ? 1 + (int)(k - 10) : 1);
+        gkr_fr *dst = static_cast<gkr_fr *>(pinned_get(n * sizeof(gkr_fr)));
+        if (which == 0) { P->d_coef = dst; P->d_n = n; } else { P->input_coef = dst; P->input_n = n; }
+        if (!dst || !P->q_stage) {
+            set_last_error("pinned host allocation failed");
+            return GKR_ERR_OOM;
+        }
+        GKR_CUDA_TRY(cudaMemcpyAsync(ctx->aux_mob.ptr, w->vals[layer], n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->aux));
+        ctx->begin_launch(ctx->aux);
+        launch_mobius(ctx->aux_mob.as<Fr>(), k, ctx->aux);
+        ctx->end_launch(KC_MOBIUS, 64.0 * n * (k > 10 ? 1 + (k - 10) : 1), k > 10 ? 1 + (int)(k - 10) : 1, ctx->aux);
         GKR_TRY(ctx->check_launch("mobius"));
-        GKR_TRY(download_table(ctx, ctx->mob.as<Fr>(), n, dst.data()));
+        ctx->begin_launch(ctx->aux);
+        launch_from_mont(ctx->aux_mob.as<Fr>(), ctx->aux_stage.as<Fr>(), n, ctx->aux);
+        ctx->end_launch(KC_OTHER, 64.0 * n, 1, ctx->aux);
+        GKR_TRY(ctx->check_launch("from_mont"));
+        GKR_CUDA_TRY(cudaMemcpyAsync(dst, ctx->aux_stage.ptr, n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->aux));
+        ctx->stats.d2h_bytes += n * sizeof(Fr);
     }
 
     // z_0 = 0 (prover.rs:16-21)
     std::vector<HFr> z(c->k[0], hfr_zero());
     std::vector<HFr> rs;
-    std::vector<gkr_fr> qbuf;
 
     for (uint32_t li = 0; li < n_layers; ++li) {
         const LayerDev &L = c->layers[li];
@@ -638,7 +735,8 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         io.H = H; io.W = W; io.A = A; io.k = k; io.dep_mask = dep_mask;
         io.challenges = rs.data();
         io.msgs = &P->msgs[3 * ro]; io.msg_len = &P->msg_len[ro]; io.chal_out = &P->chal[ro];
-        GKR_TRY(run_phase(ctx, t, io, &last_hash));
+        HFr claim = hfr_zero();
+        GKR_TRY(run_phase(ctx, t, io, &last_hash, nullptr, &claim));
         // W(u): fold the last size-2 W table with r_k
         ctx->begin_launch();
         launch_fold(io.W_last, wu, to_dev(rs[k - 1]), 1, ctx->stream);
@@ -653,35 +751,31 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         GKR_TRY(ctx->check_launch("wiring_phase2"));
         io.challenges = rs.data() + k;
         io.msgs = &P->msgs[3 * (ro + k)]; io.msg_len = &P->msg_len[ro + k]; io.chal_out = &P->chal[ro + k];
-        GKR_TRY(run_phase(ctx, t, io, &last_hash));
+        GKR_TRY(run_phase(ctx, t, io, &last_hash, &claim, &claim));
 
-        // ---- q_i = W restricted to the line b* -> c* (poly.rs:469-500), static length 1 + max_deg ----
+        // ---- q_i = W restricted to the line b* -> c* (poly.rs:469-500): needs only b*, c* => runs on the
+        //      low-priority stream while the next layer's rounds proceed; collected after the last layer ----
         {
             const Fr *cur = W;
             uint64_t cnt = N;
             for (uint32_t j = 0; j < k; ++j) {
                 Fr *nxt = (j & 1) ? ctx->lineB.as<Fr>() : ctx->lineA.as<Fr>();
                 const HFr g = hfr_sub(rs[k + j], rs[j]);
-                ctx->begin_launch();
-                launch_line_fold(cur, nxt, cnt, j, to_dev(rs[j]), to_dev(g), ctx->stream);
-                ctx->end_launch(KC_LINE, 32.0 * (double)(cnt * (j + 1)) + 32.0 * (double)(cnt / 2 * (j + 2)));
+                ctx->begin_launch(ctx->aux);
+                launch_line_fold(cur, nxt, cnt, j, to_dev(rs[j]), to_dev(g), ctx->aux);
+                ctx->end_launch(KC_LINE, 32.0 * (double)(cnt * (j + 1)) + 32.0 * (double)(cnt / 2 * (j + 2)), 1, ctx->aux);
                 GKR_TRY(ctx->check_launch("line_fold"));
                 cur = nxt;
                 cnt /= 2;
             }
-            qbuf.assign(k + 1, gkr_fr{});
-            GKR_TRY(download_table(ctx, cur, k + 1, qbuf.data()));     // ascending coefficients
-            const uint32_t len = max_deg + 1;
-            for (uint32_t d = len; d <= k; ++d) {
-                bool zero = true;
-                for (int l = 0; l < 8; ++l) zero &= qbuf[d].l[l] == 0;
-                if (!zero) {
-                    set_last_error("layer %u: q has degree above the static bound", li);
-                    return GKR_ERR_INTERNAL;
-                }
-            }
-            for (uint32_t d = 0; d < len; ++d) P->q[P->q_off[li] + d] = qbuf[len - 1 - d];
-            P->q_len[li] = len;
+            Fr *qd = ctx->qdev.as<Fr>() + P->q_off[li];
+            ctx->begin_launch(ctx->aux);
+            launch_from_mont(cur, qd, k + 1, ctx->aux);                 // ascending coefficients
+            ctx->end_launch(KC_OTHER, 64.0 * (k + 1), 1, ctx->aux);
+            GKR_TRY(ctx->check_launch("from_mont"));
+            GKR_CUDA_TRY(cudaMemcpyAsync(P->q_stage + P->q_off[li], qd, (k + 1) * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->aux));
+            ctx->stats.d2h_bytes += (k + 1) * sizeof(Fr);
+            P->q_len[li] = max_deg + 1;                                  // static length 1 + max_deg
         }
 
         // ---- r*_i = hash of the last message (prover.rs:74-78); z_{i+1} = b* + r*(c* - b*) (poly.rs:538-551) ----
@@ -690,6 +784,21 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         for (uint32_t j = 0; j < k; ++j) znext[j] = hfr_add(rs[j], hfr_mul(hfr_sub(rs[k + j], rs[j]), last_hash));
         for (uint32_t j = 0; j < k; ++j) hfr_to_canonical(&P->z[P->z_off[li + 1] + j], znext[j]);
         z.swap(znext);
+    }
+    // collect the q_i (ascending on the staging buffer -> descending, truncated to the static length)
+    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->aux));
+    for (uint32_t li = 0; li < n_layers; ++li) {
+        const uint32_t k = c->k[li + 1], len = P->q_len[li];
+        const gkr_fr *asc = P->q_stage + P->q_off[li];
+        for (uint32_t d = len; d <= k; ++d) {
+            bool zero = true;
+            for (int l = 0; l < 8; ++l) zero &= asc[d].l[l] == 0;
+            if (!zero) {
+                set_last_error("layer %u: q has degree above the static bound", li);
+                return GKR_ERR_INTERNAL;
+            }
+        }
+        for (uint32_t d = 0; d < len; ++d) P->q[P->q_off[li] + d] = asc[len - 1 - d];
     }
     // z_0 entries are zero already
     P->finish();
@@ -776,18 +885,21 @@ extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_var
     const Fr *Ac = T[0], *Bc = T[1], *Cc = T[2];
     uint64_t n = N;
     HFr r = hfr_zero();
+    HFr claim = hfr_zero();
     for (uint32_t j = 0; j < n_vars; ++j) {
         const uint32_t s = ctx->next_seq();
+        const bool full = (j == 0) || ctx->paranoid;     // the first claim (the sum itself) is not known in advance
         ctx->begin_launch();
         if (j == 0) {
-            launch_prod3_round(false, Ac, Bc, Cc, nullptr, nullptr, nullptr, to_dev(r), n / 2, ctx->ws, ctx->slot_dev(s), s,
-                               ctx->stream);
+            launch_prod3_round(false, full, Ac, Bc, Cc, nullptr, nullptr, nullptr, to_dev(r), n / 2, ctx->ws,
+                               ctx->slot_dev(s), s, ctx->stream);
             ctx->end_launch(KC_PROD3, 96.0 * n);
         } else {
             DevBuf &dst = (j & 1) ? ctx->foldA : ctx->foldB;
             const uint64_t half = n / 2;
             Fr *Ao = dst.as<Fr>(), *Bo = Ao + half, *Co = Bo + half;
-            launch_prod3_round(true, Ac, Bc, Cc, Ao, Bo, Co, to_dev(r), half / 2, ctx->ws, ctx->slot_dev(s), s, ctx->stream);
+            launch_prod3_round(true, full, Ac, Bc, Cc, Ao, Bo, Co, to_dev(r), half / 2, ctx->ws, ctx->slot_dev(s), s,
+                               ctx->stream);
             ctx->end_launch(KC_PROD3_FUSED, 96.0 * n + 96.0 * half);
             Ac = Ao; Bc = Bo; Cc = Co;
             n = half;
@@ -796,9 +908,15 @@ extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_var
         const HostSlot *slot;
         GKR_TRY(ctx->wait_slot(s, &slot));
         HFr g0, g1, gm, ginf;
-        if (!hfr_from_canonical(&g0, &slot->v[0]) || !hfr_from_canonical(&g1, &slot->v[1]) ||
-            !hfr_from_canonical(&gm, &slot->v[2]) || !hfr_from_canonical(&ginf, &slot->v[3]))
+        if (!hfr_from_canonical(&g0, &slot->v[0]) || !hfr_from_canonical(&gm, &slot->v[1]) ||
+            !hfr_from_canonical(&ginf, &slot->v[2]) || (full && !hfr_from_canonical(&g1, &slot->v[3])))
             return GKR_ERR_INTERNAL;
+        if (!full) {
+            g1 = hfr_sub(claim, g0);
+        } else if (j > 0 && !hfr_eq(hfr_add(g0, g1), claim)) {
+            set_last_error("sumcheck claim mismatch at round %u", j);
+            return GKR_ERR_INTERNAL;
+        }
         // g(X) = c3 X^3 + c2 X^2 + c1 X + c0 from g(0), g(1), g(-1), c3
         const HFr c0 = g0, c3 = ginf;
         const HFr c2 = hfr_sub(hfr_mul(hfr_add(g1, gm), inv2), c0);
@@ -854,6 +972,7 @@ extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_var
         msg_len[j] = (uint8_t)len;
         GKR_TRY(challenge_for(ctx, t, src, len, &r));
         hfr_to_canonical(&chal[j], r);
+        claim = hfr_add(hfr_mul(hfr_add(hfr_mul(hfr_add(hfr_mul(c3, r), c2), r), c1), r), c0);   // g(r)
         if (last && final_vals)
             for (int i = 0; i < 3; ++i) hfr_to_canonical(&final_vals[i], hfr_add(lo[i], hfr_mul(r, hfr_sub(hi[i], lo[i]))));
     }

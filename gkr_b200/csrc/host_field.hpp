@@ -73,35 +73,33 @@ inline HFr hfr_sub(const HFr &a, const HFr &b) {
 }
 inline HFr hfr_neg(const HFr &a) { return hfr_sub(hfr_zero(), a); }
 
-// Montgomery product: product scanning into an 8-limb buffer, then 4 reduction sweeps
+// Montgomery product, "no-carry" interleaved CIOS: the two carry chains (a*b_i and m*p) advance together
+// and no fifth limb is needed because the top limb of p is below 2^63 - 1.  Inputs < p, output < p.
+namespace hf {
+inline void mac(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t &hi, uint64_t &lo) {
+    const u128 r = (u128)a * b + c + d;
+    lo = (uint64_t)r;
+    hi = (uint64_t)(r >> 64);
+}
+}  // namespace hf
 inline HFr hfr_mul(const HFr &a, const HFr &b) {
-    using hf::u128;
-    uint64_t t[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     for (int i = 0; i < 4; ++i) {
-        uint64_t carry = 0;
-        for (int j = 0; j < 4; ++j) {
-            u128 cur = (u128)a.l[i] * b.l[j] + t[i + j] + carry;
-            t[i + j] = (uint64_t)cur;
-            carry = (uint64_t)(cur >> 64);
-        }
-        t[i + 4] = carry;
+        const uint64_t bi = b.l[i];
+        uint64_t A, C, lo;
+        hf::mac(a.l[0], bi, t0, 0, A, t0);
+        const uint64_t m = t0 * hf::NINV;
+        hf::mac(m, hf::P[0], t0, 0, C, lo);
+        hf::mac(a.l[1], bi, t1, A, A, t1);
+        hf::mac(m, hf::P[1], t1, C, C, t0);
+        hf::mac(a.l[2], bi, t2, A, A, t2);
+        hf::mac(m, hf::P[2], t2, C, C, t1);
+        hf::mac(a.l[3], bi, t3, A, A, t3);
+        hf::mac(m, hf::P[3], t3, C, C, t2);
+        t3 = C + A;
     }
-    for (int i = 0; i < 4; ++i) {
-        const uint64_t m = t[i] * hf::NINV;
-        uint64_t carry = 0;
-        for (int j = 0; j < 4; ++j) {
-            u128 cur = (u128)m * hf::P[j] + t[i + j] + carry;
-            t[i + j] = (uint64_t)cur;
-            carry = (uint64_t)(cur >> 64);
-        }
-        for (int j = i + 4; carry && j < 9; ++j) {
-            u128 cur = (u128)t[j] + carry;
-            t[j] = (uint64_t)cur;
-            carry = (uint64_t)(cur >> 64);
-        }
-    }
-    HFr r{{t[4], t[5], t[6], t[7]}};
-    if (t[8] || hf::geq_p(r.l)) hf::sub_p(r.l);
+    HFr r{{t0, t1, t2, t3}};
+    if (hf::geq_p(r.l)) hf::sub_p(r.l);
     return r;
 }
 inline HFr hfr_sqr(const HFr &a) { return hfr_mul(a, a); }

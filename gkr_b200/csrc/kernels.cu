@@ -307,19 +307,31 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 
 // ------------------------------------------------------------------------------------------------
 // GKR sumcheck round, degree 2:  g(X) = sum_i (H_lo + X dH)(W_lo + X dW) + (A_lo + X dA)
-//   X0 = g(0) = sum H_lo W_lo + A_lo ;  X1 = g(1) = sum H_hi W_hi + A_hi ;  X2 = sum dH dW
+//   X0 = g(0) = sum H_lo W_lo + A_lo ;  X2 = sum dH dW ;  X1 = g(1) = sum H_hi W_hi + A_hi
 //   message = [X2, X1 - X0 - X2, X0]  (rust/src/gkr/sumcheck.rs:80-85,125-130 build the same coefficients)
-// FOLD: fold-by-r of the previous round fused with this round's evaluation (each table crosses HBM once)
+// FOLD: fold-by-r of the previous round fused with this round's evaluation (each table crosses HBM once).
+// FULL: also accumulate X1; otherwise the host derives g(1) = claim - g(0) from the running claim
+//       (g_j(0) + g_j(1) = g_{j-1}(r_{j-1}) holds identically for the honest prover, so values are equal).
+// LAZY: products are accumulated as exact 512-bit integers and reduced once per thread.
+// Published: v[0] = X0, v[1] = X2, v[2] = X1 (FULL only).
 // ------------------------------------------------------------------------------------------------
-template <bool FOLD>
-__global__ void __launch_bounds__(kThreads) k_gkr_round(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
-                                                        const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
-                                                        Fr *__restrict__ Wout, Fr *__restrict__ Aout, Fr r,
-                                                        uint64_t q, Fr *partials, unsigned int *counter,
-                                                        HostSlot *slot, uint32_t seq) {
-    Fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
+template <bool FOLD, bool FULL, bool LAZY>
+__global__ void __launch_bounds__(kThreads, 2) k_gkr_round(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+                                                           const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
+                                                           Fr *__restrict__ Wout, Fr *__restrict__ Aout, Fr r,
+                                                           uint64_t q, Fr *partials, unsigned int *counter,
+                                                           HostSlot *slot, uint32_t seq) {
+    constexpr int K = FULL ? 3 : 2;
+    Fr acc[K];
+    FrWide wide[LAZY ? K : 1];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = fr_zero();
+    if (LAZY) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) wide_zero(wide[j]);
+    }
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < q; i += (uint64_t)gridDim.x * blockDim.x) {
-        Fr wl, wh, hl, hh, al, ah;
+        Fr wl, wh, hl, hh;
         if (FOLD) {
             wl = fold2(ld_fr(Win + i), ld_fr(Win + i + 2 * q), r);
             wh = fold2(ld_fr(Win + i + q), ld_fr(Win + i + 3 * q), r);
@@ -329,77 +341,155 @@ __global__ void __launch_bounds__(kThreads) k_gkr_round(const Fr *__restrict__ H
             hh = fold2(ld_fr(Hin + i + q), ld_fr(Hin + i + 3 * q), r);
             st_fr(Hout + i, hl);
             st_fr(Hout + i + q, hh);
+        } else {
+            wl = ld_fr(Win + i); wh = ld_fr(Win + i + q);
+            hl = ld_fr(Hin + i); hh = ld_fr(Hin + i + q);
+        }
+        if (LAZY) {
+            wide_mac(wide[0], hl, wl);
+            if (FULL) wide_mac(wide[K - 1], hh, wh);
+            wide_mac(wide[1], fr_sub(hh, hl), fr_sub(wh, wl));
+        } else {
+            acc[0] = fr_add(acc[0], fr_mul(hl, wl));
+            if (FULL) acc[K - 1] = fr_add(acc[K - 1], fr_mul(hh, wh));
+            acc[1] = fr_add(acc[1], fr_mul(fr_sub(hh, hl), fr_sub(wh, wl)));
+        }
+        Fr al, ah;
+        if (FOLD) {
             al = fold2(ld_fr(Ain + i), ld_fr(Ain + i + 2 * q), r);
             ah = fold2(ld_fr(Ain + i + q), ld_fr(Ain + i + 3 * q), r);
             st_fr(Aout + i, al);
             st_fr(Aout + i + q, ah);
         } else {
-            wl = ld_fr(Win + i); wh = ld_fr(Win + i + q);
-            hl = ld_fr(Hin + i); hh = ld_fr(Hin + i + q);
-            al = ld_fr(Ain + i); ah = ld_fr(Ain + i + q);
+            al = ld_fr(Ain + i);
+            if (FULL) ah = ld_fr(Ain + i + q);
         }
-        acc[0] = fr_add(acc[0], fr_add(fr_mul(hl, wl), al));
-        acc[1] = fr_add(acc[1], fr_add(fr_mul(hh, wh), ah));
-        acc[2] = fr_add(acc[2], fr_mul(fr_sub(hh, hl), fr_sub(wh, wl)));
+        acc[0] = fr_add(acc[0], al);
+        if (FULL) acc[K - 1] = fr_add(acc[K - 1], ah);
     }
-    grid_sum_publish<3>(acc, partials, counter, slot, seq, 0u);
+    if (LAZY) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = fr_add(acc[j], wide_reduce(wide[j]));
+    }
+    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u);
 }
-void launch_gkr_round(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const Fr &r,
-                      uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
-    const int grid = grid_for(pairs, ws.max_blocks);
-    if (fold)
-        k_gkr_round<true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
+
+// lazy accumulation pays once a thread sees several pairs: fewer, fatter CTAs (2 resident per SM)
+static inline bool use_lazy(uint64_t pairs) { return pairs >= ((uint64_t)1 << 18); }
+static inline int round_grid(uint64_t pairs, const ReduceWs &ws) {
+    const int cap = use_lazy(pairs) ? device_sm_count() * 2 : ws.max_blocks;
+    return grid_for(pairs, cap < ws.max_blocks ? cap : ws.max_blocks);
+}
+
+template <bool FOLD, bool FULL>
+static void launch_gkr_round_t(const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const Fr &r,
+                               uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    const int grid = round_grid(pairs, ws);
+    if (use_lazy(pairs))
+        k_gkr_round<FOLD, FULL, true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
     else
-        k_gkr_round<false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
+        k_gkr_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
+}
+void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
+                      const Fr &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    if (fold) {
+        if (full) launch_gkr_round_t<true, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
+        else launch_gkr_round_t<true, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
+    } else {
+        if (full) launch_gkr_round_t<false, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
+        else launch_gkr_round_t<false, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// product-of-three sumcheck round, degree 3 (generic prove_sumcheck, rust/src/gkr/sumcheck.rs:158-214):
-// publishes g(0), g(1), g(-1) and g(inf) = X^3 coefficient; the host interpolates the coefficients.
+// product-of-three sumcheck round, degree 3 (generic prove_sumcheck, rust/src/gkr/sumcheck.rs:158-214).
+// Published: v[0] = g(0), v[1] = g(-1), v[2] = g(inf) = X^3 coefficient, v[3] = g(1) (FULL only; otherwise
+// the host uses g(1) = claim - g(0)).  The host interpolates the four coefficients.
 // ------------------------------------------------------------------------------------------------
-template <bool FOLD>
-__global__ void __launch_bounds__(kThreads) k_prod3_round(const Fr *__restrict__ Ain, const Fr *__restrict__ Bin,
-                                                          const Fr *__restrict__ Cin, Fr *__restrict__ Aout,
-                                                          Fr *__restrict__ Bout, Fr *__restrict__ Cout, Fr r,
-                                                          uint64_t q, Fr *partials, unsigned int *counter,
-                                                          HostSlot *slot, uint32_t seq) {
-    Fr acc[4] = {fr_zero(), fr_zero(), fr_zero(), fr_zero()};
+template <bool FOLD, bool FULL, bool LAZY>
+__global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restrict__ Ain, const Fr *__restrict__ Bin,
+                                                             const Fr *__restrict__ Cin, Fr *__restrict__ Aout,
+                                                             Fr *__restrict__ Bout, Fr *__restrict__ Cout, Fr r,
+                                                             uint64_t q, Fr *partials, unsigned int *counter,
+                                                             HostSlot *slot, uint32_t seq) {
+    constexpr int K = FULL ? 4 : 3;
+    Fr acc[K];
+    FrWide wide[LAZY ? K : 1];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = fr_zero();
+    if (LAZY) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) wide_zero(wide[j]);
+    }
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < q; i += (uint64_t)gridDim.x * blockDim.x) {
-        Fr a0, a1, b0, b1, c0, c1;
+        Fr t0, tm, tinf, t1;
+        {
+            Fr a0, a1, b0, b1;
+            if (FOLD) {
+                a0 = fold2(ld_fr(Ain + i), ld_fr(Ain + i + 2 * q), r);
+                a1 = fold2(ld_fr(Ain + i + q), ld_fr(Ain + i + 3 * q), r);
+                st_fr(Aout + i, a0);
+                st_fr(Aout + i + q, a1);
+                b0 = fold2(ld_fr(Bin + i), ld_fr(Bin + i + 2 * q), r);
+                b1 = fold2(ld_fr(Bin + i + q), ld_fr(Bin + i + 3 * q), r);
+                st_fr(Bout + i, b0);
+                st_fr(Bout + i + q, b1);
+            } else {
+                a0 = ld_fr(Ain + i); a1 = ld_fr(Ain + i + q);
+                b0 = ld_fr(Bin + i); b1 = ld_fr(Bin + i + q);
+            }
+            t0 = fr_mul(a0, b0);
+            if (FULL) t1 = fr_mul(a1, b1);
+            const Fr da = fr_sub(a1, a0), db = fr_sub(b1, b0);
+            tinf = fr_mul(da, db);
+            tm = fr_mul(fr_sub(a0, da), fr_sub(b0, db));          // value at X = -1 : lo - d
+        }
+        Fr c0, c1;
         if (FOLD) {
-            a0 = fold2(ld_fr(Ain + i), ld_fr(Ain + i + 2 * q), r);
-            a1 = fold2(ld_fr(Ain + i + q), ld_fr(Ain + i + 3 * q), r);
-            st_fr(Aout + i, a0);
-            st_fr(Aout + i + q, a1);
-            b0 = fold2(ld_fr(Bin + i), ld_fr(Bin + i + 2 * q), r);
-            b1 = fold2(ld_fr(Bin + i + q), ld_fr(Bin + i + 3 * q), r);
-            st_fr(Bout + i, b0);
-            st_fr(Bout + i + q, b1);
             c0 = fold2(ld_fr(Cin + i), ld_fr(Cin + i + 2 * q), r);
             c1 = fold2(ld_fr(Cin + i + q), ld_fr(Cin + i + 3 * q), r);
             st_fr(Cout + i, c0);
             st_fr(Cout + i + q, c1);
         } else {
-            a0 = ld_fr(Ain + i); a1 = ld_fr(Ain + i + q);
-            b0 = ld_fr(Bin + i); b1 = ld_fr(Bin + i + q);
             c0 = ld_fr(Cin + i); c1 = ld_fr(Cin + i + q);
         }
-        acc[0] = fr_add(acc[0], fr_mul(fr_mul(a0, b0), c0));
-        acc[1] = fr_add(acc[1], fr_mul(fr_mul(a1, b1), c1));
-        const Fr da = fr_sub(a1, a0), db = fr_sub(b1, b0), dc = fr_sub(c1, c0);
-        acc[3] = fr_add(acc[3], fr_mul(fr_mul(da, db), dc));
-        // value at X = -1 : lo - d
-        acc[2] = fr_add(acc[2], fr_mul(fr_mul(fr_sub(a0, da), fr_sub(b0, db)), fr_sub(c0, dc)));
+        const Fr dc = fr_sub(c1, c0);
+        if (LAZY) {
+            wide_mac(wide[0], t0, c0);
+            wide_mac(wide[1], tm, fr_sub(c0, dc));
+            wide_mac(wide[2], tinf, dc);
+            if (FULL) wide_mac(wide[K - 1], t1, c1);
+        } else {
+            acc[0] = fr_add(acc[0], fr_mul(t0, c0));
+            acc[1] = fr_add(acc[1], fr_mul(tm, fr_sub(c0, dc)));
+            acc[2] = fr_add(acc[2], fr_mul(tinf, dc));
+            if (FULL) acc[K - 1] = fr_add(acc[K - 1], fr_mul(t1, c1));
+        }
     }
-    grid_sum_publish<4>(acc, partials, counter, slot, seq, 0u);
+    if (LAZY) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = wide_reduce(wide[j]);
+    }
+    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u);
 }
-void launch_prod3_round(bool fold, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const Fr &r,
-                        uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
-    const int grid = grid_for(pairs, ws.max_blocks);
-    if (fold)
-        k_prod3_round<true><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq);
+template <bool FOLD, bool FULL>
+static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const Fr &r,
+                                 uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    const int grid = round_grid(pairs, ws);
+    if (use_lazy(pairs))
+        k_prod3_round<FOLD, FULL, true><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq);
     else
-        k_prod3_round<false><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq);
+        k_prod3_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq);
+}
+void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
+                        const Fr &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    if (fold) {
+        if (full) launch_prod3_round_t<true, true>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, s);
+        else launch_prod3_round_t<true, false>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, s);
+    } else {
+        if (full) launch_prod3_round_t<false, true>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, s);
+        else launch_prod3_round_t<false, false>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, s);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) k_fold(const Fr *__restrict__ in, Fr *__restrict__ out, Fr r, uint64_t half) {
@@ -571,6 +661,47 @@ __global__ void __launch_bounds__(kThreads) k_line_fold(const Fr *__restrict__ c
 }
 void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const Fr &b, const Fr &g, cudaStream_t s) {
     k_line_fold<<<stream_grid(cnt / 2), kThreads, 0, s>>>(cur, nxt, cnt, deg, b, g);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// integer-pipe ceiling: back-to-back Montgomery products, ILP independent chains per thread
+// ------------------------------------------------------------------------------------------------
+template <int ILP>
+__global__ void __launch_bounds__(kThreads) k_mul_bench(Fr *out, int iters) {
+    Fr x[ILP], y = fr_one();
+    y.l[0] ^= threadIdx.x * 2654435761u;
+    y.l[3] ^= blockIdx.x;
+#pragma unroll
+    for (int j = 0; j < ILP; ++j) { x[j] = y; x[j].l[1] += j + 1; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < ILP; ++j) x[j] = fr_mul(x[j], y);
+    }
+    Fr acc = x[0];
+#pragma unroll
+    for (int j = 1; j < ILP; ++j) acc = fr_add(acc, x[j]);
+    if (acc.l[7] == 0xffffffffu) st_fr(out + (blockIdx.x * (size_t)blockDim.x + threadIdx.x), acc);   // never true: values < p
+}
+double run_mul_bench(int ilp, int blocks_per_sm, int iters, Fr *scratch, cudaStream_t s) {
+    const int grid = device_sm_count() * blocks_per_sm;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0, s);
+        if (ilp == 1) k_mul_bench<1><<<grid, kThreads, 0, s>>>(scratch, iters);
+        else if (ilp == 2) k_mul_bench<2><<<grid, kThreads, 0, s>>>(scratch, iters);
+        else k_mul_bench<4><<<grid, kThreads, 0, s>>>(scratch, iters);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const int eff_ilp = ilp == 1 ? 1 : ilp == 2 ? 2 : 4;
+    return (double)grid * kThreads * eff_ilp * (double)iters / (ms * 1e-3);
 }
 
 }  // namespace gkr

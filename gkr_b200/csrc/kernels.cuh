@@ -51,15 +51,17 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
                           const Fr *eqz, const Fr *equ, const Fr *wu, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
 
 // ---- sumcheck rounds --------------------------------------------------------------------------
-// GKR round (degree 2) on (H, W, A).  Publishes X0 = g(0), X1 = g(1), X2 = coefficient of X^2.
+// GKR round (degree 2) on (H, W, A).  Publishes v[0] = g(0), v[1] = X^2 coefficient, and v[2] = g(1)
+// when full == true; with full == false the host derives g(1) from the running claim.
 // fold == false: tables have 2*pairs entries, no output tables.
 // fold == true : tables have 4*pairs entries; first folds them with r (writing 2*pairs entries to
 //                Hout/Wout/Aout), then evaluates the round polynomial of the folded tables -- one pass.
-void launch_gkr_round(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
+void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
                       const Fr &r_mont, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
                       cudaStream_t s);
-// product-of-3 round (degree 3).  Publishes g(0), g(1), g(-1), g(inf) (= X^3 coefficient).
-void launch_prod3_round(bool fold, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
+// product-of-3 round (degree 3).  Publishes v[0] = g(0), v[1] = g(-1), v[2] = g(inf) (= X^3 coefficient) and
+// v[3] = g(1) when full == true.
+void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
                         const Fr &r_mont, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
                         cudaStream_t s);
 // plain fold out[i] = in[i] + r (in[i+half] - in[i])
@@ -84,5 +86,7 @@ void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const 
                       cudaStream_t s);
 
 int device_sm_count();
+// field multiplications per second with `ilp` independent chains per thread and blocks_per_sm CTAs of 256 threads
+double run_mul_bench(int ilp, int blocks_per_sm, int iters, Fr *scratch, cudaStream_t s);
 
 }  // namespace gkr

@@ -77,11 +77,17 @@ inline HFr to_host(const Fr &f) {
     return h;
 }
 
+// process-wide pool of pinned host buffers (proof tables are handed to the caller in pinned memory so
+// the device can write them asynchronously; cudaHostAlloc is far too slow to call per proof)
+void *pinned_get(size_t bytes);
+void pinned_put(void *ptr, size_t bytes);
+
 }  // namespace gkr
 
 struct gkr_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;         // latency-critical round kernels (high priority)
+    cudaStream_t aux = nullptr;            // bulk work off the critical path: Moebius of d/input_func, q_i line folds, D2H
     static constexpr int kSlots = 64;
     gkr::HostSlot *slots_host = nullptr;   // pinned + mapped
     gkr::HostSlot *slots_dev = nullptr;
@@ -92,10 +98,11 @@ struct gkr_ctx {
     size_t pinned_elems = 0;
 
     // workspaces
-    gkr::DevBuf eqz, equ, eq_scratch, H, A, foldA, foldB, lineA, lineB, mob, misc, stage;
+    gkr::DevBuf eqz, equ, eq_scratch, H, A, foldA, foldB, lineA, lineB, mob, misc, stage, aux_mob, aux_stage, qdev;
 
     // accounting
     gkr_stats stats{};
+    bool paranoid = false;                 // accumulate g(1) on the device in every round and check the claim chain
     bool profiling = false;
     gkr_profile prof{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -109,13 +116,13 @@ struct gkr_ctx {
         return GKR_OK;
     }
     // bracket one launch for accounting / profiling
-    void begin_launch() {
-        if (profiling) cudaEventRecord(ev0, stream);
+    void begin_launch(cudaStream_t st = nullptr) {
+        if (profiling) cudaEventRecord(ev0, st ? st : stream);
     }
-    void end_launch(gkr::KernelClass kc, double algo_bytes, int n_kernels = 1) {
+    void end_launch(gkr::KernelClass kc, double algo_bytes, int n_kernels = 1, cudaStream_t st = nullptr) {
         stats.kernel_launches += (uint64_t)n_kernels;
         if (profiling) {
-            cudaEventRecord(ev1, stream);
+            cudaEventRecord(ev1, st ? st : stream);
             cudaEventSynchronize(ev1);
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev0, ev1);

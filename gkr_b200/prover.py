@@ -130,6 +130,9 @@ class Prover:
         """raw cudaStream_t of this context (wrap with torch.cuda.ExternalStream to record events on it)"""
         return int(self._L.gkr_ctx_stream(self._ctx) or 0)
 
+    def set_option(self, name: str, value: int):
+        _lib.check(self._L.gkr_ctx_set_option(self._ctx, name.encode(), int(value)))
+
     def sync(self):
         _lib.check(self._L.gkr_ctx_sync(self._ctx))
 
@@ -279,6 +282,12 @@ class Prover:
         s = _lib.Stats()
         _lib.check(self._L.gkr_ctx_stats(self._ctx, C.byref(s), 1 if reset else 0))
         return {f: getattr(s, f) for f, _ in s._fields_}
+
+    def bench_field_mul(self, ilp: int = 4, blocks_per_sm: int = 2, iters: int = 2000) -> float:
+        """Montgomery products per second in a register-resident loop (integer-pipe ceiling of the device)"""
+        out = C.c_double()
+        _lib.check(self._L.gkr_bench_field_mul(self._ctx, ilp, blocks_per_sm, iters, C.byref(out)))
+        return out.value
 
     def profile(self, enable: int = -1) -> dict:
         """enable = 1 / 0 switches per-kernel CUDA-event timing on / off (and clears the counters);

@@ -54,6 +54,9 @@ typedef struct gkr_witness gkr_witness;
 /* ---- context ------------------------------------------------------------------------------- */
 int gkr_ctx_create(int device, gkr_ctx **out);
 void gkr_ctx_destroy(gkr_ctx *ctx);
+/* options: "paranoid" = 1 makes every round also accumulate g(1) on the device and checks
+ * g_j(0) + g_j(1) == g_{j-1}(r_{j-1}) on the host (default 0: g(1) is derived from the running claim) */
+int gkr_ctx_set_option(gkr_ctx *ctx, const char *name, int value);
 /* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
 void *gkr_ctx_stream(gkr_ctx *ctx);
 /* block until all work enqueued by this context has finished */
@@ -163,6 +166,9 @@ typedef struct {
     double algo_bytes[GKR_N_KERNEL_CLASSES];   /* algorithmic bytes moved (reads + writes of table entries) */
 } gkr_profile;
 int gkr_ctx_profile(gkr_ctx *ctx, int enable, gkr_profile *out);
+/* integer-pipe ceiling of this device: Montgomery products per second in a register-resident loop
+ * (ilp = 1, 2 or 4 independent chains per thread; blocks_per_sm CTAs of 256 threads per SM) */
+int gkr_bench_field_mul(gkr_ctx *ctx, int ilp, int blocks_per_sm, int iters, double *mul_per_second);
 
 #ifdef __cplusplus
 }

@@ -21,3 +21,18 @@ extern "C" int frh_binop(int op, const unsigned char *a, const unsigned char *b,
     }
     return 0;
 }
+
+// sum_i a_i*b_i through the lazy accumulator, compared by the test with the Montgomery-product sum
+extern "C" int frh_dot(const unsigned char *a, const unsigned char *b, unsigned char *out, unsigned long n) {
+    FrWide acc;
+    wide_zero(acc);
+    for (unsigned long i = 0; i < n; ++i) {
+        Fr x, y;
+        std::memcpy(x.l, a + 32 * i, 32);
+        std::memcpy(y.l, b + 32 * i, 32);
+        wide_mac(acc, fr_to_mont(x), fr_to_mont(y));
+    }
+    Fr r = fr_from_mont(wide_reduce(acc));
+    std::memcpy(out, r.l, 32);
+    return 0;
+}

@@ -50,3 +50,20 @@ def test_noncanonical_rejected():
     out = np.zeros_like(A)
     assert lib.frh_binop(0, A.ctypes.data_as(C.c_void_p), A.ctypes.data_as(C.c_void_p),
                          out.ctypes.data_as(C.c_void_p), C.c_ulong(1)) == -1
+
+
+def test_lazy_accumulation_matches_bigint():
+    """wide_mac / wide_reduce (unreduced 512-bit accumulation) == sum of products mod p"""
+    lib = _lib()
+    rng = random.Random(2)
+    for n in (1, 2, 7, 300, 2000):
+        a = [rng.randrange(P) for _ in range(n)]
+        b = [rng.randrange(P) for _ in range(n)]
+        if n == 300:
+            a = [P - 1] * n
+            b = [P - 1] * n
+        A, B = orc.to_bytes(a), orc.to_bytes(b)
+        out = np.zeros((1, 32), np.uint8)
+        assert lib.frh_dot(A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                           C.c_ulong(n)) == 0
+        assert orc.from_bytes(out)[0] == sum(x * y for x, y in zip(a, b)) % P

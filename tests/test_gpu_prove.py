@@ -87,6 +87,31 @@ def test_degenerate_shapes_mid_size(pv):
         assert_same_dense(want, got)
 
 
+def test_paranoid_mode_matches_claim_derivation(pv):
+    """default mode derives g(1) from the running claim; paranoid mode accumulates it on the device and checks
+    the claim chain -- both must give the same proof (k = 19 also exercises the lazy 512-bit accumulators)"""
+    from gkr_b200 import Prover
+    pp = Prover(0)
+    pp.set_option("paranoid", 1)
+    rng = random.Random(123)
+    for ks in ([3, 4, 3], [9, 10, 9]):
+        layers = random_circuit(rng, ks, "mixed")
+        inputs = [rng.randrange(P) for _ in range(1 << ks[-1])]
+        assert_same_dense(_gpu_prove(pv, layers, inputs), _gpu_prove(pp, layers, inputs))
+    layers = syn.layered_circuit(3, 19, 2)
+    inputs = syn.input_values(3, 19)
+    proofs = []
+    for prover in (pv, pp):
+        c = prover.circuit(layers)
+        w = prover.witness_eval(c, inputs)
+        proofs.append(prover.prove(c, w))
+    assert_same_dense(proofs[0], proofs[1])
+    ol = [orc.DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in layers]
+    vals = orc.evaluate_circuit(ol, inputs.view(np.uint8).reshape(-1, 32))
+    assert_same_dense(orc.gkr_prove(ol, vals), proofs[0])
+    pp.close()
+
+
 def test_custom_transcript_callback(pv):
     """the challenge callback (how a Rust host keeps mimc_rs) must see the same messages and drive the same proof"""
     rng = random.Random(5)

@@ -74,6 +74,20 @@ def test_device_resident_synthetic_tables_2p20(pv):
     assert all(len(m) == 4 for m in got[0])
 
 
+def test_paranoid_mode_and_lazy_path(pv):
+    """2^21 entries: rounds 1-3 run the lazy-accumulation kernels; paranoid mode recomputes g(1) on the device"""
+    from gkr_b200 import Prover
+    pp = Prover(0)
+    pp.set_option("paranoid", 1)
+    v, seed = 21, 2
+    host = [orc.synth_values(seed, syn.TABLE_STREAM + t, 1 << v) for t in range(3)]
+    want = orc.sumcheck_prod(host, v)
+    for prover in (pv, pp):
+        tabs = [prover.dev_table_synth(seed, syn.TABLE_STREAM + t, 1 << v) for t in range(3)]
+        assert prover.sumcheck_prod(tabs, v) == want
+    pp.close()
+
+
 def test_rejects_unsupported(pv):
     from gkr_b200._lib import GkrError
     t = ints_to_fr([1, 2])
