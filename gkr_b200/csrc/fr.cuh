@@ -429,6 +429,65 @@ FR_HD Fr wide_reduce(const FrWide &acc) {
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// multiplication by a kernel-wide constant r (the round challenge): with the host-precomputed plain
+// integers C_j = r * 2^(32 j + 64) mod p,   sum_j d_j C_j == r * d * 2^64 (mod p)  and two single-limb
+// Montgomery steps remove the 2^64.  64 + 16 wide multiplies instead of 128 (+8) for fr_mul.
+// Input d: any Montgomery-form value < p; output: Montgomery form of r*d, < p.
+// ------------------------------------------------------------------------------------------------
+struct FrConstMul {
+    uint32_t c[8][8];
+};
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void fr_merge9(uint32_t (&t)[10], const uint32_t (&e)[9], const uint32_t (&o)[10]) {
+    t[0] = e[0];
+    asm("add.cc.u32  %0, %9,  %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32    %8, %25, 0;"
+        : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(t[8]), "=r"(t[9])
+        : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]),
+          "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]));
+}
+#else
+inline void fr_merge9(uint32_t (&t)[10], const uint32_t (&e)[9], const uint32_t (&o)[10]) {
+    t[0] = e[0];
+    uint64_t c = 0;
+    for (int i = 1; i <= 8; ++i) { c += (uint64_t)e[i] + o[i]; t[i] = (uint32_t)c; c >>= 32; }
+    t[9] = o[9] + (uint32_t)c;
+}
+#endif
+FR_HD Fr fr_mul_const(const Fr &d, const FrConstMul &K) {
+    uint32_t e[9], o[10];          // e: columns 0..7 + carries at 8 ; o: columns 1..8 + carries at 9
+#pragma unroll
+    for (int i = 0; i < 9; ++i) e[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) o[i] = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        fr_row_lo(e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], e[8], K.c[j][0], K.c[j][2], K.c[j][4], K.c[j][6], d.l[j]);
+        fr_row_lo(o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], K.c[j][1], K.c[j][3], K.c[j][5], K.c[j][7], d.l[j]);
+    }
+    uint32_t t[10];
+    fr_merge9(t, e, o);            // < 2^35 p
+    const uint32_t m1 = t[0] * frc::INV;
+    fr_row_lo(t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], frc::P0, frc::P2, frc::P4, frc::P6, m1);
+    fr_row_lo(t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9], frc::P1, frc::P3, frc::P5, frc::P7, m1);
+    const uint32_t m2 = t[1] * frc::INV;      // t[0] == 0 now; value / 2^32 < 9p
+    fr_row_lo(t[1], t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9], frc::P0, frc::P2, frc::P4, frc::P6, m2);
+    fr_row_hi(t[2], t[3], t[4], t[5], t[6], t[7], t[8], t[9], frc::P1, frc::P3, frc::P5, frc::P7, m2);
+    Fr r;                           // t[1] == 0; value / 2^64 < 2p
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.l[i] = t[2 + i];
+    fr_cond_sub_p(r.l);
+    return r;
+}
+
 // canonical (plain little-endian value < p) <-> Montgomery
 FR_HD Fr fr_to_mont(const Fr &canonical) { return fr_mul(canonical, fr_r2()); }
 FR_HD Fr fr_from_mont(const Fr &a) {

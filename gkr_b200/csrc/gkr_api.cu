@@ -34,6 +34,22 @@ void set_last_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+FrConstMul make_const_mul(const HFr &r) {
+    static HFr pow2[8];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        HFr x = hfr_one();                       // Montgomery form of 1
+        for (int i = 0; i < 64; ++i) x = hfr_add(x, x);
+        for (int j = 0; j < 8; ++j) {
+            pow2[j] = x;                         // Montgomery form of 2^(32 j + 64)
+            for (int i = 0; i < 32; ++i) x = hfr_add(x, x);
+        }
+    });
+    FrConstMul K;
+    for (int j = 0; j < 8; ++j) hfr_to_canonical(K.c[j], hfr_mul(r, pow2[j]));
+    return K;
+}
+
 namespace {
 std::mutex g_pool_mu;
 std::multimap<size_t, void *> g_pool;
@@ -557,9 +573,10 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
     for (uint32_t j = 0; j < k; ++j) {
         const uint32_t s = ctx->next_seq();
         const bool full = !have_claim || ctx->paranoid;
+        const FrConstMul rc = j ? make_const_mul(r) : FrConstMul{};
         ctx->begin_launch();
         if (j == 0) {
-            launch_gkr_round(false, full, Hc, Wc, Ac, nullptr, nullptr, nullptr, to_dev(r), n / 2, ctx->ws, ctx->slot_dev(s),
+            launch_gkr_round(false, full, Hc, Wc, Ac, nullptr, nullptr, nullptr, rc, n / 2, ctx->ws, ctx->slot_dev(s),
                              s, ctx->stream);
             ctx->end_launch(KC_ROUND, (full ? 96.0 : 80.0) * n);
         } else {
@@ -567,7 +584,7 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
             DevBuf &dst = (j & 1) ? ctx->foldA : ctx->foldB;
             const uint64_t half = n / 2;
             Fr *Ho = dst.as<Fr>(), *Wo = Ho + half, *Ao = Wo + half;
-            launch_gkr_round(true, full, Hc, Wc, Ac, Ho, Wo, Ao, to_dev(r), half / 2, ctx->ws, ctx->slot_dev(s), s,
+            launch_gkr_round(true, full, Hc, Wc, Ac, Ho, Wo, Ao, rc, half / 2, ctx->ws, ctx->slot_dev(s), s,
                              ctx->stream);
             ctx->end_launch(KC_ROUND_FUSED, 96.0 * n + 96.0 * half);
             Hc = Ho; Wc = Wo; Ac = Ao;
@@ -739,7 +756,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         GKR_TRY(run_phase(ctx, t, io, &last_hash, nullptr, &claim));
         // W(u): fold the last size-2 W table with r_k
         ctx->begin_launch();
-        launch_fold(io.W_last, wu, to_dev(rs[k - 1]), 1, ctx->stream);
+        launch_fold(io.W_last, wu, make_const_mul(rs[k - 1]), 1, ctx->stream);
         ctx->end_launch(KC_OTHER, 96.0);
         GKR_TRY(ctx->check_launch("fold"));
 
@@ -762,7 +779,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
                 Fr *nxt = (j & 1) ? ctx->lineB.as<Fr>() : ctx->lineA.as<Fr>();
                 const HFr g = hfr_sub(rs[k + j], rs[j]);
                 ctx->begin_launch(ctx->aux);
-                launch_line_fold(cur, nxt, cnt, j, to_dev(rs[j]), to_dev(g), ctx->aux);
+                launch_line_fold(cur, nxt, cnt, j, make_const_mul(rs[j]), make_const_mul(g), ctx->aux);
                 ctx->end_launch(KC_LINE, 32.0 * (double)(cnt * (j + 1)) + 32.0 * (double)(cnt / 2 * (j + 2)), 1, ctx->aux);
                 GKR_TRY(ctx->check_launch("line_fold"));
                 cur = nxt;
@@ -889,16 +906,17 @@ extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_var
     for (uint32_t j = 0; j < n_vars; ++j) {
         const uint32_t s = ctx->next_seq();
         const bool full = (j == 0) || ctx->paranoid;     // the first claim (the sum itself) is not known in advance
+        const FrConstMul rc = j ? make_const_mul(r) : FrConstMul{};
         ctx->begin_launch();
         if (j == 0) {
-            launch_prod3_round(false, full, Ac, Bc, Cc, nullptr, nullptr, nullptr, to_dev(r), n / 2, ctx->ws,
+            launch_prod3_round(false, full, Ac, Bc, Cc, nullptr, nullptr, nullptr, rc, n / 2, ctx->ws,
                                ctx->slot_dev(s), s, ctx->stream);
             ctx->end_launch(KC_PROD3, 96.0 * n);
         } else {
             DevBuf &dst = (j & 1) ? ctx->foldA : ctx->foldB;
             const uint64_t half = n / 2;
             Fr *Ao = dst.as<Fr>(), *Bo = Ao + half, *Co = Bo + half;
-            launch_prod3_round(true, full, Ac, Bc, Cc, Ao, Bo, Co, to_dev(r), half / 2, ctx->ws, ctx->slot_dev(s), s,
+            launch_prod3_round(true, full, Ac, Bc, Cc, Ao, Bo, Co, rc, half / 2, ctx->ws, ctx->slot_dev(s), s,
                                ctx->stream);
             ctx->end_launch(KC_PROD3_FUSED, 96.0 * n + 96.0 * half);
             Ac = Ao; Bc = Bo; Cc = Co;
@@ -1051,7 +1069,7 @@ extern "C" int gkr_line_restrict(gkr_ctx *ctx, const gkr_fr *values, uint32_t k,
         if (!hfr_from_canonical(&bj, &b[j]) || !hfr_from_canonical(&cj, &c[j])) return GKR_ERR_RANGE;
         Fr *nxt = (j & 1) ? ctx->lineB.as<Fr>() : ctx->lineA.as<Fr>();
         ctx->begin_launch();
-        launch_line_fold(cur, nxt, cnt, j, to_dev(bj), to_dev(hfr_sub(cj, bj)), ctx->stream);
+        launch_line_fold(cur, nxt, cnt, j, make_const_mul(bj), make_const_mul(hfr_sub(cj, bj)), ctx->stream);
         ctx->end_launch(KC_LINE, 32.0 * (double)(cnt * (j + 1)) + 32.0 * (double)(cnt / 2 * (j + 2)));
         GKR_TRY(ctx->check_launch("line_fold"));
         cur = nxt;

@@ -37,9 +37,9 @@ __device__ __forceinline__ void st_fr(Fr *p, const Fr &v) {
     q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
-// lo + r * (hi - lo)
-__device__ __forceinline__ Fr fold2(const Fr &lo, const Fr &hi, const Fr &r) {
-    return fr_add(lo, fr_mul(r, fr_sub(hi, lo)));
+// lo + r * (hi - lo), r given by its constant-multiplier table (kernel parameter => constant bank operands)
+__device__ __forceinline__ Fr fold2(const Fr &lo, const Fr &hi, const FrConstMul &r) {
+    return fr_add(lo, fr_mul_const(fr_sub(hi, lo), r));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -318,7 +318,7 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 template <bool FOLD, bool FULL, bool LAZY>
 __global__ void __launch_bounds__(kThreads, 2) k_gkr_round(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
                                                            const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
-                                                           Fr *__restrict__ Wout, Fr *__restrict__ Aout, Fr r,
+                                                           Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
                                                            uint64_t q, Fr *partials, unsigned int *counter,
                                                            HostSlot *slot, uint32_t seq) {
     constexpr int K = FULL ? 3 : 2;
@@ -382,7 +382,7 @@ static inline int round_grid(uint64_t pairs, const ReduceWs &ws) {
 }
 
 template <bool FOLD, bool FULL>
-static void launch_gkr_round_t(const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const Fr &r,
+static void launch_gkr_round_t(const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
                                uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
     const int grid = round_grid(pairs, ws);
     if (use_lazy(pairs))
@@ -391,7 +391,7 @@ static void launch_gkr_round_t(const Fr *H, const Fr *W, const Fr *A, Fr *Hout, 
         k_gkr_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
 }
 void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
-                      const Fr &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+                      const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
     if (fold) {
         if (full) launch_gkr_round_t<true, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
         else launch_gkr_round_t<true, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
@@ -409,7 +409,7 @@ void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *
 template <bool FOLD, bool FULL, bool LAZY>
 __global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restrict__ Ain, const Fr *__restrict__ Bin,
                                                              const Fr *__restrict__ Cin, Fr *__restrict__ Aout,
-                                                             Fr *__restrict__ Bout, Fr *__restrict__ Cout, Fr r,
+                                                             Fr *__restrict__ Bout, Fr *__restrict__ Cout, FrConstMul r,
                                                              uint64_t q, Fr *partials, unsigned int *counter,
                                                              HostSlot *slot, uint32_t seq) {
     constexpr int K = FULL ? 4 : 3;
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restric
     grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u);
 }
 template <bool FOLD, bool FULL>
-static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const Fr &r,
+static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const FrConstMul &r,
                                  uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
     const int grid = round_grid(pairs, ws);
     if (use_lazy(pairs))
@@ -482,7 +482,7 @@ static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout
         k_prod3_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq);
 }
 void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
-                        const Fr &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+                        const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
     if (fold) {
         if (full) launch_prod3_round_t<true, true>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, s);
         else launch_prod3_round_t<true, false>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, s);
@@ -492,11 +492,11 @@ void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_fold(const Fr *__restrict__ in, Fr *__restrict__ out, Fr r, uint64_t half) {
+__global__ void __launch_bounds__(kThreads) k_fold(const Fr *__restrict__ in, Fr *__restrict__ out, FrConstMul r, uint64_t half) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < half; i += (uint64_t)gridDim.x * blockDim.x)
         st_fr(out + i, fold2(ld_fr(in + i), ld_fr(in + i + half), r));
 }
-void launch_fold(const Fr *in, Fr *out, const Fr &r, uint64_t half, cudaStream_t s) {
+void launch_fold(const Fr *in, Fr *out, const FrConstMul &r, uint64_t half, cudaStream_t s) {
     k_fold<<<stream_grid(half), kThreads, 0, s>>>(in, out, r, half);
 }
 
@@ -646,20 +646,20 @@ void launch_table_flags(const Fr *T, uint64_t n, unsigned int *words, HostSlot *
 //   new(t) = lo(t) + (b + g t)(hi(t) - lo(t))
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_line_fold(const Fr *__restrict__ cur, Fr *__restrict__ nxt, uint64_t cnt,
-                                                        uint32_t deg, Fr b, Fr g) {
+                                                        uint32_t deg, FrConstMul b, FrConstMul g) {
     const uint64_t half = cnt / 2;
     for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e < half; e += (uint64_t)gridDim.x * blockDim.x) {
         Fr carry = fr_zero();
         for (uint32_t d = 0; d <= deg; ++d) {
             const Fr lo = ld_fr(cur + (size_t)d * cnt + e), hi = ld_fr(cur + (size_t)d * cnt + e + half);
             const Fr df = fr_sub(hi, lo);
-            st_fr(nxt + (size_t)d * half + e, fr_add(fr_add(lo, fr_mul(b, df)), carry));
-            carry = fr_mul(g, df);
+            st_fr(nxt + (size_t)d * half + e, fr_add(fr_add(lo, fr_mul_const(df, b)), carry));
+            carry = fr_mul_const(df, g);
         }
         st_fr(nxt + (size_t)(deg + 1) * half + e, carry);
     }
 }
-void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const Fr &b, const Fr &g, cudaStream_t s) {
+void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const FrConstMul &b, const FrConstMul &g, cudaStream_t s) {
     k_line_fold<<<stream_grid(cnt / 2), kThreads, 0, s>>>(cur, nxt, cnt, deg, b, g);
 }
 

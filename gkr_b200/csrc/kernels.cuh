@@ -57,15 +57,15 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 // fold == true : tables have 4*pairs entries; first folds them with r (writing 2*pairs entries to
 //                Hout/Wout/Aout), then evaluates the round polynomial of the folded tables -- one pass.
 void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
-                      const Fr &r_mont, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
+                      const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
                       cudaStream_t s);
 // product-of-3 round (degree 3).  Publishes v[0] = g(0), v[1] = g(-1), v[2] = g(inf) (= X^3 coefficient) and
 // v[3] = g(1) when full == true.
 void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
-                        const Fr &r_mont, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
+                        const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
                         cudaStream_t s);
 // plain fold out[i] = in[i] + r (in[i+half] - in[i])
-void launch_fold(const Fr *in, Fr *out, const Fr &r_mont, uint64_t half, cudaStream_t s);
+void launch_fold(const Fr *in, Fr *out, const FrConstMul &r, uint64_t half, cudaStream_t s);
 // publish up to 6 device values (Montgomery -> canonical) to a slot
 void launch_publish(const Fr *const *ptrs6, int count, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
 
@@ -82,7 +82,7 @@ void launch_table_flags(const Fr *T, uint64_t n, unsigned int *dev_words3, HostS
 
 // ---- line restriction (reduce_multiple_polynomial, rust/src/gkr/poly.rs:469-500) -----------------
 // one level: cnt entries with (deg+1) coefficients each (coefficient-major) -> cnt/2 entries with deg+2
-void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const Fr &b_mont, const Fr &g_mont,
+void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const FrConstMul &b, const FrConstMul &g,
                       cudaStream_t s);
 
 int device_sm_count();

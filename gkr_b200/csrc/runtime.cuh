@@ -71,6 +71,8 @@ inline Fr to_dev(const HFr &h) {      // identical Montgomery representation: pl
     std::memcpy(f.l, h.l, 32);
     return f;
 }
+// constant-multiplier table of r for fr_mul_const: C_j = r * 2^(32 j + 64) mod p as plain integers
+FrConstMul make_const_mul(const HFr &r);
 inline HFr to_host(const Fr &f) {
     HFr h;
     std::memcpy(h.l, f.l, 32);

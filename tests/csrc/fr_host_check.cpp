@@ -36,3 +36,16 @@ extern "C" int frh_dot(const unsigned char *a, const unsigned char *b, unsigned 
     std::memcpy(out, r.l, 32);
     return 0;
 }
+
+// r*d through fr_mul_const with constants C_j = r * 2^(32j+64) mod p supplied by the test (plain integers)
+extern "C" int frh_mul_const(const unsigned char *consts /*8x32*/, const unsigned char *d, unsigned char *out, unsigned long n) {
+    FrConstMul K;
+    std::memcpy(K.c, consts, 256);
+    for (unsigned long i = 0; i < n; ++i) {
+        Fr x;
+        std::memcpy(x.l, d + 32 * i, 32);
+        Fr r = fr_from_mont(fr_mul_const(fr_to_mont(x), K));
+        std::memcpy(out + 32 * i, r.l, 32);
+    }
+    return 0;
+}

@@ -67,3 +67,27 @@ def test_lazy_accumulation_matches_bigint():
         assert lib.frh_dot(A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
                            C.c_ulong(n)) == 0
         assert orc.from_bytes(out)[0] == sum(x * y for x, y in zip(a, b)) % P
+
+
+def test_mul_by_constant_matches_bigint():
+    """fr_mul_const: r*d via the 8 precomputed constants r*2^(32j+64) mod p and two Montgomery steps"""
+    lib = _lib()
+    rng = random.Random(3)
+    for r in [0, 1, P - 1, rng.randrange(P), rng.randrange(P)]:
+        consts = orc.to_bytes([r * pow(2, 32 * j + 64, P) % P for j in range(8)])
+        d = _edge_values() + [rng.randrange(P) for _ in range(500)]
+        D = orc.to_bytes(d)
+        out = np.zeros_like(D)
+        assert lib.frh_mul_const(consts.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p),
+                                 out.ctypes.data_as(C.c_void_p), C.c_ulong(len(d))) == 0
+        assert orc.from_bytes(out) == [r * x % P for x in d]
+    # worst case for the intermediate bounds: every constant and every limb at its maximum
+    consts = orc.to_bytes([P - 1] * 8)      # not of the form r*2^k, the routine only needs C_j < p
+    D = orc.to_bytes([P - 1, (1 << 254) - 1 if (1 << 254) - 1 < P else P - 2])
+    out = np.zeros_like(D)
+    lib.frh_mul_const(consts.ctypes.data_as(C.c_void_p), D.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_ulong(2))
+    R = pow(2, 256, P)
+    for x, got in zip(orc.from_bytes(D), orc.from_bytes(out)):
+        xm = x * R % P
+        want_m = sum(((xm >> (32 * j)) & 0xFFFFFFFF) * (P - 1) for j in range(8)) * pow(2, -64, P) % P
+        assert got == want_m * pow(R, -1, P) % P
