@@ -254,33 +254,80 @@ def run_ours(args):
                         "measurement is the `sumcheck` object (tables larger than L2)",
                 "share_of_device_time": d["ms"] / max(1e-9, sum(x["ms"] for x in prof.values()))}
 
-    # ---- standalone product sumcheck (BASELINE.json config 4 at 1 GPU; tables larger than L2) ----------
+    # ---- standalone product sumcheck (BASELINE.json config 4; tables larger than L2) --------------------------
+    # N = 1: whole tables on one GPU.  N > 1: tables sharded on the low log2(N) index bits, per-round NCCL
+    # all-gather of the partial sums (strong scaling); rank 0 also times the unsharded run for the speed-up.
     sumcheck = None
     if args.sumcheck_vars:
+        from gkr_b200 import dist as gd
+        from gkr_b200._lib import GkrError
         v = args.sumcheck_vars
         N = 1 << v
-        tabs = [pv.dev_table_synth(seed, syn.TABLE_STREAM + t, N) for t in range(3)]
+        sc_seed = 1
 
-        def step_sc():
-            pv.sumcheck_prod_raw(tabs, v)
-        sc_ms = timed(step_sc, args.steps, args.warmup) / args.steps
-        pv.profile(1)
-        step_sc()
-        sp = pv.profile(0)
+        def make_tables(n_loc, first, stride):
+            return [pv.dev_table_synth(sc_seed, syn.TABLE_STREAM + t, n_loc, first=first, stride=stride) for t in range(3)]
+
+        def sc_profile(fn):
+            pv.profile(1)
+            fn()
+            sp = pv.profile(0)
+            kern_ms = sp["prod3_round"]["ms"] + sp["prod3_round_fused"]["ms"]
+            kern_bytes = sp["prod3_round"]["algo_bytes"] + sp["prod3_round_fused"]["algo_bytes"]
+            return {"ms": kern_ms, "gbs": kern_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms else 0.0,
+                    "frac": kern_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak if kern_ms else 0.0,
+                    "first_round_ms": sp["prod3_round"]["ms"],
+                    "first_round_gbs": sp["prod3_round"]["algo_bytes"] / (sp["prod3_round"]["ms"] * 1e-3) / 1e9
+                    if sp["prod3_round"]["ms"] else 0.0}
         algo = 32.0 * 3 * (4 * N - 6)
-        kern_ms = sp["prod3_round"]["ms"] + sp["prod3_round_fused"]["ms"]
-        kern_bytes = sp["prod3_round"]["algo_bytes"] + sp["prod3_round_fused"]["algo_bytes"]
-        sumcheck = {"n_vars": v, "tables": 3, "ms": sc_ms, "melem_s": N / (sc_ms * 1e-3) / 1e6 * world,
-                    "algo_bytes": algo, "gbs_whole_sumcheck": algo / (sc_ms * 1e-3) / 1e9,
-                    "frac_whole_sumcheck": algo / (sc_ms * 1e-3) / 1e9 / hbm_peak,
-                    "round_kernels": {"ms": kern_ms, "gbs": kern_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms else 0.0,
-                                      "frac": kern_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak if kern_ms else 0.0,
-                                      "first_round_ms": sp["prod3_round"]["ms"],
-                                      "first_round_gbs": sp["prod3_round"]["algo_bytes"] / (sp["prod3_round"]["ms"] * 1e-3) / 1e9
-                                      if sp["prod3_round"]["ms"] else 0.0},
-                    "l2": "inputs larger than L2 (3 x %d MiB)" % (N * 32 >> 20)}
-        for t in tabs:
-            t.close()
+        try:
+            if world == 1:
+                tabs = make_tables(N, 0, 1)
+                sc_ms = timed(lambda: pv.sumcheck_prod_raw(tabs, v), args.steps, args.warmup) / args.steps
+                rk = sc_profile(lambda: pv.sumcheck_prod_raw(tabs, v))
+                extra = {}
+            else:
+                gd.init_comm(pv)
+                tabs = make_tables(N // world, rank, world)
+                sc_ms = timed(lambda: pv.sumcheck_prod_sharded_raw(tabs, v), args.steps, args.warmup) / args.steps
+                rk = sc_profile(lambda: pv.sumcheck_prod_sharded_raw(tabs, v))
+                for t in tabs:
+                    t.close()
+                tabs = []
+                single_ms = None
+                if rank == 0:
+                    full = make_tables(N, 0, 1)
+                    for _ in range(2):
+                        pv.sumcheck_prod_raw(full, v)
+                    t0 = torch.cuda.Event(enable_timing=True)
+                    t1 = torch.cuda.Event(enable_timing=True)
+                    t0.record(ext)
+                    for _ in range(args.steps):
+                        pv.sumcheck_prod_raw(full, v)
+                    t1.record(ext)
+                    t1.synchronize()
+                    single_ms = t0.elapsed_time(t1) / args.steps
+                    for t in full:
+                        t.close()
+                barrier()
+                extra = {"sharding": f"low log2({world}) index bits, per-round ncclAllGather of 96-128 B partial sums",
+                         "single_gpu_ms_same_run": single_ms,
+                         "speedup_vs_single_gpu": (single_ms / sc_ms) if single_ms else None}
+            sumcheck = {"n_vars": v, "tables": 3, "n_gpus": world, "ms": sc_ms, "melem_s": N / (sc_ms * 1e-3) / 1e6,
+                        "algo_bytes": algo, "gbs_whole_sumcheck": algo / (sc_ms * 1e-3) / 1e9,
+                        "frac_whole_sumcheck": algo / (sc_ms * 1e-3) / 1e9 / (hbm_peak * world),
+                        "round_kernels_this_rank": rk, "l2": "inputs larger than L2 (3 x %d MiB per rank)" % (N * 32 // world >> 20),
+                        **extra}
+            for t in tabs:
+                t.close()
+        except GkrError as e:
+            sumcheck = {"n_vars": v, "error": str(e)}
+
+    # ---- integer-multiply ceiling of this device (register-resident Montgomery products) ------------------------
+    gmul = pv.bench_field_mul(4, 4, 2000) / 1e9
+    int_roof = {"gmul_per_s": gmul, "unit": "G Montgomery products/s (8x32-bit limbs, IMAD.WIDE)",
+                "note": "IMAD.WIDE issues at 32 lanes/clk/SM; a fused degree-3 round needs ~1095 wide multiplies per 576 B, "
+                        "so the integer pipe, not HBM, bounds the round kernels"}
 
     # ---- CPU baseline on rank 0, N = 1 only -----------------------------------------------------------------
     cpu = None
@@ -306,6 +353,7 @@ def run_ours(args):
                     "note": "pinned input layer -> H2D -> device circuit evaluation -> gkr_prove -> Proof on host"},
             "gpu_launches": int(launches_timed),
             "roofline": roofline, "cpu_baseline": cpu, "sumcheck": sumcheck, "clocks": clock_info,
+            "integer_roofline": int_roof,
             "kernel_classes": {n: {"launches": x["launches"], "ms": round(x["ms"], 4),
                                    "gbs": round(x["algo_bytes"] / (x["ms"] * 1e-3) / 1e9, 1) if x["ms"] else None}
                                for n, x in classes.items()},
@@ -325,7 +373,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--k", type=int, default=20, help="log2 gates per layer (BASELINE config 3: 20)")
     ap.add_argument("--layers", type=int, default=16)
-    ap.add_argument("--sumcheck-vars", type=int, default=24, help="standalone 3-table sumcheck size (0 = skip)")
+    ap.add_argument("--sumcheck-vars", type=int, default=28, help="standalone 3-table sumcheck size (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

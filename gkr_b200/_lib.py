@@ -13,6 +13,7 @@ SO_PATH = os.path.join(_HERE, "libgkr_b200.so")
 _SRC = os.path.join(_HERE, "csrc")
 
 GKR_N_KERNEL_CLASSES = 9
+GKR_COMM_ID_BYTES = 256
 KERNEL_CLASS_NAMES = ["gkr_round", "gkr_round_fused", "prod3_round", "prod3_round_fused", "wiring", "eq",
                       "mobius", "line", "other"]
 STATUS = {0: "GKR_OK", -1: "GKR_ERR_INVALID", -2: "GKR_ERR_CUDA", -3: "GKR_ERR_OOM", -4: "GKR_ERR_RANGE",
@@ -64,7 +65,8 @@ class Profile(C.Structure):
 EXPORTS = [
     "gkr_ctx_create", "gkr_ctx_destroy", "gkr_ctx_stream", "gkr_ctx_sync", "gkr_ctx_set_option", "gkr_last_error", "gkr_version", "gkr_mimc7_multi_hash", "gkr_mimc7_hash",
     "gkr_circuit_create", "gkr_circuit_destroy", "gkr_witness_create", "gkr_witness_eval", "gkr_witness_layer",
-    "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_sumcheck_prod", "gkr_dev_table_synth",
+    "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_sumcheck_prod", "gkr_dev_table_synth", "gkr_dev_table_synth_strided", "gkr_comm_unique_id", "gkr_comm_init", "gkr_comm_destroy",
+    "gkr_sumcheck_prod_sharded",
     "gkr_dev_table_upload", "gkr_dev_table_download", "gkr_dev_table_free", "gkr_fr_binop", "gkr_eq_table",
     "gkr_mobius", "gkr_line_restrict", "gkr_ctx_stats", "gkr_ctx_profile", "gkr_bench_field_mul",
 ]
@@ -114,6 +116,12 @@ def lib():
     L.gkr_proof_free.restype = None
     L.gkr_sumcheck_prod.argtypes = [vp, u32, u32, C.POINTER(vp), i32, C.POINTER(Transcript), vp, vp, vp, vp]
     L.gkr_dev_table_synth.argtypes = [vp, u64, u64, u64, C.POINTER(vp)]
+    L.gkr_dev_table_synth_strided.argtypes = [vp, u64, u64, u64, u64, u64, C.POINTER(vp)]
+    L.gkr_comm_unique_id.argtypes = [vp]
+    L.gkr_comm_init.argtypes = [vp, i32, i32, vp]
+    L.gkr_comm_destroy.argtypes = [vp]
+    L.gkr_comm_destroy.restype = None
+    L.gkr_sumcheck_prod_sharded.argtypes = [vp, u32, u32, C.POINTER(vp), C.POINTER(Transcript), vp, vp, vp, vp]
     L.gkr_dev_table_upload.argtypes = [vp, vp, u64, C.POINTER(vp)]
     L.gkr_dev_table_download.argtypes = [vp, vp, u64, vp]
     L.gkr_dev_table_free.argtypes = [vp, vp]

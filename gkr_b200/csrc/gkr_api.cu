@@ -159,9 +159,11 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     return GKR_OK;
 }
 
+extern "C" void gkr_comm_destroy(gkr_ctx *ctx);
 extern "C" void gkr_ctx_destroy(gkr_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    gkr_comm_destroy(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->aux) cudaStreamSynchronize(ctx->aux);
     for (DevBuf *b : {&ctx->eqz, &ctx->equ, &ctx->eq_scratch, &ctx->H, &ctx->A, &ctx->foldA, &ctx->foldB, &ctx->lineA,
@@ -826,7 +828,8 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
 // ------------------------------------------------------------------------------------------------
 // standalone product sumcheck (BASELINE.json config 4)
 // ------------------------------------------------------------------------------------------------
-extern "C" int gkr_dev_table_synth(gkr_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t n, void **out) {
+extern "C" int gkr_dev_table_synth_strided(gkr_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t first, uint64_t stride,
+                                           uint64_t n, void **out) {
     if (!ctx || !out || n == 0) return GKR_ERR_INVALID;
     GKR_TRY(ctx->bind());
     Fr *p = nullptr;
@@ -837,13 +840,16 @@ extern "C" int gkr_dev_table_synth(gkr_ctx *ctx, uint64_t seed, uint64_t stream,
         return e == cudaErrorMemoryAllocation ? GKR_ERR_OOM : GKR_ERR_CUDA;
     }
     ctx->begin_launch();
-    launch_synth_values(seed, stream, 0, n, p, ctx->stream);
+    launch_synth_values(seed, stream, first, stride, n, p, ctx->stream);
     ctx->end_launch(KC_OTHER, 32.0 * n);
     int rc = ctx->check_launch("synth_values");
     if (rc == GKR_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = GKR_ERR_CUDA;
     if (rc != GKR_OK) { cudaFree(p); return rc; }
     *out = p;
     return GKR_OK;
+}
+extern "C" int gkr_dev_table_synth(gkr_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t n, void **out) {
+    return gkr_dev_table_synth_strided(ctx, seed, stream, 0, 1, n, out);
 }
 extern "C" int gkr_dev_table_upload(gkr_ctx *ctx, const gkr_fr *host, uint64_t n, void **out) {
     if (!ctx || !out || !host || n == 0) return GKR_ERR_INVALID;
@@ -866,63 +872,78 @@ extern "C" void gkr_dev_table_free(gkr_ctx *ctx, void *dev) {
     cudaFree(dev);
 }
 
-extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_vars, const void *const *tables,
-                                 int on_device, const gkr_transcript *t, gkr_fr *msgs, uint8_t *msg_len, gkr_fr *chal,
-                                 gkr_fr *final_vals) {
-    if (!ctx || !tables || !msgs || !msg_len || !chal) return GKR_ERR_INVALID;
-    if (n_tables != 3) {
-        set_last_error("gkr_sumcheck_prod: only products of 3 tables are implemented (got %u)", n_tables);
-        return GKR_ERR_INVALID;
-    }
-    if (n_vars < 2 || n_vars > 32) {
-        set_last_error("gkr_sumcheck_prod: n_vars=%u outside 2..32 (v=1 is broken in the reference, sumcheck.rs:167)", n_vars);
-        return GKR_ERR_INVALID;
-    }
-    GKR_TRY(ctx->bind());
-    const uint64_t N = (uint64_t)1 << n_vars;
-    const Fr *T[3];
-    Fr *owned[3] = {nullptr, nullptr, nullptr};
-    struct Cleanup {
-        Fr **p;
-        ~Cleanup() { for (int i = 0; i < 3; ++i) if (p[i]) cudaFree(p[i]); }
-    } cleanup{owned};
-    for (int i = 0; i < 3; ++i) {
-        if (!tables[i]) return GKR_ERR_INVALID;
-        if (on_device) {
-            T[i] = static_cast<const Fr *>(tables[i]);
-        } else {
-            GKR_CUDA_TRY(cudaMalloc((void **)&owned[i], N * sizeof(Fr)));
-            GKR_TRY(upload_table(ctx, static_cast<const gkr_fr *>(tables[i]), N, owned[i]));
-            T[i] = owned[i];
-        }
-    }
-    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 2, 2)));
-    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 4, 2)));
+// Shared driver of the product sumcheck.  T[i]: device tables holding this rank's shard (the whole table
+// when n_ranks == 1), 2^(n_vars - log2 n_ranks) entries each.
+static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3], const gkr_transcript *t, gkr_fr *msgs,
+                             uint8_t *msg_len, gkr_fr *chal, gkr_fr *final_vals) {
+    const int P = ctx->nccl_comm ? ctx->n_ranks : 1;
+    uint32_t lb = 0;
+    while ((1 << lb) < P) ++lb;
+    const uint32_t local_vars = n_vars - lb;
+    const uint64_t Nloc = (uint64_t)1 << local_vars;
+    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(Nloc / 2, 64)));
+    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(Nloc / 4, 64)));
+    GKR_TRY(ctx->misc.ensure(sizeof(Fr) * (64 + 3 * (size_t)P)));
     const HFr inv2 = hfr_inv(hfr_from_u64(2));
     const Fr *Ac = T[0], *Bc = T[1], *Cc = T[2];
-    uint64_t n = N;
+    uint64_t n = Nloc;                 // entries per current table on this rank
+    bool pending_fold = false;         // the next round kernel still has to fold the current tables with r
+    int flip = 0;                      // ping-pong between foldA / foldB
     HFr r = hfr_zero();
     HFr claim = hfr_zero();
     for (uint32_t j = 0; j < n_vars; ++j) {
+        const bool sharded_round = P > 1 && j < local_vars;
+        if (P > 1 && j == local_vars) {
+            // every rank is down to 2 entries per table: fold them with r, gather the single entries of all
+            // ranks and continue on the P-entry tables (entry index = rank = the low index bits)
+            const FrConstMul rc = make_const_mul(r);
+            Fr *one = ctx->comm_send;
+            const Fr *cur[3] = {Ac, Bc, Cc};
+            for (int i = 0; i < 3; ++i) {
+                ctx->begin_launch();
+                launch_fold(cur[i], one + i, rc, 1, ctx->stream);
+                ctx->end_launch(KC_OTHER, 96.0);
+                GKR_TRY(ctx->check_launch("fold"));
+            }
+            GKR_TRY(comm_all_gather(ctx, one, ctx->comm_recv, 3 * sizeof(Fr)));
+            Fr *mini = ctx->misc.as<Fr>() + 8;                     // misc holds >= 64 entries: 8 + 3 * P <= 32
+            ctx->begin_launch();
+            launch_transpose_gathered(ctx->comm_recv, mini, P, 3, ctx->stream);
+            ctx->end_launch(KC_OTHER, 192.0 * P);
+            GKR_TRY(ctx->check_launch("transpose_gathered"));
+            Ac = mini; Bc = mini + P; Cc = mini + 2 * P;
+            n = (uint64_t)P;
+            pending_fold = false;
+        }
         const uint32_t s = ctx->next_seq();
         const bool full = (j == 0) || ctx->paranoid;     // the first claim (the sum itself) is not known in advance
-        const FrConstMul rc = j ? make_const_mul(r) : FrConstMul{};
+        const FrConstMul rc = pending_fold ? make_const_mul(r) : FrConstMul{};
+        Fr *dev_out = sharded_round ? ctx->comm_send : nullptr;
         ctx->begin_launch();
-        if (j == 0) {
-            launch_prod3_round(false, full, Ac, Bc, Cc, nullptr, nullptr, nullptr, rc, n / 2, ctx->ws,
-                               ctx->slot_dev(s), s, ctx->stream);
+        if (!pending_fold) {
+            launch_prod3_round(false, full, Ac, Bc, Cc, nullptr, nullptr, nullptr, rc, n / 2, ctx->ws, ctx->slot_dev(s), s,
+                               ctx->stream, dev_out);
             ctx->end_launch(KC_PROD3, 96.0 * n);
         } else {
-            DevBuf &dst = (j & 1) ? ctx->foldA : ctx->foldB;
+            DevBuf &dst = (flip ^= 1) ? ctx->foldA : ctx->foldB;
             const uint64_t half = n / 2;
             Fr *Ao = dst.as<Fr>(), *Bo = Ao + half, *Co = Bo + half;
-            launch_prod3_round(true, full, Ac, Bc, Cc, Ao, Bo, Co, rc, half / 2, ctx->ws, ctx->slot_dev(s), s,
-                               ctx->stream);
+            launch_prod3_round(true, full, Ac, Bc, Cc, Ao, Bo, Co, rc, half / 2, ctx->ws, ctx->slot_dev(s), s, ctx->stream,
+                               dev_out);
             ctx->end_launch(KC_PROD3_FUSED, 96.0 * n + 96.0 * half);
             Ac = Ao; Bc = Bo; Cc = Co;
             n = half;
         }
         GKR_TRY(ctx->check_launch("prod3_round"));
+        if (sharded_round) {
+            const int K = full ? 4 : 3;
+            GKR_TRY(comm_all_gather(ctx, ctx->comm_send, ctx->comm_recv, (size_t)K * sizeof(Fr)));
+            ctx->begin_launch();
+            launch_sum_ranks_publish(ctx->comm_recv, P, K, ctx->slot_dev(s), s, ctx->stream);
+            ctx->end_launch(KC_OTHER, 32.0 * K * P);
+            GKR_TRY(ctx->check_launch("sum_ranks_publish"));
+        }
+        pending_fold = true;
         const HostSlot *slot;
         GKR_TRY(ctx->wait_slot(s, &slot));
         HFr g0, g1, gm, ginf;
@@ -968,10 +989,15 @@ extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_var
                 bool nonzero = !(hfr_is_zero(lo[i]) && hfr_is_zero(hi[i]));
                 if (!dep || !nonzero) {
                     // ambiguous from the folded values alone: decide exactly on the original table
+                    if (P > 1) {
+                        set_last_error("degenerate table %d (constant in the last variable or zero): the exact static "
+                                       "message length needs neighbouring shards; use the single-GPU entry point", i);
+                        return GKR_ERR_INVALID;
+                    }
                     const uint32_t s3 = ctx->next_seq();
                     ctx->begin_launch();
-                    launch_table_flags(T[i], N, ctx->words + 4, ctx->slot_dev(s3), s3, ctx->stream);
-                    ctx->end_launch(KC_OTHER, 32.0 * N, 2);
+                    launch_table_flags(T[i], Nloc, ctx->words + 4, ctx->slot_dev(s3), s3, ctx->stream);
+                    ctx->end_launch(KC_OTHER, 32.0 * Nloc, 2);
                     GKR_TRY(ctx->check_launch("table_flags"));
                     const HostSlot *fl;
                     GKR_TRY(ctx->wait_slot(s3, &fl));
@@ -996,6 +1022,67 @@ extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_var
     }
     GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return GKR_OK;
+}
+
+extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_vars, const void *const *tables,
+                                 int on_device, const gkr_transcript *t, gkr_fr *msgs, uint8_t *msg_len, gkr_fr *chal,
+                                 gkr_fr *final_vals) {
+    if (!ctx || !tables || !msgs || !msg_len || !chal) return GKR_ERR_INVALID;
+    if (n_tables != 3) {
+        set_last_error("gkr_sumcheck_prod: only products of 3 tables are implemented (got %u)", n_tables);
+        return GKR_ERR_INVALID;
+    }
+    if (n_vars < 2 || n_vars > 32) {
+        set_last_error("gkr_sumcheck_prod: n_vars=%u outside 2..32 (v=1 is broken in the reference, sumcheck.rs:167)", n_vars);
+        return GKR_ERR_INVALID;
+    }
+    GKR_TRY(ctx->bind());
+    const uint64_t N = (uint64_t)1 << n_vars;
+    const Fr *T[3];
+    Fr *owned[3] = {nullptr, nullptr, nullptr};
+    struct Cleanup {
+        Fr **p;
+        ~Cleanup() { for (int i = 0; i < 3; ++i) if (p[i]) cudaFree(p[i]); }
+    } cleanup{owned};
+    for (int i = 0; i < 3; ++i) {
+        if (!tables[i]) return GKR_ERR_INVALID;
+        if (on_device) {
+            T[i] = static_cast<const Fr *>(tables[i]);
+        } else {
+            GKR_CUDA_TRY(cudaMalloc((void **)&owned[i], N * sizeof(Fr)));
+            GKR_TRY(upload_table(ctx, static_cast<const gkr_fr *>(tables[i]), N, owned[i]));
+            T[i] = owned[i];
+        }
+    }
+    // the single-GPU entry point ignores a communicator that may be attached to the context
+    void *saved = ctx->nccl_comm;
+    ctx->nccl_comm = nullptr;
+    const int rc = sumcheck_prod_run(ctx, n_vars, T, t, msgs, msg_len, chal, final_vals);
+    ctx->nccl_comm = saved;
+    return rc;
+}
+
+extern "C" int gkr_sumcheck_prod_sharded(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_vars, const void *const *local_tables,
+                                         const gkr_transcript *t, gkr_fr *msgs, uint8_t *msg_len, gkr_fr *chal,
+                                         gkr_fr *final_vals) {
+    if (!ctx || !local_tables || !msgs || !msg_len || !chal) return GKR_ERR_INVALID;
+    if (!ctx->nccl_comm) {
+        set_last_error("gkr_sumcheck_prod_sharded: call gkr_comm_init first");
+        return GKR_ERR_COMM;
+    }
+    uint32_t lb = 0;
+    while ((1 << lb) < ctx->n_ranks) ++lb;
+    if (n_tables != 3 || n_vars < 2 || n_vars > 34 || n_vars < lb + 1 || n_vars - lb > 32) {
+        set_last_error("gkr_sumcheck_prod_sharded: need 3 tables and log2(n_ranks)+1 <= n_vars <= 34");
+        return GKR_ERR_INVALID;
+    }
+    GKR_TRY(ctx->bind());
+    const Fr *T[3];
+    for (int i = 0; i < 3; ++i) {
+        if (!local_tables[i]) return GKR_ERR_INVALID;
+        T[i] = static_cast<const Fr *>(local_tables[i]);
+    }
+    return sumcheck_prod_run(ctx, n_vars, T, t, msgs, msg_len, chal, final_vals);
 }
 
 // ------------------------------------------------------------------------------------------------

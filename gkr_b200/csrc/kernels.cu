@@ -77,9 +77,11 @@ __device__ __forceinline__ void block_sum(Fr (&acc)[K], Fr (*smem)[kWarps]) {
 }
 
 // Grid-wide sum of K accumulators; the last CTA to arrive publishes the canonical totals.
+// If dev_out != nullptr (multi-GPU: the totals still have to be combined across ranks) the last CTA
+// stores the Montgomery totals there and nothing is published to the host.
 template <int K>
 __device__ __forceinline__ void grid_sum_publish(Fr (&acc)[K], Fr *partials, unsigned int *counter,
-                                                 HostSlot *slot, uint32_t seq, uint32_t aux0) {
+                                                 HostSlot *slot, uint32_t seq, uint32_t aux0, Fr *dev_out = nullptr) {
     __shared__ Fr red[K][kWarps];
     __shared__ bool is_last;
     block_sum<K>(acc, red);
@@ -100,6 +102,12 @@ __device__ __forceinline__ void grid_sum_publish(Fr (&acc)[K], Fr *partials, uns
         for (int j = 0; j < K; ++j) acc[j] = fr_add(acc[j], ld_fr_cg(&partials[(size_t)b * K + j]));
     }
     block_sum<K>(acc, red);
+    if (threadIdx.x == 0 && dev_out != nullptr) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) st_fr(&dev_out[j], acc[j]);
+        *counter = 0;
+        return;
+    }
     if (threadIdx.x == 0) {
         uint32_t nz = 0;
 #pragma unroll
@@ -167,11 +175,11 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 __global__ void __launch_bounds__(kThreads) k_synth_values(uint64_t seed, uint64_t stream_id, uint64_t first,
-                                                           uint64_t n, Fr *__restrict__ out) {
+                                                           uint64_t stride, uint64_t n, Fr *__restrict__ out) {
     const uint64_t G = 0x9E3779B97F4A7C15ULL;
     const uint64_t h0 = mix64(seed + G * (stream_id + 1));
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t h1 = mix64(h0 + G * (first + i + 1));
+        const uint64_t h1 = mix64(h0 + G * (first + i * stride + 1));
         Fr v;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -184,9 +192,10 @@ __global__ void __launch_bounds__(kThreads) k_synth_values(uint64_t seed, uint64
         st_fr(out + i, fr_to_mont(v));
     }
 }
-void launch_synth_values(uint64_t seed, uint64_t stream_id, uint64_t first, uint64_t n, Fr *out, cudaStream_t s) {
+void launch_synth_values(uint64_t seed, uint64_t stream_id, uint64_t first, uint64_t stride, uint64_t n, Fr *out,
+                         cudaStream_t s) {
     if (n == 0) return;
-    k_synth_values<<<stream_grid(n), kThreads, 0, s>>>(seed, stream_id, first, n, out);
+    k_synth_values<<<stream_grid(n), kThreads, 0, s>>>(seed, stream_id, first, stride, n, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -411,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restric
                                                              const Fr *__restrict__ Cin, Fr *__restrict__ Aout,
                                                              Fr *__restrict__ Bout, Fr *__restrict__ Cout, FrConstMul r,
                                                              uint64_t q, Fr *partials, unsigned int *counter,
-                                                             HostSlot *slot, uint32_t seq) {
+                                                             HostSlot *slot, uint32_t seq, Fr *dev_out) {
     constexpr int K = FULL ? 4 : 3;
     Fr acc[K];
     FrWide wide[LAZY ? K : 1];
@@ -470,26 +479,59 @@ __global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restric
 #pragma unroll
         for (int j = 0; j < K; ++j) acc[j] = wide_reduce(wide[j]);
     }
-    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u);
+    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, dev_out);
 }
 template <bool FOLD, bool FULL>
 static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const FrConstMul &r,
-                                 uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+                                 uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, Fr *dev_out,
+                                 cudaStream_t s) {
     const int grid = round_grid(pairs, ws);
     if (use_lazy(pairs))
-        k_prod3_round<FOLD, FULL, true><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq);
+        k_prod3_round<FOLD, FULL, true><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq, dev_out);
     else
-        k_prod3_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq);
+        k_prod3_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq, dev_out);
 }
 void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
-                        const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+                        const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s,
+                        Fr *dev_out) {
     if (fold) {
-        if (full) launch_prod3_round_t<true, true>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, s);
-        else launch_prod3_round_t<true, false>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, s);
+        if (full) launch_prod3_round_t<true, true>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, dev_out, s);
+        else launch_prod3_round_t<true, false>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, dev_out, s);
     } else {
-        if (full) launch_prod3_round_t<false, true>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, s);
-        else launch_prod3_round_t<false, false>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, s);
+        if (full) launch_prod3_round_t<false, true>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, dev_out, s);
+        else launch_prod3_round_t<false, false>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, dev_out, s);
     }
+}
+
+// multi-GPU: every rank contributed `count` Montgomery partial sums (rank-major in `gathered`); add them up
+// (exact modular sums => identical on every rank) and publish the canonical totals to the host slot
+__global__ void k_sum_ranks_publish(const Fr *__restrict__ gathered, int n_ranks, int count, HostSlot *slot, uint32_t seq) {
+    const int j = threadIdx.x;
+    if (j < count) {
+        Fr acc = fr_zero();
+        for (int rk = 0; rk < n_ranks; ++rk) acc = fr_add(acc, ld_fr_cg(gathered + (size_t)rk * count + j));
+        st_fr(&slot->v[j], fr_from_mont(acc));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        slot->seq = seq;
+    }
+}
+void launch_sum_ranks_publish(const Fr *gathered, int n_ranks, int count, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    k_sum_ranks_publish<<<1, 32, 0, s>>>(gathered, n_ranks, count, slot, seq);
+}
+// multi-GPU tail: gathered[rank][table] (one fully folded entry per rank and table) -> n_tables contiguous
+// tables of n_ranks entries (entry index = rank = the low index bits the tables were sharded on)
+__global__ void k_transpose_gathered(const Fr *__restrict__ gathered, Fr *__restrict__ out, int n_ranks, int n_tables) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_ranks * n_tables) {
+        const int t = i / n_ranks, rk = i % n_ranks;
+        st_fr(out + i, ld_fr_cg(gathered + (size_t)rk * n_tables + t));
+    }
+}
+void launch_transpose_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_tables, cudaStream_t s) {
+    k_transpose_gathered<<<1, 64, 0, s>>>(gathered, out, n_ranks, n_tables);
 }
 
 __global__ void __launch_bounds__(kThreads) k_fold(const Fr *__restrict__ in, Fr *__restrict__ out, FrConstMul r, uint64_t half) {

@@ -32,7 +32,9 @@ struct ReduceWs {
 // ---- conversions / generators ------------------------------------------------------------------
 void launch_to_mont(const Fr *in, Fr *out, uint64_t n, unsigned int *err_flag, cudaStream_t s);
 void launch_from_mont(const Fr *in, Fr *out, uint64_t n, cudaStream_t s);
-void launch_synth_values(uint64_t seed, uint64_t stream_id, uint64_t first, uint64_t n, Fr *out_mont, cudaStream_t s);
+// element i of the output is element (first + i * stride) of the stream
+void launch_synth_values(uint64_t seed, uint64_t stream_id, uint64_t first, uint64_t stride, uint64_t n, Fr *out_mont,
+                         cudaStream_t s);
 
 // ---- circuit evaluation (rust/src/convert.rs:812-830) -----------------------------------------
 void launch_layer_eval(const uint8_t *type, const uint32_t *left, const uint32_t *right, const Fr *in, Fr *out,
@@ -63,7 +65,10 @@ void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *
 // v[3] = g(1) when full == true.
 void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
                         const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
-                        cudaStream_t s);
+                        cudaStream_t s, Fr *dev_out = nullptr);
+// multi-GPU: sum the per-rank partial totals (rank-major, Montgomery) and publish; gathered final entries -> tables
+void launch_sum_ranks_publish(const Fr *gathered, int n_ranks, int count, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
+void launch_transpose_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_tables, cudaStream_t s);
 // plain fold out[i] = in[i] + r (in[i+half] - in[i])
 void launch_fold(const Fr *in, Fr *out, const FrConstMul &r, uint64_t half, cudaStream_t s);
 // publish up to 6 device values (Montgomery -> canonical) to a slot

@@ -14,6 +14,8 @@
 #include "host_field.hpp"
 #include "kernels.cuh"
 
+struct gkr_ctx;
+
 namespace gkr {
 
 void set_last_error(const char *fmt, ...);
@@ -81,6 +83,7 @@ inline HFr to_host(const Fr &f) {
 
 // process-wide pool of pinned host buffers (proof tables are handed to the caller in pinned memory so
 // the device can write them asynchronously; cudaHostAlloc is far too slow to call per proof)
+int comm_all_gather(gkr_ctx *ctx, const void *send, void *recv, size_t bytes);   // on ctx->stream
 void *pinned_get(size_t bytes);
 void pinned_put(void *ptr, size_t bytes);
 
@@ -98,6 +101,11 @@ struct gkr_ctx {
     unsigned int *words = nullptr;         // [8] device words: [0] range-error flag, [4..6] support/flags scratch
     gkr_fr *pinned = nullptr;              // small pinned staging (q coefficients, flags)
     size_t pinned_elems = 0;
+
+    // multi-GPU (comm.cpp): NCCL communicator, this rank, staging for the per-round partial sums
+    void *nccl_comm = nullptr;
+    int n_ranks = 1, rank = 0;
+    Fr *comm_send = nullptr, *comm_recv = nullptr;
 
     // workspaces
     gkr::DevBuf eqz, equ, eq_scratch, H, A, foldA, foldB, lineA, lineB, mob, misc, stage, aux_mob, aux_stage, qdev;

@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), `torch.distributed` for the bootstrap, NCCL inside
+the CUDA library for the per-round exchange of the table-sharded sumcheck (csrc/comm.cpp).
+
+Two ways the prover path scales:
+  * independent proofs (sub-circuits of one input -- rust/src/aggregator.rs:352-355 proves them under
+    `par_iter` -- or batches of inputs) are dealt round-robin to the ranks: no data-path collective;
+  * one large sumcheck is split on the variables bound LAST (the low log2(P) index bits, because rounds bind
+    the most significant index bit first): rank p holds entries idx = i*P + p.  Each round every rank
+    reduces its shard, the 96-128 byte partial sums are all-gathered and added modulo p on every rank.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+
+
+def world():
+    """(rank, world_size, local_rank) from the torchrun environment"""
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def assign_round_robin(n_items: int, rank: int, world_size: int) -> list:
+    """indices of the independent proofs this rank owns"""
+    return list(range(rank, n_items, world_size))
+
+
+def shard_table(values: np.ndarray, rank: int, world_size: int) -> np.ndarray:
+    """host helper: the shard of a full table that rank `rank` holds (entries idx = i*P + rank)"""
+    return np.ascontiguousarray(values[rank::world_size])
+
+
+def unshard_tables(shards) -> np.ndarray:
+    """inverse of shard_table over all ranks"""
+    P = len(shards)
+    out = np.empty((shards[0].shape[0] * P,) + shards[0].shape[1:], dtype=shards[0].dtype)
+    for r, s in enumerate(shards):
+        out[r::P] = s
+    return out
+
+
+def broadcast_bytes(payload: bytes | None, n: int, src: int = 0) -> bytes:
+    """ship `n` bytes from rank `src` to every rank over the default torch.distributed group"""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.zeros(n, dtype=torch.uint8, device=dev)
+    if dist.get_rank() == src:
+        t.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(t, src=src)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def max_over_ranks(value: float) -> float:
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def init_comm(prover) -> None:
+    """create the library's NCCL communicator on `prover` (collective over the default process group)"""
+    import torch.distributed as dist
+    L = _lib.lib()
+    rank, ws = dist.get_rank(), dist.get_world_size()
+    buf = (C.c_uint8 * _lib.GKR_COMM_ID_BYTES)()
+    if rank == 0:
+        _lib.check(L.gkr_comm_unique_id(buf))
+    ident = broadcast_bytes(bytes(buf) if rank == 0 else None, _lib.GKR_COMM_ID_BYTES, 0)
+    arr = (C.c_uint8 * _lib.GKR_COMM_ID_BYTES).from_buffer_copy(ident)
+    _lib.check(L.gkr_comm_init(prover._ctx, ws, rank, arr))

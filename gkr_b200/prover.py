@@ -213,9 +213,10 @@ class Prover:
             self.free_raw(ptr)
 
     # ---- standalone product sumcheck -------------------------------------------------------------------
-    def dev_table_synth(self, seed: int, stream: int, n: int) -> DevTable:
+    def dev_table_synth(self, seed: int, stream: int, n: int, first: int = 0, stride: int = 1) -> DevTable:
+        """n elements of the synthetic stream, element i = stream element first + i*stride (device resident)"""
         out = C.c_void_p()
-        _lib.check(self._L.gkr_dev_table_synth(self._ctx, seed, stream, n, C.byref(out)))
+        _lib.check(self._L.gkr_dev_table_synth_strided(self._ctx, seed, stream, first, stride, n, C.byref(out)))
         return DevTable(out, lambda p: self._L.gkr_dev_table_free(self._ctx, p), n)
 
     def dev_table_upload(self, values) -> DevTable:
@@ -246,6 +247,22 @@ class Prover:
         _lib.check(self._L.gkr_sumcheck_prod(self._ctx, len(tables), n_vars, ptrs, 1 if on_dev else 0,
                                              C.byref(t) if t else None, _vp(msgs), _vp(mlen), _vp(chal), _vp(fin)))
         return msgs, mlen, chal, fin
+
+    def sumcheck_prod_sharded_raw(self, local_tables, n_vars: int, challenge=None):
+        """table-sharded product sumcheck (gkr_b200.dist.init_comm first); local_tables: 3 DevTable shards"""
+        ptrs = (C.c_void_p * len(local_tables))(*[t.ptr for t in local_tables])
+        msgs = np.zeros((n_vars, 4, 8), np.uint32)
+        mlen = np.zeros(n_vars, np.uint8)
+        chal = np.zeros((n_vars, 8), np.uint32)
+        fin = np.zeros((len(local_tables), 8), np.uint32)
+        t, keep_cb = self._transcript(challenge)
+        _lib.check(self._L.gkr_sumcheck_prod_sharded(self._ctx, len(local_tables), n_vars, ptrs, C.byref(t) if t else None,
+                                                     _vp(msgs), _vp(mlen), _vp(chal), _vp(fin)))
+        return msgs, mlen, chal, fin
+
+    def sumcheck_prod_sharded(self, local_tables, n_vars: int, challenge=None):
+        msgs, mlen, chal, fin = self.sumcheck_prod_sharded_raw(local_tables, n_vars, challenge)
+        return ([fr_to_ints(msgs[j, :mlen[j]]) for j in range(n_vars)], fr_to_ints(chal), fr_to_ints(fin))
 
     def sumcheck_prod(self, tables, n_vars: int, challenge=None):
         msgs, mlen, chal, fin = self.sumcheck_prod_raw(tables, n_vars, challenge)

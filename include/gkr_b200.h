@@ -135,8 +135,27 @@ void gkr_proof_free(gkr_proof *p);
 int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_vars, const void *const *tables, int on_device,
                       const gkr_transcript *t, gkr_fr *msgs, uint8_t *msg_len, gkr_fr *chal, gkr_fr *final_vals);
 
+/* ---- multi-GPU: one process (and one gkr_ctx) per GPU, NCCL over NVLink -----------------------------
+ * Rank 0 calls gkr_comm_unique_id and ships the bytes to the other ranks (MPI, torch.distributed, a file);
+ * every rank then calls gkr_comm_init (collective).  n_ranks must be a power of two. */
+#define GKR_COMM_ID_BYTES 256
+int gkr_comm_unique_id(uint8_t out[GKR_COMM_ID_BYTES]);
+int gkr_comm_init(gkr_ctx *ctx, int n_ranks, int rank, const uint8_t id[GKR_COMM_ID_BYTES]);
+void gkr_comm_destroy(gkr_ctx *ctx);
+/* Table-sharded product sumcheck over n_vars GLOBAL variables.  The tables are split on the variables
+ * bound LAST, i.e. the low log2(n_ranks) index bits: rank p holds entries idx = i * n_ranks + p as
+ * local_tables[t][i], i < 2^(n_vars - log2 n_ranks), Montgomery-form device buffers (gkr_dev_table_*).
+ * Per round each rank reduces its shard, the partial sums are all-gathered (NCCL) and added on every rank,
+ * every rank derives the same challenge and folds locally; the last log2(n_ranks) rounds run on the
+ * gathered single entries.  Every rank returns the complete, identical proof. */
+int gkr_sumcheck_prod_sharded(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_vars, const void *const *local_tables,
+                              const gkr_transcript *t, gkr_fr *msgs, uint8_t *msg_len, gkr_fr *chal, gkr_fr *final_vals);
+
 /* device-resident tables for benchmarks at sizes that should not cross PCIe (BASELINE.json config 4) */
 int gkr_dev_table_synth(gkr_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t n, void **dev_table_out);
+/* element i = element (first + i * stride) of the synthetic stream (shards of a larger table) */
+int gkr_dev_table_synth_strided(gkr_ctx *ctx, uint64_t seed, uint64_t stream, uint64_t first, uint64_t stride, uint64_t n,
+                                void **dev_table_out);
 int gkr_dev_table_upload(gkr_ctx *ctx, const gkr_fr *host_values, uint64_t n, void **dev_table_out);
 int gkr_dev_table_download(gkr_ctx *ctx, const void *dev_table, uint64_t n, gkr_fr *host_out);
 void gkr_dev_table_free(gkr_ctx *ctx, void *dev_table);
