@@ -86,6 +86,30 @@ extern "C" const char *gkr_version(void) { return "gkr_b200 0.1 (sm_100a)"; }
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+void *gkr_ctx::pool_get(size_t bytes) {
+    auto it = dev_pool.find(bytes);
+    if (it != dev_pool.end()) {
+        void *p = it->second;
+        dev_pool.erase(it);
+        return p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        // give cached blocks back to the driver and retry once
+        for (auto &kv : dev_pool) cudaFree(kv.second);
+        dev_pool.clear();
+        cudaGetLastError();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        set_last_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
 int gkr_ctx::wait_slot(uint32_t s, const HostSlot **out) {
     const double t0 = now_seconds();
     volatile HostSlot *slot = slots_host + (s % kSlots);
@@ -169,6 +193,8 @@ extern "C" void gkr_ctx_destroy(gkr_ctx *ctx) {
     for (DevBuf *b : {&ctx->eqz, &ctx->equ, &ctx->eq_scratch, &ctx->H, &ctx->A, &ctx->foldA, &ctx->foldB, &ctx->lineA,
                       &ctx->lineB, &ctx->mob, &ctx->misc, &ctx->stage, &ctx->aux_mob, &ctx->aux_stage, &ctx->qdev})
         b->release();
+    for (auto &kv : ctx->dev_pool) cudaFree(kv.second);
+    ctx->dev_pool.clear();
     if (ctx->ws.partials) cudaFree(ctx->ws.partials);
     if (ctx->ws.counter) cudaFree(ctx->ws.counter);
     if (ctx->words) cudaFree(ctx->words);
@@ -450,29 +476,30 @@ extern "C" int gkr_circuit_create(gkr_ctx *ctx, uint32_t n_layers, const gkr_lay
 // ------------------------------------------------------------------------------------------------
 struct gkr_witness {
     int device = 0;
+    gkr_ctx *owner = nullptr;     // tables go back to the owner's pool (the context must outlive its witnesses)
     std::vector<Fr *> vals;       // Montgomery tables, layer 0 .. depth
     std::vector<uint32_t> k;
 };
 extern "C" void gkr_witness_destroy(gkr_witness *w) {
     if (!w) return;
     cudaSetDevice(w->device);
-    for (Fr *p : w->vals)
-        if (p) cudaFree(p);
+    for (size_t i = 0; i < w->vals.size(); ++i) {
+        if (!w->vals[i]) continue;
+        if (w->owner) w->owner->pool_put(w->vals[i], sizeof(Fr) << w->k[i]);
+        else cudaFree(w->vals[i]);
+    }
     delete w;
 }
 static int witness_alloc(gkr_ctx *ctx, const gkr_circuit *c, std::unique_ptr<gkr_witness, void (*)(gkr_witness *)> &w) {
     w.reset(new (std::nothrow) gkr_witness());
     if (!w) return GKR_ERR_OOM;
     w->device = ctx->device;
+    w->owner = ctx;
     w->k = c->k;
     w->vals.assign(c->k.size(), nullptr);
     for (size_t i = 0; i < c->k.size(); ++i) {
-        cudaError_t e = cudaMalloc((void **)&w->vals[i], sizeof(Fr) << c->k[i]);
-        if (e != cudaSuccess) {
-            set_last_error("cudaMalloc of witness layer %zu failed: %s", i, cudaGetErrorString(e));
-            cudaGetLastError();
-            return e == cudaErrorMemoryAllocation ? GKR_ERR_OOM : GKR_ERR_CUDA;
-        }
+        w->vals[i] = static_cast<Fr *>(ctx->pool_get(sizeof(Fr) << c->k[i]));
+        if (!w->vals[i]) return GKR_ERR_OOM;
     }
     return GKR_OK;
 }

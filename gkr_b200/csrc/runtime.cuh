@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -106,6 +107,11 @@ struct gkr_ctx {
     void *nccl_comm = nullptr;
     int n_ranks = 1, rank = 0;
     Fr *comm_send = nullptr, *comm_recv = nullptr;
+
+    // recycled device allocations for witness tables (cudaMalloc/cudaFree per proof serialise in the driver)
+    std::multimap<size_t, void *> dev_pool;
+    void *pool_get(size_t bytes);
+    void pool_put(void *p, size_t bytes) { if (p) dev_pool.emplace(bytes, p); }
 
     // workspaces
     gkr::DevBuf eqz, equ, eq_scratch, H, A, foldA, foldB, lineA, lineB, mob, misc, stage, aux_mob, aux_stage, qdev;

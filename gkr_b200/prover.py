@@ -12,6 +12,7 @@ All table arithmetic happens in the CUDA library; this module only moves data an
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -90,7 +91,9 @@ class Circuit(_Handle):
 
 
 class Witness(_Handle):
-    pass
+    def __init__(self, ptr, free, owner=None):
+        super().__init__(ptr, free)
+        self._owner = owner          # keeps the Prover (gkr_ctx) alive: the tables return to its pool
 
 
 class DevTable(_Handle):
@@ -113,9 +116,13 @@ class Prover:
         _lib.check(self._L.gkr_ctx_create(device, C.byref(ctx)))
         self._ctx = ctx
         self.device = device
+        self._witnesses = weakref.WeakSet()
 
     def close(self):
+        """destroys the context; witnesses created from it must already be closed"""
         if getattr(self, "_ctx", None):
+            for w in list(getattr(self, "_witnesses", [])):
+                w.close()
             self._L.gkr_ctx_destroy(self._ctx)
             self._ctx = None
 
@@ -162,7 +169,9 @@ class Prover:
         ptrs = (C.c_void_p * len(vals))(*[v.ctypes.data for v in vals])
         out = C.c_void_p()
         _lib.check(self._L.gkr_witness_create(self._ctx, circuit.ptr, ptrs, C.byref(out)))
-        return Witness(out, self._L.gkr_witness_destroy)
+        w = Witness(out, self._L.gkr_witness_destroy, self)
+        self._witnesses.add(w)
+        return w
 
     def witness_eval(self, circuit: Circuit, input_values) -> Witness:
         v = as_fr_array(input_values)
@@ -170,7 +179,9 @@ class Prover:
             raise ValueError("input table has the wrong length")
         out = C.c_void_p()
         _lib.check(self._L.gkr_witness_eval(self._ctx, circuit.ptr, _vp(v), C.byref(out)))
-        return Witness(out, self._L.gkr_witness_destroy)
+        w = Witness(out, self._L.gkr_witness_destroy, self)
+        self._witnesses.add(w)
+        return w
 
     def witness_layer(self, circuit: Circuit, witness: Witness, layer: int) -> np.ndarray:
         out = np.zeros((1 << circuit.k[layer], 8), np.uint32)

@@ -100,6 +100,7 @@ int gkr_witness_create(gkr_ctx *ctx, const gkr_circuit *c, const gkr_fr *const *
 int gkr_witness_eval(gkr_ctx *ctx, const gkr_circuit *c, const gkr_fr *input_values, gkr_witness **out);
 /* copy layer i (canonical values) back to the host */
 int gkr_witness_layer(gkr_ctx *ctx, const gkr_witness *w, uint32_t layer, gkr_fr *out);
+/* returns the tables to the creating context's pool: destroy witnesses BEFORE their gkr_ctx */
 void gkr_witness_destroy(gkr_witness *w);
 
 /* ---- proof == Proof<S> (gkr.rs:8-19), flat ------------------------------------------------------- */
