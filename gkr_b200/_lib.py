@@ -12,10 +12,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libgkr_b200.so")
 _SRC = os.path.join(_HERE, "csrc")
 
-GKR_N_KERNEL_CLASSES = 9
+GKR_N_KERNEL_CLASSES = 11
 GKR_COMM_ID_BYTES = 256
 KERNEL_CLASS_NAMES = ["gkr_round", "gkr_round_fused", "prod3_round", "prod3_round_fused", "wiring", "eq",
-                      "mobius", "line", "other"]
+                      "mobius", "line", "other", "gkr_round_tail", "prod3_round_tail"]
 STATUS = {0: "GKR_OK", -1: "GKR_ERR_INVALID", -2: "GKR_ERR_CUDA", -3: "GKR_ERR_OOM", -4: "GKR_ERR_RANGE",
           -5: "GKR_ERR_TRANSCRIPT", -6: "GKR_ERR_COMM", -7: "GKR_ERR_INTERNAL"}
 

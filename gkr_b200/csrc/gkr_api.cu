@@ -607,7 +607,7 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
         if (j == 0) {
             launch_gkr_round(false, full, Hc, Wc, Ac, nullptr, nullptr, nullptr, rc, n / 2, ctx->ws, ctx->slot_dev(s),
                              s, ctx->stream);
-            ctx->end_launch(KC_ROUND, (full ? 96.0 : 80.0) * n);
+            ctx->end_launch(n / 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full ? 96.0 : 80.0) * n);
         } else {
             // fold the size-n tables with r_{j} into size n/2 and evaluate round j+1 on them
             DevBuf &dst = (j & 1) ? ctx->foldA : ctx->foldB;
@@ -615,17 +615,16 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
             Fr *Ho = dst.as<Fr>(), *Wo = Ho + half, *Ao = Wo + half;
             launch_gkr_round(true, full, Hc, Wc, Ac, Ho, Wo, Ao, rc, half / 2, ctx->ws, ctx->slot_dev(s), s,
                              ctx->stream);
-            ctx->end_launch(KC_ROUND_FUSED, 96.0 * n + 96.0 * half);
+            ctx->end_launch(half / 2 >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 96.0 * n + 96.0 * half);
             Hc = Ho; Wc = Wo; Ac = Ao;
             n = half;
         }
         GKR_TRY(ctx->check_launch("gkr_round"));
         const HostSlot *slot;
         GKR_TRY(ctx->wait_slot(s, &slot));
-        HFr x0, x1, x2;
-        if (!hfr_from_canonical(&x0, &slot->v[0]) || !hfr_from_canonical(&x2, &slot->v[1]) ||
-            (full && !hfr_from_canonical(&x1, &slot->v[2]))) {
-            set_last_error("device published a non-canonical round value");
+        HFr x0 = to_host(slot->v[0]), x2 = to_host(slot->v[1]), x1 = full ? to_host(slot->v[2]) : hfr_zero();
+        if (hf::geq_p(x0.l) || hf::geq_p(x2.l) || hf::geq_p(x1.l)) {
+            set_last_error("device published an unreduced round value");
             return GKR_ERR_INTERNAL;
         }
         if (!full) {
@@ -950,14 +949,14 @@ static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3]
         if (!pending_fold) {
             launch_prod3_round(false, full, Ac, Bc, Cc, nullptr, nullptr, nullptr, rc, n / 2, ctx->ws, ctx->slot_dev(s), s,
                                ctx->stream, dev_out);
-            ctx->end_launch(KC_PROD3, 96.0 * n);
+            ctx->end_launch(n / 2 >= kTailPairs ? KC_PROD3 : KC_PROD3_TAIL, 96.0 * n);
         } else {
             DevBuf &dst = (flip ^= 1) ? ctx->foldA : ctx->foldB;
             const uint64_t half = n / 2;
             Fr *Ao = dst.as<Fr>(), *Bo = Ao + half, *Co = Bo + half;
             launch_prod3_round(true, full, Ac, Bc, Cc, Ao, Bo, Co, rc, half / 2, ctx->ws, ctx->slot_dev(s), s, ctx->stream,
                                dev_out);
-            ctx->end_launch(KC_PROD3_FUSED, 96.0 * n + 96.0 * half);
+            ctx->end_launch(half / 2 >= kTailPairs ? KC_PROD3_FUSED : KC_PROD3_TAIL, 96.0 * n + 96.0 * half);
             Ac = Ao; Bc = Bo; Cc = Co;
             n = half;
         }
@@ -973,10 +972,12 @@ static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3]
         pending_fold = true;
         const HostSlot *slot;
         GKR_TRY(ctx->wait_slot(s, &slot));
-        HFr g0, g1, gm, ginf;
-        if (!hfr_from_canonical(&g0, &slot->v[0]) || !hfr_from_canonical(&gm, &slot->v[1]) ||
-            !hfr_from_canonical(&ginf, &slot->v[2]) || (full && !hfr_from_canonical(&g1, &slot->v[3])))
+        HFr g0 = to_host(slot->v[0]), gm = to_host(slot->v[1]), ginf = to_host(slot->v[2]);
+        HFr g1 = full ? to_host(slot->v[3]) : hfr_zero();
+        if (hf::geq_p(g0.l) || hf::geq_p(gm.l) || hf::geq_p(ginf.l) || hf::geq_p(g1.l)) {
+            set_last_error("device published an unreduced round value");
             return GKR_ERR_INTERNAL;
+        }
         if (!full) {
             g1 = hfr_sub(claim, g0);
         } else if (j > 0 && !hfr_eq(hfr_add(g0, g1), claim)) {
@@ -1006,9 +1007,10 @@ static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3]
             GKR_TRY(ctx->check_launch("publish"));
             const HostSlot *fs;
             GKR_TRY(ctx->wait_slot(s2, &fs));
-            for (int i = 0; i < 3; ++i)
-                if (!hfr_from_canonical(&lo[i], &fs->v[2 * i]) || !hfr_from_canonical(&hi[i], &fs->v[2 * i + 1]))
-                    return GKR_ERR_INTERNAL;
+            for (int i = 0; i < 3; ++i) {
+                lo[i] = to_host(fs->v[2 * i]);
+                hi[i] = to_host(fs->v[2 * i + 1]);
+            }
             bool all_nonzero = true;
             uint32_t deps = 0;
             for (int i = 0; i < 3; ++i) {

@@ -37,6 +37,11 @@ __device__ __forceinline__ void st_fr(Fr *p, const Fr &v) {
     q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
 
+// pull the cache lines of a future iteration towards L2 (no register cost)
+__device__ __forceinline__ void prefetch_l2(const Fr *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // lo + r * (hi - lo), r given by its constant-multiplier table (kernel parameter => constant bank operands)
 __device__ __forceinline__ Fr fold2(const Fr &lo, const Fr &hi, const FrConstMul &r) {
     return fr_add(lo, fr_mul_const(fr_sub(hi, lo), r));
@@ -85,39 +90,42 @@ __device__ __forceinline__ void grid_sum_publish(Fr (&acc)[K], Fr *partials, uns
     __shared__ Fr red[K][kWarps];
     __shared__ bool is_last;
     block_sum<K>(acc, red);
-    if (threadIdx.x == 0) {
+    if (gridDim.x > 1) {
+        if (threadIdx.x == 0) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) st_fr(&partials[(size_t)blockIdx.x * K + j], acc[j]);
+            for (int j = 0; j < K; ++j) st_fr(&partials[(size_t)blockIdx.x * K + j], acc[j]);
+            __threadfence();
+            unsigned int ticket = atomicAdd(counter, 1u);
+            is_last = (ticket == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (!is_last) return;
         __threadfence();
-        unsigned int ticket = atomicAdd(counter, 1u);
-        is_last = (ticket == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
 #pragma unroll
-    for (int j = 0; j < K; ++j) acc[j] = fr_zero();
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+        for (int j = 0; j < K; ++j) acc[j] = fr_zero();
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) acc[j] = fr_add(acc[j], ld_fr_cg(&partials[(size_t)b * K + j]));
+            for (int j = 0; j < K; ++j) acc[j] = fr_add(acc[j], ld_fr_cg(&partials[(size_t)b * K + j]));
+        }
+        block_sum<K>(acc, red);
+        if (threadIdx.x == 0) *counter = 0;
     }
-    block_sum<K>(acc, red);
+    // single-CTA launches (small tables) skip the partials / ticket round trip entirely
     if (threadIdx.x == 0 && dev_out != nullptr) {
 #pragma unroll
         for (int j = 0; j < K; ++j) st_fr(&dev_out[j], acc[j]);
-        *counter = 0;
         return;
     }
     if (threadIdx.x == 0) {
+        // totals are published in Montgomery form (the host shares the representation); aux[1] = non-zero mask
         uint32_t nz = 0;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             nz |= fr_is_zero(acc[j]) ? 0u : (1u << j);
-            st_fr(&slot->v[j], fr_from_mont(acc[j]));
+            st_fr(&slot->v[j], acc[j]);
         }
         slot->aux[0] = aux0;
         slot->aux[1] = nz;
-        *counter = 0;
         __threadfence_system();
         slot->seq = seq;
     }
@@ -341,6 +349,19 @@ __global__ void __launch_bounds__(kThreads, 2) k_gkr_round(const Fr *__restrict_
     }
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < q; i += (uint64_t)gridDim.x * blockDim.x) {
         Fr wl, wh, hl, hh;
+        {
+            // no-fold rounds are memory-bound: pull the next iteration's lines towards L2 (in the fused
+            // rounds this raised DRAM reads by 32 % without a speed-up -- ncu r01 -- so it is off there)
+            const uint64_t nx = i + (uint64_t)gridDim.x * blockDim.x;
+            if (!FOLD && nx < q) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    prefetch_l2(Win + nx + t * q);
+                    prefetch_l2(Hin + nx + t * q);
+                    prefetch_l2(Ain + nx + t * q);
+                }
+            }
+        }
         if (FOLD) {
             wl = fold2(ld_fr(Win + i), ld_fr(Win + i + 2 * q), r);
             wh = fold2(ld_fr(Win + i + q), ld_fr(Win + i + 3 * q), r);
@@ -431,6 +452,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restric
         for (int j = 0; j < K; ++j) wide_zero(wide[j]);
     }
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < q; i += (uint64_t)gridDim.x * blockDim.x) {
+        {
+            const uint64_t nx = i + (uint64_t)gridDim.x * blockDim.x;
+            if (!FOLD && nx < q) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    prefetch_l2(Ain + nx + t * q);
+                    prefetch_l2(Bin + nx + t * q);
+                    prefetch_l2(Cin + nx + t * q);
+                }
+            }
+        }
         Fr t0, tm, tinf, t1;
         {
             Fr a0, a1, b0, b1;
@@ -448,10 +480,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restric
                 b0 = ld_fr(Bin + i); b1 = ld_fr(Bin + i + q);
             }
             t0 = fr_mul(a0, b0);
-            if (FULL) t1 = fr_mul(a1, b1);
             const Fr da = fr_sub(a1, a0), db = fr_sub(b1, b0);
             tinf = fr_mul(da, db);
-            tm = fr_mul(fr_sub(a0, da), fr_sub(b0, db));          // value at X = -1 : lo - d
+            if (FULL) {
+                // three products serve all four points: with X = a0 b1 + a1 b0 = t0 + t1 - tinf,
+                // (a0 - da)(b0 - db) = (2a0 - a1)(2b0 - b1) = 4 t0 - 2 X + t1 = 2 t0 - t1 + 2 tinf
+                t1 = fr_mul(a1, b1);
+                tm = fr_add(fr_sub(fr_dbl(t0), t1), fr_dbl(tinf));
+            } else {
+                tm = fr_mul(fr_sub(a0, da), fr_sub(b0, db));      // value at X = -1 : lo - d
+            }
         }
         Fr c0, c1;
         if (FOLD) {
@@ -510,7 +548,7 @@ __global__ void k_sum_ranks_publish(const Fr *__restrict__ gathered, int n_ranks
     if (j < count) {
         Fr acc = fr_zero();
         for (int rk = 0; rk < n_ranks; ++rk) acc = fr_add(acc, ld_fr_cg(gathered + (size_t)rk * count + j));
-        st_fr(&slot->v[j], fr_from_mont(acc));
+        st_fr(&slot->v[j], acc);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -545,7 +583,7 @@ void launch_fold(const Fr *in, Fr *out, const FrConstMul &r, uint64_t half, cuda
 struct Ptrs6 { const Fr *p[6]; };
 __global__ void k_publish(Ptrs6 ptrs, int count, HostSlot *slot, uint32_t seq) {
     if (threadIdx.x == 0) {
-        for (int j = 0; j < count; ++j) st_fr(&slot->v[j], fr_from_mont(ld_fr_cg(ptrs.p[j])));
+        for (int j = 0; j < count; ++j) st_fr(&slot->v[j], ld_fr_cg(ptrs.p[j]));
         __threadfence_system();
         slot->seq = seq;
     }

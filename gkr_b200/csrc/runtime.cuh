@@ -36,7 +36,10 @@ void set_last_error(const char *fmt, ...);
         if (rc__ != GKR_OK) return rc__; \
     } while (0)
 
-enum KernelClass { KC_ROUND = 0, KC_ROUND_FUSED, KC_PROD3, KC_PROD3_FUSED, KC_WIRING, KC_EQ, KC_MOBIUS, KC_LINE, KC_OTHER };
+enum KernelClass { KC_ROUND = 0, KC_ROUND_FUSED, KC_PROD3, KC_PROD3_FUSED, KC_WIRING, KC_EQ, KC_MOBIUS, KC_LINE, KC_OTHER,
+                   KC_ROUND_TAIL, KC_PROD3_TAIL };
+// round launches below this many pairs are latency-bound "tail" launches, accounted separately from the streaming ones
+constexpr uint64_t kTailPairs = (uint64_t)1 << 16;
 
 // grow-only device buffer
 struct DevBuf {

@@ -178,8 +178,9 @@ typedef struct {
 int gkr_ctx_stats(gkr_ctx *ctx, gkr_stats *out, int reset);
 /* per-kernel-class device timing (CUDA events around every launch; slows the prover down).
  * classes: 0 gkr_round (no fold), 1 gkr_round fused fold, 2 prod3 round, 3 prod3 fused, 4 wiring,
- * 5 eq, 6 mobius/alt-sum, 7 line, 8 other */
-#define GKR_N_KERNEL_CLASSES 9
+ * 5 eq, 6 mobius/alt-sum, 7 line, 8 other, 9 gkr_round launches below 2^16 pairs (latency-bound tail),
+ * 10 prod3 launches below 2^16 pairs; classes 0-3 count only launches of at least 2^16 pairs */
+#define GKR_N_KERNEL_CLASSES 11
 typedef struct {
     uint64_t launches[GKR_N_KERNEL_CLASSES];
     double ms[GKR_N_KERNEL_CLASSES];
