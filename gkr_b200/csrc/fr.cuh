@@ -437,6 +437,7 @@ FR_HD Fr wide_reduce(const FrWide &acc) {
 // ------------------------------------------------------------------------------------------------
 struct FrConstMul {
     uint32_t c[8][8];
+    FR_HD uint32_t get(int j, int i) const { return c[j][i]; }
 };
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ void fr_merge9(uint32_t (&t)[10], const uint32_t (&e)[9], const uint32_t (&o)[10]) {
@@ -462,7 +463,8 @@ inline void fr_merge9(uint32_t (&t)[10], const uint32_t (&e)[9], const uint32_t 
     t[9] = o[9] + (uint32_t)c;
 }
 #endif
-FR_HD Fr fr_mul_const(const Fr &d, const FrConstMul &K) {
+template <class KT>
+FR_HD Fr fr_mul_const(const Fr &d, const KT &K) {
     uint32_t e[9], o[10];          // e: columns 0..7 + carries at 8 ; o: columns 1..8 + carries at 9
 #pragma unroll
     for (int i = 0; i < 9; ++i) e[i] = 0;
@@ -470,8 +472,8 @@ FR_HD Fr fr_mul_const(const Fr &d, const FrConstMul &K) {
     for (int i = 0; i < 10; ++i) o[i] = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        fr_row_lo(e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], e[8], K.c[j][0], K.c[j][2], K.c[j][4], K.c[j][6], d.l[j]);
-        fr_row_lo(o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], K.c[j][1], K.c[j][3], K.c[j][5], K.c[j][7], d.l[j]);
+        fr_row_lo(e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], e[8], K.get(j, 0), K.get(j, 2), K.get(j, 4), K.get(j, 6), d.l[j]);
+        fr_row_lo(o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], K.get(j, 1), K.get(j, 3), K.get(j, 5), K.get(j, 7), d.l[j]);
     }
     uint32_t t[10];
     fr_merge9(t, e, o);            // < 2^35 p

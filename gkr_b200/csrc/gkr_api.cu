@@ -168,6 +168,9 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->slots_host, sizeof(HostSlot) * gkr_ctx::kSlots, cudaHostAllocMapped));
     std::memset((void *)ctx->slots_host, 0, sizeof(HostSlot) * gkr_ctx::kSlots);
     GKR_CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->slots_dev, (void *)ctx->slots_host, 0));
+    GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->cmds_host, sizeof(HostCmd) * gkr_ctx::kSlots, cudaHostAllocMapped));
+    std::memset((void *)ctx->cmds_host, 0, sizeof(HostCmd) * gkr_ctx::kSlots);
+    GKR_CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->cmds_dev, (void *)ctx->cmds_host, 0));
     ctx->pinned_elems = 4096;
     GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->pinned, sizeof(gkr_fr) * ctx->pinned_elems, cudaHostAllocDefault));
     ctx->ws.max_blocks = device_sm_count() * 4;
@@ -199,6 +202,7 @@ extern "C" void gkr_ctx_destroy(gkr_ctx *ctx) {
     if (ctx->ws.counter) cudaFree(ctx->ws.counter);
     if (ctx->words) cudaFree(ctx->words);
     if (ctx->slots_host) cudaFreeHost((void *)ctx->slots_host);
+    if (ctx->cmds_host) cudaFreeHost((void *)ctx->cmds_host);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -220,6 +224,10 @@ extern "C" int gkr_ctx_set_option(gkr_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return GKR_ERR_INVALID;
     if (std::strcmp(name, "paranoid") == 0) {
         ctx->paranoid = value != 0;
+        return GKR_OK;
+    }
+    if (std::strcmp(name, "prelaunch") == 0) {
+        ctx->prelaunch = value != 0;
         return GKR_OK;
     }
     set_last_error("unknown option '%s'", name);
@@ -586,6 +594,21 @@ struct PhaseIO {
     const Fr *W_last;          // out: device pointer to the size-2 W table of the last round
 };
 
+// host -> waiting kernel: payload first, then the five line tags (x86 keeps the store order)
+static void write_cmd(HostCmd *c, const FrConstMul *K, uint32_t tag) {
+    if (K) {
+        const uint32_t *src = &K->c[0][0];
+        for (int line = 0; line < 5; ++line)
+            for (int o = 0; o < 15; ++o) {
+                const int p = line * 15 + o;
+                c->w[line * 16 + o] = p < 64 ? src[p] : 0u;
+            }
+    }
+    std::atomic_thread_fence(std::memory_order_release);
+    for (int line = 0; line < 5; ++line) c->w[line * 16 + 15] = tag;
+    std::atomic_thread_fence(std::memory_order_release);
+}
+
 // claim: in = g_{prev}(r_prev) if known (nullptr => the first round also accumulates g(1) on the device);
 //        out = g_k(r_k), the claim the next phase starts from.
 static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *last_hash, const HFr *claim_in,
@@ -594,34 +617,91 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
     const uint64_t N = (uint64_t)1 << k;
     GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 2, 2)));
     GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 4, 2)));
-    const Fr *Hc = io.H, *Wc = io.W, *Ac = io.A;
-    uint64_t n = N;                                   // size of the current tables
+    // plan of the k launches: round 0 evaluates the size-N inputs, round j >= 1 folds size n_in tables with r_j
+    // into size n_in/2 (ping-pong buffers) and evaluates round j+1 on them
+    struct Plan {
+        const Fr *H, *W, *A;
+        Fr *Ho, *Wo, *Ao;
+        uint64_t n_in, pairs;
+        uint32_t seq;
+        bool launched, commanded;
+    };
+    std::vector<Plan> plan(k);
+    {
+        const Fr *Hc = io.H, *Wc = io.W, *Ac = io.A;
+        uint64_t n = N;
+        for (uint32_t j = 0; j < k; ++j) {
+            Plan &p = plan[j];
+            p.H = Hc; p.W = Wc; p.A = Ac; p.n_in = n;
+            p.launched = p.commanded = false;
+            p.seq = 0;
+            if (j == 0) {
+                p.Ho = p.Wo = p.Ao = nullptr;
+                p.pairs = n / 2;
+            } else {
+                DevBuf &dst = (j & 1) ? ctx->foldA : ctx->foldB;
+                const uint64_t half = n / 2;
+                p.Ho = dst.as<Fr>(); p.Wo = p.Ho + half; p.Ao = p.Wo + half;
+                p.pairs = half / 2;
+                Hc = p.Ho; Wc = p.Wo; Ac = p.Ao;
+                n = half;
+            }
+        }
+        io.W_last = Wc;
+    }
+    // if anything fails after kernels were pre-launched, release them (abort tag) before unwinding
+    struct AbortGuard {
+        gkr_ctx *ctx;
+        std::vector<Plan> &plan;
+        ~AbortGuard() {
+            bool any = false;
+            for (Plan &p : plan)
+                if (p.launched && p.seq && !p.commanded && p.Ho) {
+                    write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), nullptr, kCmdAbort);
+                    any = true;
+                }
+            if (any) cudaStreamSynchronize(ctx->stream);
+        }
+    } guard{ctx, plan};
+    const bool can_prelaunch = ctx->prelaunch && !ctx->profiling;
     HFr r = hfr_zero();
     HFr claim = claim_in ? *claim_in : hfr_zero();
     bool have_claim = claim_in != nullptr;
     for (uint32_t j = 0; j < k; ++j) {
-        const uint32_t s = ctx->next_seq();
+        Plan &p = plan[j];
         const bool full = !have_claim || ctx->paranoid;
-        const FrConstMul rc = j ? make_const_mul(r) : FrConstMul{};
-        ctx->begin_launch();
-        if (j == 0) {
-            launch_gkr_round(false, full, Hc, Wc, Ac, nullptr, nullptr, nullptr, rc, n / 2, ctx->ws, ctx->slot_dev(s),
-                             s, ctx->stream);
-            ctx->end_launch(n / 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full ? 96.0 : 80.0) * n);
-        } else {
-            // fold the size-n tables with r_{j} into size n/2 and evaluate round j+1 on them
-            DevBuf &dst = (j & 1) ? ctx->foldA : ctx->foldB;
-            const uint64_t half = n / 2;
-            Fr *Ho = dst.as<Fr>(), *Wo = Ho + half, *Ao = Wo + half;
-            launch_gkr_round(true, full, Hc, Wc, Ac, Ho, Wo, Ao, rc, half / 2, ctx->ws, ctx->slot_dev(s), s,
+        if (!p.launched) {
+            p.seq = ctx->next_seq();
+            const FrConstMul rc = j ? make_const_mul(r) : FrConstMul{};
+            ctx->begin_launch();
+            launch_gkr_round(j != 0, full, p.H, p.W, p.A, p.Ho, p.Wo, p.Ao, rc, p.pairs, ctx->ws, ctx->slot_dev(p.seq), p.seq,
                              ctx->stream);
-            ctx->end_launch(half / 2 >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 96.0 * n + 96.0 * half);
-            Hc = Ho; Wc = Wo; Ac = Ao;
-            n = half;
+            if (j == 0) ctx->end_launch(p.pairs >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full ? 96.0 : 80.0) * p.n_in);
+            else ctx->end_launch(p.pairs >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 96.0 * p.n_in + 48.0 * p.n_in);
+            GKR_TRY(ctx->check_launch("gkr_round"));
+            p.launched = p.commanded = true;
         }
-        GKR_TRY(ctx->check_launch("gkr_round"));
+        // small-table rounds that follow are launched now, ahead of their challenges: each waits for its command
+        // block, so kernel launch latency overlaps the host transcript instead of adding to every round
+        if (can_prelaunch && j + 1 < k && !plan[j + 1].launched && plan[j + 1].pairs < kPrelaunchPairs) {
+            for (uint32_t u = j + 1; u < k; ++u) {
+                Plan &f = plan[u];
+                f.seq = ctx->next_seq();
+                HostCmd *cmd_h = ctx->cmds_host + (f.seq % gkr_ctx::kSlots);
+                write_cmd(cmd_h, nullptr, 0u);                         // clear stale tags
+                launch_gkr_round(true, ctx->paranoid, f.H, f.W, f.A, f.Ho, f.Wo, f.Ao, FrConstMul{}, f.pairs, ctx->ws,
+                                 ctx->slot_dev(f.seq), f.seq, ctx->stream, ctx->cmds_dev + (f.seq % gkr_ctx::kSlots));
+                ctx->stats.kernel_launches += 1;
+                GKR_TRY(ctx->check_launch("gkr_round_cmd"));
+                f.launched = true;
+            }
+        }
         const HostSlot *slot;
-        GKR_TRY(ctx->wait_slot(s, &slot));
+        GKR_TRY(ctx->wait_slot(p.seq, &slot));
+        if (slot->aux[2] == 0xDEADu) {
+            set_last_error("pre-launched round kernel %u gave up waiting for its challenge", j);
+            return GKR_ERR_INTERNAL;
+        }
         HFr x0 = to_host(slot->v[0]), x2 = to_host(slot->v[1]), x1 = full ? to_host(slot->v[2]) : hfr_zero();
         if (hf::geq_p(x0.l) || hf::geq_p(x2.l) || hf::geq_p(x1.l)) {
             set_last_error("device published an unreduced round value");
@@ -644,13 +724,18 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
         for (uint32_t i = 0; i < len; ++i) hfr_to_canonical(&io.msgs[3 * j + i], msg[i]);
         io.msg_len[j] = (uint8_t)len;
         GKR_TRY(challenge_for(ctx, t, msg, len, &r));
+        // hand the challenge to the next (already running, waiting) kernel as early as possible
+        if (j + 1 < k && plan[j + 1].launched && !plan[j + 1].commanded) {
+            const FrConstMul rc = make_const_mul(r);
+            write_cmd(ctx->cmds_host + (plan[j + 1].seq % gkr_ctx::kSlots), &rc, plan[j + 1].seq);
+            plan[j + 1].commanded = true;
+        }
         io.challenges[j] = r;
         hfr_to_canonical(&io.chal_out[j], r);
         *last_hash = r;
         claim = hfr_add(hfr_mul(hfr_add(hfr_mul(x2, r), c1), r), x0);      // g(r), Horner
         have_claim = true;
     }
-    io.W_last = Wc;
     if (claim_out) *claim_out = claim;
     return GKR_OK;
 }

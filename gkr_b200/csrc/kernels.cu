@@ -43,8 +43,51 @@ __device__ __forceinline__ void prefetch_l2(const Fr *p) {
 }
 
 // lo + r * (hi - lo), r given by its constant-multiplier table (kernel parameter => constant bank operands)
-__device__ __forceinline__ Fr fold2(const Fr &lo, const Fr &hi, const FrConstMul &r) {
+template <class KT>
+__device__ __forceinline__ Fr fold2(const Fr &lo, const Fr &hi, const KT &r) {
     return fr_add(lo, fr_mul_const(fr_sub(hi, lo), r));
+}
+
+// constant-multiplier table received through a HostCmd (shared memory copy of its 80 raw words)
+struct CmdConst {
+    const uint32_t *raw;
+    __device__ __forceinline__ uint32_t get(int j, int i) const {
+        const int p = 8 * j + i;
+        return raw[(p / 15) * 16 + (p % 15)];
+    }
+};
+__device__ __forceinline__ uint32_t ld_sys(const volatile uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Warp 0 polls the command block until all five line tags equal `tag` (or an abort tag / timeout shows up),
+// then leaves the 80 raw words in shared memory.  Returns false on abort or timeout.
+__device__ __forceinline__ bool wait_cmd(const HostCmd *cmd, uint32_t tag, uint32_t *raw_smem, int *ok_smem) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int ok = 0;
+        for (uint32_t spin = 0; spin < (1u << 24); ++spin) {       // ~30 s, then give up loudly
+            const uint32_t v0 = ld_sys(&cmd->w[lane]);
+            const uint32_t v1 = ld_sys(&cmd->w[32 + lane]);
+            const uint32_t v2 = lane < 16 ? ld_sys(&cmd->w[64 + lane]) : tag;
+            const bool is_tag_lane = (lane & 15) == 15;
+            const bool good = !is_tag_lane || (v0 == tag && v1 == tag && v2 == tag);
+            const bool abort = is_tag_lane && (v0 == kCmdAbort || v1 == kCmdAbort || v2 == kCmdAbort);
+            if (__any_sync(0xffffffffu, abort)) break;
+            if (__all_sync(0xffffffffu, good)) {
+                raw_smem[lane] = v0;
+                raw_smem[32 + lane] = v1;
+                if (lane < 16) raw_smem[64 + lane] = v2;
+                ok = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+        if (lane == 0) *ok_smem = ok;
+    }
+    __syncthreads();
+    return *ok_smem != 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -126,6 +169,7 @@ __device__ __forceinline__ void grid_sum_publish(Fr (&acc)[K], Fr *partials, uns
         }
         slot->aux[0] = aux0;
         slot->aux[1] = nz;
+        slot->aux[2] = 0;
         __threadfence_system();
         slot->seq = seq;
     }
@@ -332,12 +376,12 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 // LAZY: products are accumulated as exact 512-bit integers and reduced once per thread.
 // Published: v[0] = X0, v[1] = X2, v[2] = X1 (FULL only).
 // ------------------------------------------------------------------------------------------------
-template <bool FOLD, bool FULL, bool LAZY>
-__global__ void __launch_bounds__(kThreads, 2) k_gkr_round(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
-                                                           const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
-                                                           Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
-                                                           uint64_t q, Fr *partials, unsigned int *counter,
-                                                           HostSlot *slot, uint32_t seq) {
+template <bool FOLD, bool FULL, bool LAZY, bool CMD, class KT>
+__device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+                                               const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
+                                               Fr *__restrict__ Wout, Fr *__restrict__ Aout, const KT &r,
+                                               uint64_t q, Fr *partials, unsigned int *counter,
+                                               HostSlot *slot, uint32_t seq) {
     constexpr int K = FULL ? 3 : 2;
     Fr acc[K];
     FrWide wide[LAZY ? K : 1];
@@ -403,6 +447,34 @@ __global__ void __launch_bounds__(kThreads, 2) k_gkr_round(const Fr *__restrict_
     }
     grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u);
 }
+template <bool FOLD, bool FULL, bool LAZY>
+__global__ void __launch_bounds__(kThreads, 2) k_gkr_round(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+                                                           const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
+                                                           Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
+                                                           uint64_t q, Fr *partials, unsigned int *counter,
+                                                           HostSlot *slot, uint32_t seq) {
+    gkr_round_body<FOLD, FULL, LAZY, false>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq);
+}
+// pre-launched variant: waits for the challenge's constant table in a mapped command block
+template <bool FULL>
+__global__ void __launch_bounds__(kThreads, 2) k_gkr_round_cmd(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+                                                               const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
+                                                               Fr *__restrict__ Wout, Fr *__restrict__ Aout,
+                                                               const HostCmd *cmd, uint64_t q, Fr *partials,
+                                                               unsigned int *counter, HostSlot *slot, uint32_t seq) {
+    __shared__ uint32_t raw[80];
+    __shared__ int ok;
+    if (!wait_cmd(cmd, seq, raw, &ok)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {       // tell the host instead of leaving it waiting
+            slot->aux[2] = 0xDEADu;
+            __threadfence_system();
+            slot->seq = seq;
+        }
+        return;
+    }
+    CmdConst r{raw};
+    gkr_round_body<true, FULL, false, true>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq);
+}
 
 // lazy accumulation pays once a thread sees several pairs: fewer, fatter CTAs (2 resident per SM)
 static inline bool use_lazy(uint64_t pairs) { return pairs >= ((uint64_t)1 << 18); }
@@ -411,17 +483,27 @@ static inline int round_grid(uint64_t pairs, const ReduceWs &ws) {
     return grid_for(pairs, cap < ws.max_blocks ? cap : ws.max_blocks);
 }
 
+// the degree-2 GKR round is light on multiplies (memory/latency-bound): the lazy variant's per-thread
+// reduction epilogue only pays for very large tables
+static inline bool use_lazy_gkr(uint64_t pairs) { return pairs >= ((uint64_t)1 << 21); }
 template <bool FOLD, bool FULL>
 static void launch_gkr_round_t(const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
                                uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
-    const int grid = round_grid(pairs, ws);
-    if (use_lazy(pairs))
+    const int grid = use_lazy_gkr(pairs) ? round_grid(pairs, ws) : grid_for(pairs, ws.max_blocks);
+    if (use_lazy_gkr(pairs))
         k_gkr_round<FOLD, FULL, true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
     else
         k_gkr_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
 }
 void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
-                      const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+                      const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s,
+                      const HostCmd *cmd) {
+    if (cmd) {
+        const int grid = grid_for(pairs, ws.max_blocks);
+        if (full) k_gkr_round_cmd<true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, cmd, pairs, ws.partials, ws.counter, slot, seq);
+        else k_gkr_round_cmd<false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, cmd, pairs, ws.partials, ws.counter, slot, seq);
+        return;
+    }
     if (fold) {
         if (full) launch_gkr_round_t<true, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
         else launch_gkr_round_t<true, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);

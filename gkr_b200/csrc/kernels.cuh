@@ -18,6 +18,14 @@ struct alignas(256) HostSlot {
 };
 static_assert(sizeof(HostSlot) == 256, "HostSlot layout");
 
+// Command block for pre-launched round kernels, in pinned device-mapped host memory: 5 cache lines of
+// 15 payload words + 1 tag word.  The host fills the payload (the 64 words of the challenge's FrConstMul)
+// and then the tags; a waiting kernel accepts the block once all five tags equal its sequence number.
+struct alignas(64) HostCmd {
+    volatile uint32_t w[80];
+};
+constexpr uint32_t kCmdAbort = 0xFFFFFFFFu;
+
 struct FrVec {            // up to 32 field elements passed by value as a kernel parameter
     Fr v[32];
 };
@@ -58,9 +66,11 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 // fold == false: tables have 2*pairs entries, no output tables.
 // fold == true : tables have 4*pairs entries; first folds them with r (writing 2*pairs entries to
 //                Hout/Wout/Aout), then evaluates the round polynomial of the folded tables -- one pass.
+// cmd != nullptr (fold rounds only): the kernel is launched BEFORE the challenge exists and waits for it
+// (bounded spin) in the mapped command block, so that launch latency overlaps the host transcript.
 void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
                       const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
-                      cudaStream_t s);
+                      cudaStream_t s, const HostCmd *cmd = nullptr);
 // product-of-3 round (degree 3).  Publishes v[0] = g(0), v[1] = g(-1), v[2] = g(inf) (= X^3 coefficient) and
 // v[3] = g(1) when full == true.
 void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,

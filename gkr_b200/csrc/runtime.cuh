@@ -40,6 +40,8 @@ enum KernelClass { KC_ROUND = 0, KC_ROUND_FUSED, KC_PROD3, KC_PROD3_FUSED, KC_WI
                    KC_ROUND_TAIL, KC_PROD3_TAIL };
 // round launches below this many pairs are latency-bound "tail" launches, accounted separately from the streaming ones
 constexpr uint64_t kTailPairs = (uint64_t)1 << 16;
+// rounds below this many pairs are launched ahead of their challenge and wait for it in a mapped command block
+constexpr uint64_t kPrelaunchPairs = (uint64_t)1 << 12;
 
 // grow-only device buffer
 struct DevBuf {
@@ -100,6 +102,9 @@ struct gkr_ctx {
     static constexpr int kSlots = 64;
     gkr::HostSlot *slots_host = nullptr;   // pinned + mapped
     gkr::HostSlot *slots_dev = nullptr;
+    gkr::HostCmd *cmds_host = nullptr;     // pinned + mapped: challenge tables for pre-launched round kernels
+    gkr::HostCmd *cmds_dev = nullptr;
+    bool prelaunch = true;                 // pre-launch the small-table rounds of a phase (option "prelaunch")
     uint32_t seq = 0;
     gkr::ReduceWs ws{};
     unsigned int *words = nullptr;         // [8] device words: [0] range-error flag, [4..6] support/flags scratch

@@ -55,7 +55,10 @@ typedef struct gkr_witness gkr_witness;
 int gkr_ctx_create(int device, gkr_ctx **out);
 void gkr_ctx_destroy(gkr_ctx *ctx);
 /* options: "paranoid" = 1 makes every round also accumulate g(1) on the device and checks
- * g_j(0) + g_j(1) == g_{j-1}(r_{j-1}) on the host (default 0: g(1) is derived from the running claim) */
+ * g_j(0) + g_j(1) == g_{j-1}(r_{j-1}) on the host (default 0: g(1) is derived from the running claim);
+ * "prelaunch" = 0 disables launching the small-table rounds of a phase ahead of their challenges (default 1:
+ * those kernels wait up to ~30 s for each challenge in a mapped command block, so a transcript callback must
+ * not block for longer than that) */
 int gkr_ctx_set_option(gkr_ctx *ctx, const char *name, int value);
 /* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
 void *gkr_ctx_stream(gkr_ctx *ctx);

@@ -112,6 +112,19 @@ def test_paranoid_mode_matches_claim_derivation(pv):
     pp.close()
 
 
+def test_prelaunch_off_matches(pv):
+    """pre-launched (command-waiting) tail rounds vs plain per-round launches: same proof"""
+    from gkr_b200 import Prover
+    pn = Prover(0)
+    pn.set_option("prelaunch", 0)
+    rng = random.Random(321)
+    for ks in ([2, 3, 2], [11, 13, 12], [14, 14]):
+        layers = random_circuit(rng, ks, "mixed")
+        inputs = [rng.randrange(P) for _ in range(1 << ks[-1])]
+        assert_same_dense(_gpu_prove(pv, layers, inputs), _gpu_prove(pn, layers, inputs))
+    pn.close()
+
+
 def test_custom_transcript_callback(pv):
     """the challenge callback (how a Rust host keeps mimc_rs) must see the same messages and drive the same proof"""
     rng = random.Random(5)
