@@ -194,7 +194,7 @@ extern "C" void gkr_ctx_destroy(gkr_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->aux) cudaStreamSynchronize(ctx->aux);
     for (DevBuf *b : {&ctx->eqz, &ctx->equ, &ctx->eq_scratch, &ctx->H, &ctx->A, &ctx->foldA, &ctx->foldB, &ctx->lineA,
-                      &ctx->lineB, &ctx->mob, &ctx->misc, &ctx->stage, &ctx->aux_mob, &ctx->aux_stage, &ctx->qdev})
+                      &ctx->lineB, &ctx->mob, &ctx->misc, &ctx->stage, &ctx->aux_mob, &ctx->aux_stage, &ctx->qdev, &ctx->wP, &ctx->wQ})
         b->release();
     for (auto &kv : ctx->dev_pool) cudaFree(kv.second);
     ctx->dev_pool.clear();
@@ -789,6 +789,12 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
     GKR_TRY(ctx->lineB.ensure(sizeof(Fr) * std::max<uint64_t>(Nmax, 64)));
     GKR_TRY(ctx->mob.ensure(sizeof(Fr) * Nmax));
     GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
+    {
+        uint32_t max_gates = 1;
+        for (const LayerDev &L : c->layers) max_gates = std::max(max_gates, L.n_gates);
+        GKR_TRY(ctx->wP.ensure(sizeof(Fr) * max_gates));
+        GKR_TRY(ctx->wQ.ensure(sizeof(Fr) * max_gates));
+    }
 
     // d and input_func as dense monomial tables (prover.rs:88,93; get_multi_ext, poly.rs:502-536):
     // Moebius transform + D2H into pinned proof memory on the low-priority stream, overlapped with the rounds
@@ -841,8 +847,9 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
 
         GKR_TRY(eq_table_dev(ctx, z.data(), L.k_out, ctx->eqz.as<Fr>()));
         ctx->begin_launch();
-        launch_wiring_phase1(L.rowptr1, L.gate1, L.other1, ctx->eqz.as<Fr>(), W, H, A, N, ctx->stream);
-        ctx->end_launch(KC_WIRING, 76.0 * L.n_gates + 64.0 * N);
+        launch_wiring_phase1(L.rowptr1, L.gate1, L.other1, L.n_gates, ctx->eqz.as<Fr>(), W, ctx->wP.as<Fr>(),
+                             ctx->wQ.as<Fr>(), H, A, N, ctx->stream);
+        ctx->end_launch(KC_WIRING, 76.0 * L.n_gates + 64.0 * N, 2);
         GKR_TRY(ctx->check_launch("wiring_phase1"));
 
         uint32_t dep_mask = (uint32_t)(N - 1), max_deg = k;
@@ -876,8 +883,9 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         // ---- phase 2: variables c ----
         GKR_TRY(eq_table_dev(ctx, rs.data(), k, ctx->equ.as<Fr>()));
         ctx->begin_launch();
-        launch_wiring_phase2(L.rowptr2, L.gate2, L.other2, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu, H, A, N, ctx->stream);
-        ctx->end_launch(KC_WIRING, 76.0 * L.n_gates + 64.0 * N);
+        launch_wiring_phase2(L.rowptr2, L.gate2, L.other2, L.n_gates, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu,
+                             ctx->wP.as<Fr>(), H, A, N, ctx->stream);
+        ctx->end_launch(KC_WIRING, 76.0 * L.n_gates + 64.0 * N, 2);
         GKR_TRY(ctx->check_launch("wiring_phase2"));
         io.challenges = rs.data() + k;
         io.msgs = &P->msgs[3 * (ro + k)]; io.msg_len = &P->msg_len[ro + k]; io.chal_out = &P->chal[ro + k];

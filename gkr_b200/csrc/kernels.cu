@@ -307,47 +307,56 @@ void launch_eq_table(const FrVec &z, uint32_t k, Fr *out, Fr *scratch, cudaStrea
 }
 
 // ------------------------------------------------------------------------------------------------
-// wiring-predicate sums, one thread per row of the CSR (deterministic, no atomics)
+// wiring-predicate sums (deterministic, no atomics), two uniform passes over the CSR:
+//   edges: one thread per gate in CSR order: P[e] = X[gate[e]] * Y[other[e]]  (two independent gathers, one
+//          multiply; optionally Q[e] = X[gate[e]]) -- no divergence, one level of dependent loads
+//   rows : one thread per table row sums its contiguous segment of P (and Q) -- streaming reads
+// phase 1 (CSR by left):  X = eqz, Y = W:    H[b] = sum_add Q + sum_mul P ;  A[b] = sum_add P
+// phase 2 (CSR by right): X = eqz, Y = equ:  S_add, S_mul = sums of P by type; H2 = S_add + W(u) S_mul ; A2 = W(u) S_add
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_wiring_phase1(const uint32_t *__restrict__ rowptr,
-                                                            const uint32_t *__restrict__ csr_gate,
-                                                            const uint32_t *__restrict__ csr_other,
-                                                            const Fr *__restrict__ eqz, const Fr *__restrict__ W,
-                                                            Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n) {
+__global__ void __launch_bounds__(kThreads) k_wiring_edges(const uint32_t *__restrict__ csr_gate,
+                                                           const uint32_t *__restrict__ csr_other,
+                                                           const Fr *__restrict__ X, const Fr *__restrict__ Y,
+                                                           Fr *__restrict__ P, Fr *__restrict__ Q, uint32_t n_edges) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x) {
+        const uint32_t g = csr_gate[e], o = csr_other[e] & 0x7fffffffu;
+        const Fr x = ld_fr(X + g), y = ld_fr(Y + o);
+        st_fr(P + e, fr_mul(x, y));
+        if (Q) st_fr(Q + e, x);
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_wiring_rows1(const uint32_t *__restrict__ rowptr,
+                                                           const uint32_t *__restrict__ csr_other,
+                                                           const Fr *__restrict__ P, const Fr *__restrict__ Q,
+                                                           Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n) {
     for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < n; b += (uint64_t)gridDim.x * blockDim.x) {
         Fr h = fr_zero(), a = fr_zero();
         const uint32_t e0 = rowptr[b], e1 = rowptr[b + 1];
         for (uint32_t e = e0; e < e1; ++e) {
-            const uint32_t g = csr_gate[e], o = csr_other[e];
-            const Fr ez = ld_fr(eqz + g);
-            const Fr ew = fr_mul(ez, ld_fr(W + (o & 0x7fffffffu)));
-            if (o >> 31) {
-                h = fr_add(h, ew);                 // mult gate: eqz[g] * W[r_g] multiplies W(b)
+            const Fr p = ld_fr(P + e);
+            if (csr_other[e] >> 31) {
+                h = fr_add(h, p);                      // mult gate: eqz[g] * W[r_g] multiplies W(b)
             } else {
-                h = fr_add(h, ez);                 // add gate: eqz[g] multiplies W(b)
-                a = fr_add(a, ew);                 //           eqz[g] * W[r_g] is the constant part
+                h = fr_add(h, ld_fr(Q + e));           // add gate: eqz[g] multiplies W(b)
+                a = fr_add(a, p);                      //           eqz[g] * W[r_g] is the constant part
             }
         }
         st_fr(H + b, h);
         st_fr(A + b, a);
     }
 }
-__global__ void __launch_bounds__(kThreads) k_wiring_phase2(const uint32_t *__restrict__ rowptr,
-                                                            const uint32_t *__restrict__ csr_gate,
-                                                            const uint32_t *__restrict__ csr_other,
-                                                            const Fr *__restrict__ eqz, const Fr *__restrict__ equ,
-                                                            const Fr *__restrict__ wu_ptr, Fr *__restrict__ H,
-                                                            Fr *__restrict__ A, uint64_t n) {
+__global__ void __launch_bounds__(kThreads) k_wiring_rows2(const uint32_t *__restrict__ rowptr,
+                                                           const uint32_t *__restrict__ csr_other,
+                                                           const Fr *__restrict__ P, const Fr *__restrict__ wu_ptr,
+                                                           Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n) {
     const Fr wu = ld_fr(wu_ptr);
     for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
         Fr sa = fr_zero(), sm = fr_zero();
         const uint32_t e0 = rowptr[c], e1 = rowptr[c + 1];
         for (uint32_t e = e0; e < e1; ++e) {
-            const uint32_t g = csr_gate[e], o = csr_other[e];
-            const Fr t = fr_mul(ld_fr(eqz + g), ld_fr(equ + (o & 0x7fffffffu)));
-            if (o >> 31) sm = fr_add(sm, t); else sa = fr_add(sa, t);
+            const Fr p = ld_fr(P + e);
+            if (csr_other[e] >> 31) sm = fr_add(sm, p); else sa = fr_add(sa, p);
         }
-        // H2[c] = S_add + W(u) S_mul ;  A2[c] = W(u) S_add
         Fr h = sa, a = fr_zero();
         if (e1 > e0) {
             h = fr_add(sa, fr_mul(wu, sm));
@@ -357,13 +366,15 @@ __global__ void __launch_bounds__(kThreads) k_wiring_phase2(const uint32_t *__re
         st_fr(A + c, a);
     }
 }
-void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, const Fr *eqz,
-                          const Fr *W, Fr *H, Fr *A, uint64_t n, cudaStream_t s) {
-    k_wiring_phase1<<<stream_grid(n), kThreads, 0, s>>>(rowptr, csr_gate, csr_other, eqz, W, H, A, n);
+void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, uint32_t n_edges,
+                          const Fr *eqz, const Fr *W, Fr *P, Fr *Q, Fr *H, Fr *A, uint64_t n, cudaStream_t s) {
+    k_wiring_edges<<<stream_grid(n_edges), kThreads, 0, s>>>(csr_gate, csr_other, eqz, W, P, Q, n_edges);
+    k_wiring_rows1<<<stream_grid(n), kThreads, 0, s>>>(rowptr, csr_other, P, Q, H, A, n);
 }
-void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, const Fr *eqz,
-                          const Fr *equ, const Fr *wu, Fr *H, Fr *A, uint64_t n, cudaStream_t s) {
-    k_wiring_phase2<<<stream_grid(n), kThreads, 0, s>>>(rowptr, csr_gate, csr_other, eqz, equ, wu, H, A, n);
+void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, uint32_t n_edges,
+                          const Fr *eqz, const Fr *equ, const Fr *wu, Fr *P, Fr *H, Fr *A, uint64_t n, cudaStream_t s) {
+    k_wiring_edges<<<stream_grid(n_edges), kThreads, 0, s>>>(csr_gate, csr_other, eqz, equ, P, nullptr, n_edges);
+    k_wiring_rows2<<<stream_grid(n), kThreads, 0, s>>>(rowptr, csr_other, P, wu, H, A, n);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -477,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gkr_round_cmd(const Fr *__restr
 }
 
 // lazy accumulation pays once a thread sees several pairs: fewer, fatter CTAs (2 resident per SM)
-static inline bool use_lazy(uint64_t pairs) { return pairs >= ((uint64_t)1 << 18); }
+static inline bool use_lazy(uint64_t pairs) { return pairs >= ((uint64_t)1 << 20); }
 static inline int round_grid(uint64_t pairs, const ReduceWs &ws) {
     const int cap = use_lazy(pairs) ? device_sm_count() * 2 : ws.max_blocks;
     return grid_for(pairs, cap < ws.max_blocks ? cap : ws.max_blocks);

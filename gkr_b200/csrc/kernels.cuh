@@ -53,12 +53,13 @@ void launch_layer_eval(const uint8_t *type, const uint32_t *left, const uint32_t
 void launch_eq_table(const FrVec &z_mont, uint32_t k, Fr *out, Fr *scratch, cudaStream_t s);
 
 // ---- wiring-predicate sums (implicit in rust/src/gkr/sumcheck.rs:49-78,97-124) ------------------
+// Two passes: edge-parallel products P[e] (and Q[e] = eqz[gate[e]] in phase 1), then row sums.  P, Q: n_edges Fr.
 // CSR by left operand: row b lists (gate, right|type<<31)
-void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
-                          const Fr *eqz, const Fr *W, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
+void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, uint32_t n_edges,
+                          const Fr *eqz, const Fr *W, Fr *P, Fr *Q, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
 // CSR by right operand: row c lists (gate, left|type<<31); wu = W(u) on device
-void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
-                          const Fr *eqz, const Fr *equ, const Fr *wu, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
+void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, uint32_t n_edges,
+                          const Fr *eqz, const Fr *equ, const Fr *wu, Fr *P, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
 
 // ---- sumcheck rounds --------------------------------------------------------------------------
 // GKR round (degree 2) on (H, W, A).  Publishes v[0] = g(0), v[1] = X^2 coefficient, and v[2] = g(1)

@@ -169,6 +169,32 @@ def test_config2_synthetic_2p16_x8(pv):
             claim = verifier.horner(m, r)
 
 
+def test_large_layer_2p22_lazy_gkr_kernels(pv):
+    """one 2^22-gate layer over a 2^22 input layer: the only size class where the degree-2 round uses the lazy
+    512-bit accumulators (pairs >= 2^21); bit-exact vs the dense CPU oracle, also in paranoid mode"""
+    from gkr_b200 import Prover
+    k, seed = 22, 7
+    layers = syn.layered_circuit(seed, k, 1)
+    inputs = syn.input_values(seed, k)
+    ol = [orc.DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in layers]
+    vals = orc.evaluate_circuit(ol, inputs.view(np.uint8).reshape(-1, 32))
+    want = orc.gkr_prove(ol, vals)
+    c = pv.circuit(layers)
+    w = pv.witness_eval(c, inputs)
+    got = pv.prove(c, w)
+    w.close()
+    assert got.sumcheck_proofs == want.sumcheck_proofs and got.sumcheck_r == want.sumcheck_r
+    assert got.q == want.q and got.z == want.z and got.r == want.r
+    assert got.d_coef == want.d_coef and got.input_coef == want.input_coef
+    pp = Prover(0)
+    pp.set_option("paranoid", 1)
+    c2 = pp.circuit(layers)
+    w2 = pp.witness_eval(c2, inputs)
+    got2 = pp.prove(c2, w2)
+    assert got2.sumcheck_proofs == want.sumcheck_proofs and got2.q == want.q
+    pp.close()
+
+
 @pytest.mark.parametrize("seed", [1])
 def test_config3_synthetic_2p20_x16(pv, seed):
     """BASELINE.json config 3 at full size: 2^20 gates/layer x 16 layers, bit-exact vs the dense CPU oracle"""
