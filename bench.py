@@ -313,7 +313,22 @@ def run_ours(args):
                     for t in full:
                         t.close()
                 barrier()
+                # one proof of the headline circuit with every layer table-sharded over all ranks (strong scaling;
+                # latency-bound: 640 serial rounds each pay an NCCL all-gather)
+                try:
+                    sh_layers = syn.layered_circuit(1, k, layers)
+                    sh_circ = pv.circuit(sh_layers)                     # created after init_comm => per-rank CSRs
+                    sh_wit = pv.witness_eval(sh_circ, syn.input_values(1, k))
+
+                    def step_sharded():
+                        ptr = pv.prove_raw(sh_circ, sh_wit)
+                        pv.free_raw(ptr)
+                    gkr_sharded_ms = timed(step_sharded, max(2, args.steps // 2), 1) / max(2, args.steps // 2)
+                    sh_wit.close()
+                except GkrError as e:
+                    gkr_sharded_ms = f"error: {e}"
                 extra = {"sharding": f"low log2({world}) index bits, per-round ncclAllGather of 96-128 B partial sums",
+                         "gkr_table_sharded_ms_per_proof": gkr_sharded_ms,
                          "single_gpu_ms_same_run": single_ms,
                          "speedup_vs_single_gpu": (single_ms / sc_ms) if single_ms else None}
             sumcheck = {"n_vars": v, "tables": 3, "n_gpus": world, "ms": sc_ms, "melem_s": N / (sc_ms * 1e-3) / 1e6,

@@ -194,7 +194,7 @@ extern "C" void gkr_ctx_destroy(gkr_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->aux) cudaStreamSynchronize(ctx->aux);
     for (DevBuf *b : {&ctx->eqz, &ctx->equ, &ctx->eq_scratch, &ctx->H, &ctx->A, &ctx->foldA, &ctx->foldB, &ctx->lineA,
-                      &ctx->lineB, &ctx->mob, &ctx->misc, &ctx->stage, &ctx->aux_mob, &ctx->aux_stage, &ctx->qdev, &ctx->wP, &ctx->wQ})
+                      &ctx->lineB, &ctx->mob, &ctx->misc, &ctx->stage, &ctx->aux_mob, &ctx->aux_stage, &ctx->qdev, &ctx->wP, &ctx->wQ, &ctx->shard_w, &ctx->shard_mini})
         b->release();
     for (auto &kv : ctx->dev_pool) cudaFree(kv.second);
     ctx->dev_pool.clear();
@@ -370,6 +370,8 @@ static int mobius_support(gkr_ctx *ctx, Fr *table, uint32_t k, uint32_t *dep_mas
 // ------------------------------------------------------------------------------------------------
 struct LayerDev {
     uint32_t k_out = 0, k_in = 0, n_gates = 0;
+    bool sharded = false;         // CSRs hold only this rank's rows (row b = i * n_ranks + rank stored as i)
+    uint32_t n_edges1 = 0, n_edges2 = 0;
     uint8_t *type = nullptr;
     uint32_t *left = nullptr, *right = nullptr;
     uint32_t *rowptr1 = nullptr, *gate1 = nullptr, *other1 = nullptr;   // CSR by left operand
@@ -377,22 +379,30 @@ struct LayerDev {
 };
 struct gkr_circuit {
     int device = 0;
+    int n_ranks = 1, rank = 0;    // communicator geometry the CSRs were built for
     std::vector<LayerDev> layers;
     std::vector<uint32_t> k;      // k_0 .. k_depth
     uint32_t max_k = 0;
 };
 
-// stable counting sort of the gates of one layer by `key` -> CSR rows
+// stable counting sort of the gates of one layer by `key` -> CSR rows.  With n_ranks > 1 only the rows
+// key % n_ranks == rank are kept, stored under the local row index key / n_ranks (multi-GPU sharding on the
+// low index bits); gate ids and the other operand stay global (eq tables and W are replicated).
 static void build_csr(uint32_t n_rows, uint32_t n_gates, const uint32_t *key, const uint32_t *other, const uint8_t *type,
-                      std::vector<uint32_t> &rowptr, std::vector<uint32_t> &gate, std::vector<uint32_t> &oth) {
-    rowptr.assign((size_t)n_rows + 1, 0);
-    for (uint32_t g = 0; g < n_gates; ++g) rowptr[key[g] + 1]++;
-    for (uint32_t r = 0; r < n_rows; ++r) rowptr[r + 1] += rowptr[r];
+                      uint32_t n_ranks, uint32_t rank, std::vector<uint32_t> &rowptr, std::vector<uint32_t> &gate,
+                      std::vector<uint32_t> &oth) {
+    const uint32_t local_rows = n_rows / n_ranks;
+    rowptr.assign((size_t)local_rows + 1, 0);
+    uint32_t n_edges = 0;
+    for (uint32_t g = 0; g < n_gates; ++g)
+        if (key[g] % n_ranks == rank) { rowptr[key[g] / n_ranks + 1]++; ++n_edges; }
+    for (uint32_t r = 0; r < local_rows; ++r) rowptr[r + 1] += rowptr[r];
     std::vector<uint32_t> cursor(rowptr.begin(), rowptr.end() - 1);
-    gate.resize(n_gates);
-    oth.resize(n_gates);
+    gate.resize(n_edges);
+    oth.resize(n_edges);
     for (uint32_t g = 0; g < n_gates; ++g) {
-        const uint32_t pos = cursor[key[g]]++;
+        if (key[g] % n_ranks != rank) continue;
+        const uint32_t pos = cursor[key[g] / n_ranks]++;
         gate[pos] = g;
         oth[pos] = other[g] | ((uint32_t)type[g] << 31);
     }
@@ -451,6 +461,10 @@ extern "C" int gkr_circuit_create(gkr_ctx *ctx, uint32_t n_layers, const gkr_lay
     std::unique_ptr<gkr_circuit, void (*)(gkr_circuit *)> c(new (std::nothrow) gkr_circuit(), gkr_circuit_destroy);
     if (!c) return GKR_ERR_OOM;
     c->device = ctx->device;
+    c->n_ranks = ctx->nccl_comm ? ctx->n_ranks : 1;
+    c->rank = ctx->nccl_comm ? ctx->rank : 0;
+    uint32_t lb = 0;
+    while ((1 << lb) < c->n_ranks) ++lb;
     c->layers.resize(n_layers);
     c->k.push_back(layers[0].k_out);
     std::vector<uint32_t> rowptr, gate, oth;
@@ -464,12 +478,17 @@ extern "C" int gkr_circuit_create(gkr_ctx *ctx, uint32_t n_layers, const gkr_lay
         GKR_TRY(dev_copy(ctx, &L.left, d.left, d.n_gates));
         GKR_TRY(dev_copy(ctx, &L.right, d.right, d.n_gates));
         const uint32_t rows = (uint32_t)1 << d.k_in;
-        build_csr(rows, d.n_gates, d.left, d.right, d.type, rowptr, gate, oth);
+        // a layer is table-sharded across the ranks when every rank keeps at least two rows of it
+        L.sharded = c->n_ranks > 1 && d.k_in >= lb + 1;
+        const uint32_t P = L.sharded ? (uint32_t)c->n_ranks : 1u, rk = L.sharded ? (uint32_t)c->rank : 0u;
+        build_csr(rows, d.n_gates, d.left, d.right, d.type, P, rk, rowptr, gate, oth);
+        L.n_edges1 = (uint32_t)gate.size();
         GKR_TRY(dev_copy(ctx, &L.rowptr1, rowptr.data(), rowptr.size()));
         GKR_TRY(dev_copy(ctx, &L.gate1, gate.data(), gate.size()));
         GKR_TRY(dev_copy(ctx, &L.other1, oth.data(), oth.size()));
         GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // host vectors are reused below
-        build_csr(rows, d.n_gates, d.right, d.left, d.type, rowptr, gate, oth);
+        build_csr(rows, d.n_gates, d.right, d.left, d.type, P, rk, rowptr, gate, oth);
+        L.n_edges2 = (uint32_t)gate.size();
         GKR_TRY(dev_copy(ctx, &L.rowptr2, rowptr.data(), rowptr.size()));
         GKR_TRY(dev_copy(ctx, &L.gate2, gate.data(), gate.size()));
         GKR_TRY(dev_copy(ctx, &L.other2, oth.data(), oth.size()));
@@ -592,6 +611,7 @@ struct PhaseIO {
     uint8_t *msg_len;          // out: [k]
     gkr_fr *chal_out;          // out: [k] canonical
     const Fr *W_last;          // out: device pointer to the size-2 W table of the last round
+    uint32_t shard_bits = 0;   // > 0: H, W, A hold this rank's shard (2^(k - shard_bits) rows each)
 };
 
 // host -> waiting kernel: payload first, then the five line tags (x86 keeps the store order)
@@ -607,6 +627,119 @@ static void write_cmd(HostCmd *c, const FrConstMul *K, uint32_t tag) {
     std::atomic_thread_fence(std::memory_order_release);
     for (int line = 0; line < 5; ++line) c->w[line * 16 + 15] = tag;
     std::atomic_thread_fence(std::memory_order_release);
+}
+
+struct RoundState {
+    HFr claim, r;
+    bool have_claim;
+};
+// host half of one round: published sums -> message (static length rule) -> challenge -> next claim
+static int consume_round(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, uint32_t j, bool full, const HostSlot *slot,
+                         RoundState &st, HFr *last_hash) {
+    const uint32_t k = io.k;
+    HFr x0 = to_host(slot->v[0]), x2 = to_host(slot->v[1]), x1 = full ? to_host(slot->v[2]) : hfr_zero();
+    if (hf::geq_p(x0.l) || hf::geq_p(x2.l) || hf::geq_p(x1.l)) {
+        set_last_error("device published an unreduced round value");
+        return GKR_ERR_INTERNAL;
+    }
+    if (!full) {
+        x1 = hfr_sub(st.claim, x0);                  // g(0) + g(1) = claim
+    } else if (st.have_claim && !hfr_eq(hfr_add(x0, x1), st.claim)) {
+        set_last_error("sumcheck claim mismatch at round %u: g(0)+g(1) != previous g(r)", j);
+        return GKR_ERR_INTERNAL;
+    }
+    // message: descending coefficients [c2, c1, c0] or [c1, c0] when W does not depend on x_{j+1}
+    const HFr c1 = hfr_sub(hfr_sub(x1, x0), x2);
+    const bool dep = (io.dep_mask >> (k - 1 - j)) & 1u;
+    HFr msg[3];
+    uint32_t len;
+    if (dep) { msg[0] = x2; msg[1] = c1; msg[2] = x0; len = 3; }
+    else { msg[0] = c1; msg[1] = x0; len = 2; }
+    std::memset(&io.msgs[3 * j], 0, 3 * sizeof(gkr_fr));
+    for (uint32_t i = 0; i < len; ++i) hfr_to_canonical(&io.msgs[3 * j + i], msg[i]);
+    io.msg_len[j] = (uint8_t)len;
+    GKR_TRY(challenge_for(ctx, t, msg, len, &st.r));
+    io.challenges[j] = st.r;
+    hfr_to_canonical(&io.chal_out[j], st.r);
+    *last_hash = st.r;
+    st.claim = hfr_add(hfr_mul(hfr_add(hfr_mul(x2, st.r), c1), st.r), x0);      // g(r), Horner
+    st.have_claim = true;
+    return GKR_OK;
+}
+
+// Multi-GPU phase: H, W, A are this rank's shards (rows idx = i * P + rank).  The first k - log2(P) rounds
+// reduce locally, all-gather the partial sums (NCCL) and add them on every rank; then every rank folds its
+// last two rows, the single entries are gathered and the remaining log2(P) rounds run on the P-entry tables.
+static int run_phase_sharded(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *last_hash, const HFr *claim_in,
+                             HFr *claim_out) {
+    const uint32_t k = io.k, lb = io.shard_bits, k_local = k - lb;
+    const int P = 1 << lb;
+    const uint64_t Nloc = (uint64_t)1 << k_local;
+    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(Nloc / 2, 64)));
+    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(Nloc / 4, 64)));
+    GKR_TRY(ctx->shard_mini.ensure(sizeof(Fr) * 3 * (size_t)P));
+    const Fr *Hc = io.H, *Wc = io.W, *Ac = io.A;
+    uint64_t n = Nloc;
+    bool pending_fold = false;
+    int flip = 0;
+    RoundState st{claim_in ? *claim_in : hfr_zero(), hfr_zero(), claim_in != nullptr};
+    for (uint32_t j = 0; j < k; ++j) {
+        const bool sharded_round = j < k_local;
+        if (j == k_local) {
+            const FrConstMul rc = make_const_mul(st.r);
+            const Fr *cur[3] = {Hc, Wc, Ac};
+            for (int i = 0; i < 3; ++i) {
+                ctx->begin_launch();
+                launch_fold(cur[i], ctx->comm_send + i, rc, 1, ctx->stream);
+                ctx->end_launch(KC_OTHER, 96.0);
+                GKR_TRY(ctx->check_launch("fold"));
+            }
+            GKR_TRY(comm_all_gather(ctx, ctx->comm_send, ctx->comm_recv, 3 * sizeof(Fr)));
+            Fr *mini = ctx->shard_mini.as<Fr>();
+            ctx->begin_launch();
+            launch_transpose_gathered(ctx->comm_recv, mini, P, 3, ctx->stream);
+            ctx->end_launch(KC_OTHER, 192.0 * P);
+            GKR_TRY(ctx->check_launch("transpose_gathered"));
+            Hc = mini; Wc = mini + P; Ac = mini + 2 * P;
+            n = (uint64_t)P;
+            pending_fold = false;
+        }
+        const uint32_t s = ctx->next_seq();
+        const bool full = !st.have_claim || ctx->paranoid;
+        const FrConstMul rc = pending_fold ? make_const_mul(st.r) : FrConstMul{};
+        Fr *dev_out = sharded_round ? ctx->comm_send : nullptr;
+        ctx->begin_launch();
+        if (!pending_fold) {
+            launch_gkr_round(false, full, Hc, Wc, Ac, nullptr, nullptr, nullptr, rc, n / 2, ctx->ws, ctx->slot_dev(s), s,
+                             ctx->stream, nullptr, dev_out);
+            ctx->end_launch(n / 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full ? 96.0 : 80.0) * n);
+        } else {
+            DevBuf &dst = (flip ^= 1) ? ctx->foldA : ctx->foldB;
+            const uint64_t half = n / 2;
+            Fr *Ho = dst.as<Fr>(), *Wo = Ho + half, *Ao = Wo + half;
+            launch_gkr_round(true, full, Hc, Wc, Ac, Ho, Wo, Ao, rc, half / 2, ctx->ws, ctx->slot_dev(s), s, ctx->stream,
+                             nullptr, dev_out);
+            ctx->end_launch(half / 2 >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 144.0 * n);
+            Hc = Ho; Wc = Wo; Ac = Ao;
+            n = half;
+        }
+        GKR_TRY(ctx->check_launch("gkr_round"));
+        if (sharded_round) {
+            const int K = full ? 3 : 2;
+            GKR_TRY(comm_all_gather(ctx, ctx->comm_send, ctx->comm_recv, (size_t)K * sizeof(Fr)));
+            ctx->begin_launch();
+            launch_sum_ranks_publish(ctx->comm_recv, P, K, ctx->slot_dev(s), s, ctx->stream);
+            ctx->end_launch(KC_OTHER, 32.0 * K * P);
+            GKR_TRY(ctx->check_launch("sum_ranks_publish"));
+        }
+        pending_fold = true;
+        const HostSlot *slot;
+        GKR_TRY(ctx->wait_slot(s, &slot));
+        GKR_TRY(consume_round(ctx, t, io, j, full, slot, st, last_hash));
+    }
+    io.W_last = Wc;
+    if (claim_out) *claim_out = st.claim;
+    return GKR_OK;
 }
 
 // claim: in = g_{prev}(r_prev) if known (nullptr => the first round also accumulates g(1) on the device);
@@ -664,15 +797,13 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
         }
     } guard{ctx, plan};
     const bool can_prelaunch = ctx->prelaunch && !ctx->profiling;
-    HFr r = hfr_zero();
-    HFr claim = claim_in ? *claim_in : hfr_zero();
-    bool have_claim = claim_in != nullptr;
+    RoundState st{claim_in ? *claim_in : hfr_zero(), hfr_zero(), claim_in != nullptr};
     for (uint32_t j = 0; j < k; ++j) {
         Plan &p = plan[j];
-        const bool full = !have_claim || ctx->paranoid;
+        const bool full = !st.have_claim || ctx->paranoid;
         if (!p.launched) {
             p.seq = ctx->next_seq();
-            const FrConstMul rc = j ? make_const_mul(r) : FrConstMul{};
+            const FrConstMul rc = j ? make_const_mul(st.r) : FrConstMul{};
             ctx->begin_launch();
             launch_gkr_round(j != 0, full, p.H, p.W, p.A, p.Ho, p.Wo, p.Ao, rc, p.pairs, ctx->ws, ctx->slot_dev(p.seq), p.seq,
                              ctx->stream);
@@ -702,41 +833,15 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
             set_last_error("pre-launched round kernel %u gave up waiting for its challenge", j);
             return GKR_ERR_INTERNAL;
         }
-        HFr x0 = to_host(slot->v[0]), x2 = to_host(slot->v[1]), x1 = full ? to_host(slot->v[2]) : hfr_zero();
-        if (hf::geq_p(x0.l) || hf::geq_p(x2.l) || hf::geq_p(x1.l)) {
-            set_last_error("device published an unreduced round value");
-            return GKR_ERR_INTERNAL;
-        }
-        if (!full) {
-            x1 = hfr_sub(claim, x0);                  // g(0) + g(1) = claim
-        } else if (have_claim && !hfr_eq(hfr_add(x0, x1), claim)) {
-            set_last_error("sumcheck claim mismatch at round %u: g(0)+g(1) != previous g(r)", j);
-            return GKR_ERR_INTERNAL;
-        }
-        // message: descending coefficients [c2, c1, c0] or [c1, c0] when W does not depend on x_{j+1}
-        const HFr c1 = hfr_sub(hfr_sub(x1, x0), x2);
-        const bool dep = (io.dep_mask >> (k - 1 - j)) & 1u;
-        HFr msg[3];
-        uint32_t len;
-        if (dep) { msg[0] = x2; msg[1] = c1; msg[2] = x0; len = 3; }
-        else { msg[0] = c1; msg[1] = x0; len = 2; }
-        std::memset(&io.msgs[3 * j], 0, 3 * sizeof(gkr_fr));
-        for (uint32_t i = 0; i < len; ++i) hfr_to_canonical(&io.msgs[3 * j + i], msg[i]);
-        io.msg_len[j] = (uint8_t)len;
-        GKR_TRY(challenge_for(ctx, t, msg, len, &r));
-        // hand the challenge to the next (already running, waiting) kernel as early as possible
+        GKR_TRY(consume_round(ctx, t, io, j, full, slot, st, last_hash));
+        // hand the challenge to the next (already running, waiting) kernel
         if (j + 1 < k && plan[j + 1].launched && !plan[j + 1].commanded) {
-            const FrConstMul rc = make_const_mul(r);
+            const FrConstMul rc = make_const_mul(st.r);
             write_cmd(ctx->cmds_host + (plan[j + 1].seq % gkr_ctx::kSlots), &rc, plan[j + 1].seq);
             plan[j + 1].commanded = true;
         }
-        io.challenges[j] = r;
-        hfr_to_canonical(&io.chal_out[j], r);
-        *last_hash = r;
-        claim = hfr_add(hfr_mul(hfr_add(hfr_mul(x2, r), c1), r), x0);      // g(r), Horner
-        have_claim = true;
     }
-    if (claim_out) *claim_out = claim;
+    if (claim_out) *claim_out = st.claim;
     return GKR_OK;
 }
 
@@ -751,6 +856,13 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         set_last_error("gkr_prove: witness/circuit/context mismatch");
         return GKR_ERR_INVALID;
     }
+    if (c->n_ranks != (ctx->nccl_comm ? ctx->n_ranks : 1) || c->rank != (ctx->nccl_comm ? ctx->rank : 0)) {
+        set_last_error("gkr_prove: the circuit was created for %d rank(s) / rank %d; create it after gkr_comm_init on "
+                       "this context", c->n_ranks, c->rank);
+        return GKR_ERR_INVALID;
+    }
+    uint32_t shard_bits = 0;
+    while ((1 << shard_bits) < c->n_ranks) ++shard_bits;
     GKR_TRY(ctx->bind());
     const uint32_t n_layers = (uint32_t)c->layers.size();
     std::unique_ptr<ProofHolder> P(new (std::nothrow) ProofHolder());
@@ -845,11 +957,23 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         ctx->end_launch(KC_MOBIUS, 32.0 * N);
         GKR_TRY(ctx->check_launch("alt_sum"));
 
+        // table-sharded layer: this rank owns rows idx = i * P + rank of H, A and of the W copy the rounds fold;
+        // eq tables and W_{i+1} itself stay replicated (the wiring sums gather from them at random)
+        const uint64_t Nrows = L.sharded ? (N >> shard_bits) : N;
+        const Fr *Wrounds = W;
+        if (L.sharded) {
+            GKR_TRY(ctx->shard_w.ensure(sizeof(Fr) * Nrows));
+            ctx->begin_launch();
+            launch_take_strided(W, ctx->shard_w.as<Fr>(), (uint64_t)c->rank, (uint64_t)c->n_ranks, Nrows, ctx->stream);
+            ctx->end_launch(KC_OTHER, 64.0 * Nrows);
+            GKR_TRY(ctx->check_launch("take_strided"));
+            Wrounds = ctx->shard_w.as<Fr>();
+        }
         GKR_TRY(eq_table_dev(ctx, z.data(), L.k_out, ctx->eqz.as<Fr>()));
         ctx->begin_launch();
-        launch_wiring_phase1(L.rowptr1, L.gate1, L.other1, L.n_gates, ctx->eqz.as<Fr>(), W, ctx->wP.as<Fr>(),
-                             ctx->wQ.as<Fr>(), H, A, N, ctx->stream);
-        ctx->end_launch(KC_WIRING, 76.0 * L.n_gates + 64.0 * N, 2);
+        launch_wiring_phase1(L.rowptr1, L.gate1, L.other1, L.n_edges1, ctx->eqz.as<Fr>(), W, ctx->wP.as<Fr>(),
+                             ctx->wQ.as<Fr>(), H, A, Nrows, ctx->stream);
+        ctx->end_launch(KC_WIRING, 76.0 * L.n_edges1 + 64.0 * Nrows, 2);
         GKR_TRY(ctx->check_launch("wiring_phase1"));
 
         uint32_t dep_mask = (uint32_t)(N - 1), max_deg = k;
@@ -869,11 +993,13 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
 
         // ---- phase 1: variables b ----
         PhaseIO io{};
-        io.H = H; io.W = W; io.A = A; io.k = k; io.dep_mask = dep_mask;
+        io.H = H; io.W = Wrounds; io.A = A; io.k = k; io.dep_mask = dep_mask;
+        io.shard_bits = L.sharded ? shard_bits : 0;
         io.challenges = rs.data();
         io.msgs = &P->msgs[3 * ro]; io.msg_len = &P->msg_len[ro]; io.chal_out = &P->chal[ro];
         HFr claim = hfr_zero();
-        GKR_TRY(run_phase(ctx, t, io, &last_hash, nullptr, &claim));
+        GKR_TRY(L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, nullptr, &claim)
+                          : run_phase(ctx, t, io, &last_hash, nullptr, &claim));
         // W(u): fold the last size-2 W table with r_k
         ctx->begin_launch();
         launch_fold(io.W_last, wu, make_const_mul(rs[k - 1]), 1, ctx->stream);
@@ -883,13 +1009,14 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         // ---- phase 2: variables c ----
         GKR_TRY(eq_table_dev(ctx, rs.data(), k, ctx->equ.as<Fr>()));
         ctx->begin_launch();
-        launch_wiring_phase2(L.rowptr2, L.gate2, L.other2, L.n_gates, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu,
-                             ctx->wP.as<Fr>(), H, A, N, ctx->stream);
-        ctx->end_launch(KC_WIRING, 76.0 * L.n_gates + 64.0 * N, 2);
+        launch_wiring_phase2(L.rowptr2, L.gate2, L.other2, L.n_edges2, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu,
+                             ctx->wP.as<Fr>(), H, A, Nrows, ctx->stream);
+        ctx->end_launch(KC_WIRING, 76.0 * L.n_edges2 + 64.0 * Nrows, 2);
         GKR_TRY(ctx->check_launch("wiring_phase2"));
         io.challenges = rs.data() + k;
         io.msgs = &P->msgs[3 * (ro + k)]; io.msg_len = &P->msg_len[ro + k]; io.chal_out = &P->chal[ro + k];
-        GKR_TRY(run_phase(ctx, t, io, &last_hash, &claim, &claim));
+        GKR_TRY(L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, &claim, &claim)
+                          : run_phase(ctx, t, io, &last_hash, &claim, &claim));
 
         // ---- q_i = W restricted to the line b* -> c* (poly.rs:469-500): needs only b*, c* => runs on the
         //      low-priority stream while the next layer's rounds proceed; collected after the last layer ----

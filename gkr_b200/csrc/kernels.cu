@@ -392,7 +392,7 @@ __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const
                                                const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                                Fr *__restrict__ Wout, Fr *__restrict__ Aout, const KT &r,
                                                uint64_t q, Fr *partials, unsigned int *counter,
-                                               HostSlot *slot, uint32_t seq) {
+                                               HostSlot *slot, uint32_t seq, Fr *dev_out = nullptr) {
     constexpr int K = FULL ? 3 : 2;
     Fr acc[K];
     FrWide wide[LAZY ? K : 1];
@@ -456,15 +456,15 @@ __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const
 #pragma unroll
         for (int j = 0; j < K; ++j) acc[j] = fr_add(acc[j], wide_reduce(wide[j]));
     }
-    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u);
+    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, dev_out);
 }
 template <bool FOLD, bool FULL, bool LAZY>
 __global__ void __launch_bounds__(kThreads, 2) k_gkr_round(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
                                                            const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                                            Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
                                                            uint64_t q, Fr *partials, unsigned int *counter,
-                                                           HostSlot *slot, uint32_t seq) {
-    gkr_round_body<FOLD, FULL, LAZY, false>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq);
+                                                           HostSlot *slot, uint32_t seq, Fr *dev_out) {
+    gkr_round_body<FOLD, FULL, LAZY, false>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq, dev_out);
 }
 // pre-launched variant: waits for the challenge's constant table in a mapped command block
 template <bool FULL>
@@ -499,16 +499,16 @@ static inline int round_grid(uint64_t pairs, const ReduceWs &ws) {
 static inline bool use_lazy_gkr(uint64_t pairs) { return pairs >= ((uint64_t)1 << 21); }
 template <bool FOLD, bool FULL>
 static void launch_gkr_round_t(const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
-                               uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+                               uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s, Fr *dev_out) {
     const int grid = use_lazy_gkr(pairs) ? round_grid(pairs, ws) : grid_for(pairs, ws.max_blocks);
     if (use_lazy_gkr(pairs))
-        k_gkr_round<FOLD, FULL, true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
+        k_gkr_round<FOLD, FULL, true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq, dev_out);
     else
-        k_gkr_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq);
+        k_gkr_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq, dev_out);
 }
 void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
                       const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s,
-                      const HostCmd *cmd) {
+                      const HostCmd *cmd, Fr *dev_out) {
     if (cmd) {
         const int grid = grid_for(pairs, ws.max_blocks);
         if (full) k_gkr_round_cmd<true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, cmd, pairs, ws.partials, ws.counter, slot, seq);
@@ -516,11 +516,11 @@ void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *
         return;
     }
     if (fold) {
-        if (full) launch_gkr_round_t<true, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
-        else launch_gkr_round_t<true, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
+        if (full) launch_gkr_round_t<true, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, dev_out);
+        else launch_gkr_round_t<true, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, dev_out);
     } else {
-        if (full) launch_gkr_round_t<false, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
-        else launch_gkr_round_t<false, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s);
+        if (full) launch_gkr_round_t<false, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, dev_out);
+        else launch_gkr_round_t<false, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, dev_out);
     }
 }
 
@@ -665,6 +665,15 @@ void launch_transpose_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_t
     k_transpose_gathered<<<1, 64, 0, s>>>(gathered, out, n_ranks, n_tables);
 }
 
+// multi-GPU: this rank's shard of a replicated table: out[i] = in[i * stride + first]
+__global__ void __launch_bounds__(kThreads) k_take_strided(const Fr *__restrict__ in, Fr *__restrict__ out, uint64_t first,
+                                                           uint64_t stride, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        st_fr(out + i, ld_fr(in + i * stride + first));
+}
+void launch_take_strided(const Fr *in, Fr *out, uint64_t first, uint64_t stride, uint64_t n, cudaStream_t s) {
+    k_take_strided<<<stream_grid(n), kThreads, 0, s>>>(in, out, first, stride, n);
+}
 __global__ void __launch_bounds__(kThreads) k_fold(const Fr *__restrict__ in, Fr *__restrict__ out, FrConstMul r, uint64_t half) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < half; i += (uint64_t)gridDim.x * blockDim.x)
         st_fr(out + i, fold2(ld_fr(in + i), ld_fr(in + i + half), r));

@@ -71,7 +71,8 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 // (bounded spin) in the mapped command block, so that launch latency overlaps the host transcript.
 void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
                       const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
-                      cudaStream_t s, const HostCmd *cmd = nullptr);
+                      cudaStream_t s, const HostCmd *cmd = nullptr, Fr *dev_out = nullptr);
+void launch_take_strided(const Fr *in, Fr *out, uint64_t first, uint64_t stride, uint64_t n, cudaStream_t s);
 // product-of-3 round (degree 3).  Publishes v[0] = g(0), v[1] = g(-1), v[2] = g(inf) (= X^3 coefficient) and
 // v[3] = g(1) when full == true.
 void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,

@@ -122,7 +122,7 @@ struct gkr_ctx {
     void pool_put(void *p, size_t bytes) { if (p) dev_pool.emplace(bytes, p); }
 
     // workspaces
-    gkr::DevBuf eqz, equ, eq_scratch, H, A, foldA, foldB, lineA, lineB, mob, misc, stage, aux_mob, aux_stage, qdev, wP, wQ;
+    gkr::DevBuf eqz, equ, eq_scratch, H, A, foldA, foldB, lineA, lineB, mob, misc, stage, aux_mob, aux_stage, qdev, wP, wQ, shard_w, shard_mini;
 
     // accounting
     gkr_stats stats{};
