@@ -97,8 +97,10 @@ extern "C" int gkr_comm_init(gkr_ctx *ctx, int n_ranks, int rank, const uint8_t 
     ctx->nccl_comm = comm;
     ctx->n_ranks = n_ranks;
     ctx->rank = rank;
-    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->comm_send, sizeof(Fr) * 8));
-    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->comm_recv, sizeof(Fr) * 8 * (size_t)n_ranks));
+    // room for the per-round partial sums and for the one-off gather of the folded shards (3 tables)
+    const size_t per_rank = 8 + 3 * (size_t)kGatherEntries;
+    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->comm_send, sizeof(Fr) * per_rank));
+    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->comm_recv, sizeof(Fr) * per_rank * (size_t)n_ranks));
     return GKR_OK;
 }
 

@@ -675,35 +675,43 @@ static int run_phase_sharded(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io,
     const uint32_t k = io.k, lb = io.shard_bits, k_local = k - lb;
     const int P = 1 << lb;
     const uint64_t Nloc = (uint64_t)1 << k_local;
-    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(Nloc / 2, 64)));
-    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(Nloc / 4, 64)));
-    GKR_TRY(ctx->shard_mini.ensure(sizeof(Fr) * 3 * (size_t)P));
+    const uint64_t fold_cap = std::max<uint64_t>(std::max<uint64_t>(Nloc / 2, 64), kGatherEntries * (uint64_t)P / 2);
+    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * fold_cap));
+    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * fold_cap));
     const Fr *Hc = io.H, *Wc = io.W, *Ac = io.A;
     uint64_t n = Nloc;
     bool pending_fold = false;
     int flip = 0;
     RoundState st{claim_in ? *claim_in : hfr_zero(), hfr_zero(), claim_in != nullptr};
+    bool gathered = false;
     for (uint32_t j = 0; j < k; ++j) {
-        const bool sharded_round = j < k_local;
-        if (j == k_local) {
-            const FrConstMul rc = make_const_mul(st.r);
+        if (!gathered && n <= std::max<uint64_t>(kGatherEntries, 2) && (pending_fold || n <= kGatherEntries / 2)) {
+            const uint64_t m = pending_fold ? n / 2 : n;
+            Fr *send = ctx->comm_send + 8;
             const Fr *cur[3] = {Hc, Wc, Ac};
             for (int i = 0; i < 3; ++i) {
-                ctx->begin_launch();
-                launch_fold(cur[i], ctx->comm_send + i, rc, 1, ctx->stream);
-                ctx->end_launch(KC_OTHER, 96.0);
-                GKR_TRY(ctx->check_launch("fold"));
+                if (pending_fold) {
+                    ctx->begin_launch();
+                    launch_fold(cur[i], send + i * m, make_const_mul(st.r), m, ctx->stream);
+                    ctx->end_launch(KC_OTHER, 96.0 * m);
+                    GKR_TRY(ctx->check_launch("fold"));
+                } else {
+                    GKR_CUDA_TRY(cudaMemcpyAsync(send + i * m, cur[i], m * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+                }
             }
-            GKR_TRY(comm_all_gather(ctx, ctx->comm_send, ctx->comm_recv, 3 * sizeof(Fr)));
+            GKR_TRY(comm_all_gather(ctx, send, ctx->comm_recv, 3 * m * sizeof(Fr)));
+            GKR_TRY(ctx->shard_mini.ensure(sizeof(Fr) * 3 * m * (size_t)P));
             Fr *mini = ctx->shard_mini.as<Fr>();
             ctx->begin_launch();
-            launch_transpose_gathered(ctx->comm_recv, mini, P, 3, ctx->stream);
-            ctx->end_launch(KC_OTHER, 192.0 * P);
-            GKR_TRY(ctx->check_launch("transpose_gathered"));
-            Hc = mini; Wc = mini + P; Ac = mini + 2 * P;
-            n = (uint64_t)P;
+            launch_interleave_gathered(ctx->comm_recv, mini, P, 3, m, ctx->stream);
+            ctx->end_launch(KC_OTHER, 192.0 * m * P);
+            GKR_TRY(ctx->check_launch("interleave_gathered"));
+            Hc = mini; Wc = mini + m * P; Ac = mini + 2 * m * P;
+            n = m * (uint64_t)P;
             pending_fold = false;
+            gathered = true;
         }
+        const bool sharded_round = !gathered;
         const uint32_t s = ctx->next_seq();
         const bool full = !st.have_claim || ctx->paranoid;
         const FrConstMul rc = pending_fold ? make_const_mul(st.r) : FrConstMul{};
@@ -1127,9 +1135,10 @@ static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3]
     while ((1 << lb) < P) ++lb;
     const uint32_t local_vars = n_vars - lb;
     const uint64_t Nloc = (uint64_t)1 << local_vars;
-    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(Nloc / 2, 64)));
-    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(Nloc / 4, 64)));
-    GKR_TRY(ctx->misc.ensure(sizeof(Fr) * (64 + 3 * (size_t)P)));
+    const uint64_t fold_cap = std::max<uint64_t>(std::max<uint64_t>(Nloc / 2, 64), P > 1 ? kGatherEntries * (uint64_t)P / 2 : 0);
+    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * fold_cap));
+    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * fold_cap));
+    GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
     const HFr inv2 = hfr_inv(hfr_from_u64(2));
     const Fr *Ac = T[0], *Bc = T[1], *Cc = T[2];
     uint64_t n = Nloc;                 // entries per current table on this rank
@@ -1137,30 +1146,37 @@ static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3]
     int flip = 0;                      // ping-pong between foldA / foldB
     HFr r = hfr_zero();
     HFr claim = hfr_zero();
+    bool gathered = (P == 1);
     for (uint32_t j = 0; j < n_vars; ++j) {
-        const bool sharded_round = P > 1 && j < local_vars;
-        if (P > 1 && j == local_vars) {
-            // every rank is down to 2 entries per table: fold them with r, gather the single entries of all
-            // ranks and continue on the P-entry tables (entry index = rank = the low index bits)
-            const FrConstMul rc = make_const_mul(r);
-            Fr *one = ctx->comm_send;
+        if (!gathered && n <= std::max<uint64_t>(kGatherEntries, 2) && (pending_fold || n <= kGatherEntries / 2)) {
+            // the shards are small: fold them with the pending challenge, all-gather every rank's folded shard
+            // and continue on the full-size (replicated) tables without any further exchange
+            const uint64_t m = pending_fold ? n / 2 : n;
+            Fr *send = ctx->comm_send + 8;
             const Fr *cur[3] = {Ac, Bc, Cc};
             for (int i = 0; i < 3; ++i) {
-                ctx->begin_launch();
-                launch_fold(cur[i], one + i, rc, 1, ctx->stream);
-                ctx->end_launch(KC_OTHER, 96.0);
-                GKR_TRY(ctx->check_launch("fold"));
+                if (pending_fold) {
+                    ctx->begin_launch();
+                    launch_fold(cur[i], send + i * m, make_const_mul(r), m, ctx->stream);
+                    ctx->end_launch(KC_OTHER, 96.0 * m);
+                    GKR_TRY(ctx->check_launch("fold"));
+                } else {
+                    GKR_CUDA_TRY(cudaMemcpyAsync(send + i * m, cur[i], m * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+                }
             }
-            GKR_TRY(comm_all_gather(ctx, one, ctx->comm_recv, 3 * sizeof(Fr)));
-            Fr *mini = ctx->misc.as<Fr>() + 8;                     // misc holds >= 64 entries: 8 + 3 * P <= 32
+            GKR_TRY(comm_all_gather(ctx, send, ctx->comm_recv, 3 * m * sizeof(Fr)));
+            GKR_TRY(ctx->shard_mini.ensure(sizeof(Fr) * 3 * m * (size_t)P));
+            Fr *mini = ctx->shard_mini.as<Fr>();
             ctx->begin_launch();
-            launch_transpose_gathered(ctx->comm_recv, mini, P, 3, ctx->stream);
-            ctx->end_launch(KC_OTHER, 192.0 * P);
-            GKR_TRY(ctx->check_launch("transpose_gathered"));
-            Ac = mini; Bc = mini + P; Cc = mini + 2 * P;
-            n = (uint64_t)P;
+            launch_interleave_gathered(ctx->comm_recv, mini, P, 3, m, ctx->stream);
+            ctx->end_launch(KC_OTHER, 192.0 * m * P);
+            GKR_TRY(ctx->check_launch("interleave_gathered"));
+            Ac = mini; Bc = mini + m * P; Cc = mini + 2 * m * P;
+            n = m * (uint64_t)P;
             pending_fold = false;
+            gathered = true;
         }
+        const bool sharded_round = !gathered;
         const uint32_t s = ctx->next_seq();
         const bool full = (j == 0) || ctx->paranoid;     // the first claim (the sum itself) is not known in advance
         const FrConstMul rc = pending_fold ? make_const_mul(r) : FrConstMul{};

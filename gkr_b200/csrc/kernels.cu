@@ -652,19 +652,20 @@ __global__ void k_sum_ranks_publish(const Fr *__restrict__ gathered, int n_ranks
 void launch_sum_ranks_publish(const Fr *gathered, int n_ranks, int count, HostSlot *slot, uint32_t seq, cudaStream_t s) {
     k_sum_ranks_publish<<<1, 32, 0, s>>>(gathered, n_ranks, count, slot, seq);
 }
-// multi-GPU tail: gathered[rank][table] (one fully folded entry per rank and table) -> n_tables contiguous
-// tables of n_ranks entries (entry index = rank = the low index bits the tables were sharded on)
-__global__ void k_transpose_gathered(const Fr *__restrict__ gathered, Fr *__restrict__ out, int n_ranks, int n_tables) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_ranks * n_tables) {
-        const int t = i / n_ranks, rk = i % n_ranks;
-        st_fr(out + i, ld_fr_cg(gathered + (size_t)rk * n_tables + t));
+// multi-GPU tail: gathered[rank][table][i] (every rank's folded shard of m entries per table) -> n_tables
+// contiguous tables of m * n_ranks entries in global index order idx = i * n_ranks + rank
+__global__ void __launch_bounds__(kThreads) k_interleave_gathered(const Fr *__restrict__ gathered, Fr *__restrict__ out,
+                                                                  int n_ranks, int n_tables, uint64_t m) {
+    const uint64_t total = (uint64_t)n_ranks * n_tables * m;
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < total; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t = x / (m * n_ranks), idx = x % (m * n_ranks);
+        const uint64_t i = idx / n_ranks, rk = idx % n_ranks;
+        st_fr(out + x, ld_fr_cg(gathered + (rk * n_tables + t) * m + i));
     }
 }
-void launch_transpose_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_tables, cudaStream_t s) {
-    k_transpose_gathered<<<1, 64, 0, s>>>(gathered, out, n_ranks, n_tables);
+void launch_interleave_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_tables, uint64_t m, cudaStream_t s) {
+    k_interleave_gathered<<<stream_grid((uint64_t)n_ranks * n_tables * m), kThreads, 0, s>>>(gathered, out, n_ranks, n_tables, m);
 }
-
 // multi-GPU: this rank's shard of a replicated table: out[i] = in[i * stride + first]
 __global__ void __launch_bounds__(kThreads) k_take_strided(const Fr *__restrict__ in, Fr *__restrict__ out, uint64_t first,
                                                            uint64_t stride, uint64_t n) {

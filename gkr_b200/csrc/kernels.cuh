@@ -80,7 +80,7 @@ void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr
                         cudaStream_t s, Fr *dev_out = nullptr);
 // multi-GPU: sum the per-rank partial totals (rank-major, Montgomery) and publish; gathered final entries -> tables
 void launch_sum_ranks_publish(const Fr *gathered, int n_ranks, int count, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
-void launch_transpose_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_tables, cudaStream_t s);
+void launch_interleave_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_tables, uint64_t m, cudaStream_t s);
 // plain fold out[i] = in[i] + r (in[i+half] - in[i])
 void launch_fold(const Fr *in, Fr *out, const FrConstMul &r, uint64_t half, cudaStream_t s);
 // publish up to 6 device values (Montgomery -> canonical) to a slot
