@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libgkr_b200.so")
+# GKR_B200_LIB lets kernel A/B experiments load an alternative build of the same library
+SO_PATH = os.environ.get("GKR_B200_LIB") or os.path.join(_HERE, "libgkr_b200.so")
 _SRC = os.path.join(_HERE, "csrc")
 
 GKR_N_KERNEL_CLASSES = 11

@@ -458,8 +458,11 @@ __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const
     }
     grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, dev_out);
 }
+#ifndef GKR_ROUND_MINB
+#define GKR_ROUND_MINB 2          // resident CTAs/SM the non-lazy degree-2 round kernel is compiled for
+#endif
 template <bool FOLD, bool FULL, bool LAZY>
-__global__ void __launch_bounds__(kThreads, 2) k_gkr_round(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+__global__ void __launch_bounds__(kThreads, LAZY ? 2 : GKR_ROUND_MINB) k_gkr_round(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
                                                            const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                                            Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
                                                            uint64_t q, Fr *partials, unsigned int *counter,
