@@ -116,8 +116,9 @@ __device__ __forceinline__ void block_sum(Fr (&acc)[K], Fr (*smem)[kWarps]) {
     __syncthreads();
     if (warp == 0) {
 #pragma unroll
+        const int nw = blockDim.x >> 5;            // 8 for the 256-thread kernels, 4 for the staged 128-thread ones
         for (int j = 0; j < K; ++j) {
-            Fr v = lane < kWarps ? smem[j][lane] : fr_zero();
+            Fr v = lane < nw ? smem[j][lane] : fr_zero();
             acc[j] = warp_sum(v);
         }
     }

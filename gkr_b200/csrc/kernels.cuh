@@ -103,6 +103,7 @@ void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const 
                       cudaStream_t s);
 
 int device_sm_count();
+
 // field multiplications per second with `ilp` independent chains per thread and blocks_per_sm CTAs of 256 threads
 double run_mul_bench(int ilp, int blocks_per_sm, int iters, Fr *scratch, cudaStream_t s);
 
