@@ -66,7 +66,7 @@ class Profile(C.Structure):
 EXPORTS = [
     "gkr_ctx_create", "gkr_ctx_destroy", "gkr_ctx_stream", "gkr_ctx_sync", "gkr_ctx_set_option", "gkr_last_error", "gkr_version", "gkr_mimc7_multi_hash", "gkr_mimc7_hash",
     "gkr_circuit_create", "gkr_circuit_destroy", "gkr_witness_create", "gkr_witness_eval", "gkr_witness_layer",
-    "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_sumcheck_prod", "gkr_dev_table_synth", "gkr_dev_table_synth_strided", "gkr_comm_unique_id", "gkr_comm_init", "gkr_comm_destroy",
+    "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_verify", "gkr_sumcheck_prod", "gkr_dev_table_synth", "gkr_dev_table_synth_strided", "gkr_comm_unique_id", "gkr_comm_init", "gkr_comm_destroy",
     "gkr_sumcheck_prod_sharded",
     "gkr_dev_table_upload", "gkr_dev_table_download", "gkr_dev_table_free", "gkr_fr_binop", "gkr_eq_table",
     "gkr_mobius", "gkr_line_restrict", "gkr_ctx_stats", "gkr_ctx_profile", "gkr_bench_field_mul",
@@ -113,6 +113,7 @@ def lib():
     L.gkr_witness_destroy.argtypes = [vp]
     L.gkr_witness_destroy.restype = None
     L.gkr_prove.argtypes = [vp, vp, vp, C.POINTER(Transcript), C.POINTER(C.POINTER(ProofC))]
+    L.gkr_verify.argtypes = [vp, vp, C.POINTER(ProofC), vp, C.POINTER(Transcript), C.POINTER(i32)]
     L.gkr_proof_free.argtypes = [C.POINTER(ProofC)]
     L.gkr_proof_free.restype = None
     L.gkr_sumcheck_prod.argtypes = [vp, u32, u32, C.POINTER(vp), i32, C.POINTER(Transcript), vp, vp, vp, vp]

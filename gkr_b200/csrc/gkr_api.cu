@@ -171,8 +171,6 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->cmds_host, sizeof(HostCmd) * gkr_ctx::kSlots, cudaHostAllocMapped));
     std::memset((void *)ctx->cmds_host, 0, sizeof(HostCmd) * gkr_ctx::kSlots);
     GKR_CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->cmds_dev, (void *)ctx->cmds_host, 0));
-    ctx->pinned_elems = 4096;
-    GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->pinned, sizeof(gkr_fr) * ctx->pinned_elems, cudaHostAllocDefault));
     ctx->ws.max_blocks = device_sm_count() * 4;
     GKR_CUDA_TRY(cudaMalloc((void **)&ctx->ws.partials, sizeof(Fr) * 6 * (size_t)ctx->ws.max_blocks));
     GKR_CUDA_TRY(cudaMalloc((void **)&ctx->ws.counter, sizeof(unsigned int)));
@@ -203,7 +201,6 @@ extern "C" void gkr_ctx_destroy(gkr_ctx *ctx) {
     if (ctx->words) cudaFree(ctx->words);
     if (ctx->slots_host) cudaFreeHost((void *)ctx->slots_host);
     if (ctx->cmds_host) cudaFreeHost((void *)ctx->cmds_host);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1076,6 +1073,132 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
     // z_0 entries are zero already
     P->finish();
     *out = &P.release()->pub;
+    return GKR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// verify
+// ------------------------------------------------------------------------------------------------
+static HFr horner_desc(const HFr *coef, uint32_t n, const HFr &x) {      // poly.rs:260-267
+    HFr acc = hfr_zero();
+    for (uint32_t i = 0; i < n; ++i) acc = hfr_add(hfr_mul(acc, x), coef[i]);
+    return acc;
+}
+
+extern "C" int gkr_verify(gkr_ctx *ctx, const gkr_circuit *c, const gkr_proof *pf, const gkr_fr *input_values,
+                          const gkr_transcript *t, int *accepted) {
+    if (!ctx || !c || !pf || !input_values || !accepted) return GKR_ERR_INVALID;
+    *accepted = 0;
+    GKR_TRY(ctx->bind());
+    const uint32_t n_layers = (uint32_t)c->layers.size();
+#define REJECT(...)                        \
+    do {                                   \
+        set_last_error(__VA_ARGS__);       \
+        return GKR_OK;                     \
+    } while (0)
+    if (pf->n_layers != n_layers || pf->depth != n_layers + 1) REJECT("rejected: depth mismatch");
+    for (uint32_t i = 0; i <= n_layers; ++i)
+        if (pf->k[i] != c->k[i]) REJECT("rejected: k[%u] mismatch", i);
+    if (pf->d_len != ((uint64_t)1 << c->k[0]) || pf->d_len == 0) REJECT("rejected: d has the wrong size");
+    auto load = [&](const gkr_fr &x, HFr *out) { return hfr_from_canonical(out, &x); };
+
+    const uint64_t Nmax = (uint64_t)1 << c->max_k;
+    GKR_TRY(ctx->eqz.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->equ.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->H.ensure(sizeof(Fr) * Nmax));
+    // z_0 must be zero (prover.rs:16-21); starting claim W_0(z_0) = constant monomial coefficient of d
+    HFr claim;
+    if (!load(pf->d_coef[0], &claim)) return GKR_ERR_RANGE;
+    std::vector<HFr> z(c->k[0]);
+    for (uint32_t j = 0; j < c->k[0]; ++j) {
+        if (!load(pf->z[pf->z_off[0] + j], &z[j])) return GKR_ERR_RANGE;
+        if (!hfr_is_zero(z[j])) REJECT("rejected: z_0 is not zero");
+    }
+    for (uint32_t li = 0; li < n_layers; ++li) {
+        const LayerDev &L = c->layers[li];
+        const uint32_t k = L.k_in;
+        const uint64_t ro = pf->round_off[li];
+        if (pf->round_off[li + 1] - ro != 2ull * k) REJECT("rejected: layer %u has the wrong number of rounds", li);
+        std::vector<HFr> rs(2 * k);
+        HFr last_hash = hfr_zero();
+        for (uint32_t j = 0; j < 2 * k; ++j) {
+            const uint32_t len = pf->msg_len[ro + j];
+            if (len < 2 || len > 3) REJECT("rejected: layer %u round %u: message length %u", li, j, len);
+            HFr m[3];
+            for (uint32_t i = 0; i < len; ++i)
+                if (!load(pf->msgs[3 * (ro + j) + i], &m[i])) return GKR_ERR_RANGE;
+            // g(0) + g(1) = 2 c0 + (sum of the other coefficients)
+            HFr g0 = m[len - 1], g1 = hfr_zero();
+            for (uint32_t i = 0; i < len; ++i) g1 = hfr_add(g1, m[i]);
+            if (!hfr_eq(hfr_add(g0, g1), claim)) REJECT("rejected: layer %u round %u: g(0)+g(1) != claim", li, j);
+            HFr r;
+            GKR_TRY(challenge_for(ctx, t, m, len, &r));
+            HFr given;
+            if (!load(pf->chal[ro + j], &given)) return GKR_ERR_RANGE;
+            if (!hfr_eq(r, given)) REJECT("rejected: layer %u round %u: challenge is not the transcript hash", li, j);
+            rs[j] = r;
+            last_hash = r;
+            claim = horner_desc(m, len, r);
+        }
+        // wiring predicates at (z_i, b*, c*) on the device
+        GKR_TRY(eq_table_dev(ctx, z.data(), L.k_out, ctx->eqz.as<Fr>()));
+        GKR_TRY(eq_table_dev(ctx, rs.data(), k, ctx->equ.as<Fr>()));
+        GKR_TRY(eq_table_dev(ctx, rs.data() + k, k, ctx->H.as<Fr>()));
+        if (L.sharded) {
+            set_last_error("gkr_verify: create the circuit on a context without a communicator");
+            return GKR_ERR_INVALID;
+        }
+        const uint32_t s = ctx->next_seq();
+        ctx->begin_launch();
+        launch_wiring_eval(L.type, L.left, L.right, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), ctx->H.as<Fr>(), L.n_gates, ctx->ws,
+                           ctx->slot_dev(s), s, ctx->stream);
+        ctx->end_launch(KC_WIRING, 108.0 * L.n_gates);
+        GKR_TRY(ctx->check_launch("wiring_eval"));
+        const HostSlot *slot;
+        GKR_TRY(ctx->wait_slot(s, &slot));
+        const HFr add_v = to_host(slot->v[0]), mult_v = to_host(slot->v[1]);
+        const uint32_t qlen = pf->q_len[li];
+        if (qlen < 1 || qlen > k + 1) REJECT("rejected: layer %u: q has length %u", li, qlen);
+        std::vector<HFr> q(qlen);
+        for (uint32_t i = 0; i < qlen; ++i)
+            if (!load(pf->q[pf->q_off[li] + i], &q[i])) return GKR_ERR_RANGE;
+        const HFr q0 = q[qlen - 1];
+        HFr q1 = hfr_zero();
+        for (uint32_t i = 0; i < qlen; ++i) q1 = hfr_add(q1, q[i]);
+        const HFr want = hfr_add(hfr_mul(add_v, hfr_add(q0, q1)), hfr_mul(mult_v, hfr_mul(q0, q1)));
+        if (!hfr_eq(want, claim)) REJECT("rejected: layer %u: last sumcheck claim != add(q0+q1) + mult q0 q1", li);
+        HFr rstar;
+        if (!load(pf->r[li], &rstar)) return GKR_ERR_RANGE;
+        if (!hfr_eq(rstar, last_hash)) REJECT("rejected: layer %u: r* is not the hash of the last message", li);
+        std::vector<HFr> znext(k);
+        for (uint32_t j = 0; j < k; ++j) {
+            znext[j] = hfr_add(rs[j], hfr_mul(hfr_sub(rs[k + j], rs[j]), rstar));
+            HFr given;
+            if (!load(pf->z[pf->z_off[li + 1] + j], &given)) return GKR_ERR_RANGE;
+            if (!hfr_eq(given, znext[j])) REJECT("rejected: layer %u: z_(i+1) != l(b*, c*, r*)", li);
+        }
+        claim = horner_desc(q.data(), qlen, rstar);
+        z.swap(znext);
+    }
+    // input layer: W_depth(z_depth) == claim
+    {
+        const uint32_t k = c->k[n_layers];
+        const uint64_t n = (uint64_t)1 << k;
+        GKR_TRY(ctx->mob.ensure(sizeof(Fr) * n));
+        GKR_TRY(upload_table(ctx, input_values, n, ctx->mob.as<Fr>()));
+        GKR_TRY(eq_table_dev(ctx, z.data(), k, ctx->eqz.as<Fr>()));
+        const uint32_t s = ctx->next_seq();
+        ctx->begin_launch();
+        launch_dot(ctx->eqz.as<Fr>(), ctx->mob.as<Fr>(), n, ctx->ws, ctx->slot_dev(s), s, ctx->stream);
+        ctx->end_launch(KC_OTHER, 64.0 * n);
+        GKR_TRY(ctx->check_launch("dot"));
+        const HostSlot *slot;
+        GKR_TRY(ctx->wait_slot(s, &slot));
+        if (!hfr_eq(to_host(slot->v[0]), claim)) REJECT("rejected: W_depth(z_depth) != last claim");
+    }
+#undef REJECT
+    *accepted = 1;
+    set_last_error("accepted");
     return GKR_OK;
 }
 

@@ -116,7 +116,7 @@ __device__ __forceinline__ void block_sum(Fr (&acc)[K], Fr (*smem)[kWarps]) {
     __syncthreads();
     if (warp == 0) {
 #pragma unroll
-        const int nw = blockDim.x >> 5;            // 8 for the 256-thread kernels, 4 for the staged 128-thread ones
+        const int nw = blockDim.x >> 5;
         for (int j = 0; j < K; ++j) {
             Fr v = lane < nw ? smem[j][lane] : fr_zero();
             acc[j] = warp_sum(v);
@@ -388,7 +388,7 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 // LAZY: products are accumulated as exact 512-bit integers and reduced once per thread.
 // Published: v[0] = X0, v[1] = X2, v[2] = X1 (FULL only).
 // ------------------------------------------------------------------------------------------------
-template <bool FOLD, bool FULL, bool LAZY, bool CMD, class KT>
+template <bool FOLD, bool FULL, bool LAZY, class KT>
 __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
                                                const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                                Fr *__restrict__ Wout, Fr *__restrict__ Aout, const KT &r,
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, LAZY ? 2 : GKR_ROUND_MINB) k_gkr_rou
                                                            Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
                                                            uint64_t q, Fr *partials, unsigned int *counter,
                                                            HostSlot *slot, uint32_t seq, Fr *dev_out) {
-    gkr_round_body<FOLD, FULL, LAZY, false>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq, dev_out);
+    gkr_round_body<FOLD, FULL, LAZY>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq, dev_out);
 }
 // pre-launched variant: waits for the challenge's constant table in a mapped command block
 template <bool FULL>
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gkr_round_cmd(const Fr *__restr
         return;
     }
     CmdConst r{raw};
-    gkr_round_body<true, FULL, false, true>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq);
+    gkr_round_body<true, FULL, false>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq);
 }
 
 // lazy accumulation pays once a thread sees several pairs: fewer, fatter CTAs (2 resident per SM)
@@ -670,6 +670,38 @@ __global__ void __launch_bounds__(kThreads) k_interleave_gathered(const Fr *__re
 void launch_interleave_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_tables, uint64_t m, cudaStream_t s) {
     k_interleave_gathered<<<stream_grid((uint64_t)n_ranks * n_tables * m), kThreads, 0, s>>>(gathered, out, n_ranks, n_tables, m);
 }
+// ------------------------------------------------------------------------------------------------
+// verifier side: add_i(z,b,c) and mult_i(z,b,c) = sum over gates of eq(z,g) eq(b,l_g) eq(c,r_g), split by type
+// (python/gkr.py:216-217 evaluates the same predicates term by term); and the MLE value sum_i eq(z,i) T[i]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_wiring_eval(const uint8_t *__restrict__ type, const uint32_t *__restrict__ left,
+                                                          const uint32_t *__restrict__ right, const Fr *__restrict__ eqz,
+                                                          const Fr *__restrict__ eqb, const Fr *__restrict__ eqc,
+                                                          uint32_t n_gates, Fr *partials, unsigned int *counter,
+                                                          HostSlot *slot, uint32_t seq) {
+    Fr acc[2] = {fr_zero(), fr_zero()};            // [0] add gates, [1] mult gates
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_gates; g += gridDim.x * blockDim.x) {
+        const Fr v = fr_mul(fr_mul(ld_fr(eqz + g), ld_fr(eqb + left[g])), ld_fr(eqc + right[g]));
+        if (type[g]) acc[1] = fr_add(acc[1], v); else acc[0] = fr_add(acc[0], v);
+    }
+    grid_sum_publish<2>(acc, partials, counter, slot, seq, 0u);
+}
+void launch_wiring_eval(const uint8_t *type, const uint32_t *left, const uint32_t *right, const Fr *eqz, const Fr *eqb,
+                        const Fr *eqc, uint32_t n_gates, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    k_wiring_eval<<<grid_for(n_gates, ws.max_blocks), kThreads, 0, s>>>(type, left, right, eqz, eqb, eqc, n_gates, ws.partials,
+                                                                         ws.counter, slot, seq);
+}
+__global__ void __launch_bounds__(kThreads) k_dot(const Fr *__restrict__ X, const Fr *__restrict__ Y, uint64_t n, Fr *partials,
+                                                  unsigned int *counter, HostSlot *slot, uint32_t seq) {
+    Fr acc[1] = {fr_zero()};
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        acc[0] = fr_add(acc[0], fr_mul(ld_fr(X + i), ld_fr(Y + i)));
+    grid_sum_publish<1>(acc, partials, counter, slot, seq, 0u);
+}
+void launch_dot(const Fr *X, const Fr *Y, uint64_t n, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    k_dot<<<grid_for(n, ws.max_blocks), kThreads, 0, s>>>(X, Y, n, ws.partials, ws.counter, slot, seq);
+}
+
 // multi-GPU: this rank's shard of a replicated table: out[i] = in[i * stride + first]
 __global__ void __launch_bounds__(kThreads) k_take_strided(const Fr *__restrict__ in, Fr *__restrict__ out, uint64_t first,
                                                            uint64_t stride, uint64_t n) {

@@ -102,6 +102,13 @@ void launch_table_flags(const Fr *T, uint64_t n, unsigned int *dev_words3, HostS
 void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const FrConstMul &b, const FrConstMul &g,
                       cudaStream_t s);
 
+// ---- verifier ---------------------------------------------------------------------------------------
+// publishes v[0] = add_i(z,b,c), v[1] = mult_i(z,b,c) from the three eq tables
+void launch_wiring_eval(const uint8_t *type, const uint32_t *left, const uint32_t *right, const Fr *eqz, const Fr *eqb,
+                        const Fr *eqc, uint32_t n_gates, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
+// publishes v[0] = sum_i X[i] * Y[i]
+void launch_dot(const Fr *X, const Fr *Y, uint64_t n, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
+
 int device_sm_count();
 
 // field multiplications per second with `ilp` independent chains per thread and blocks_per_sm CTAs of 256 threads

@@ -111,8 +111,6 @@ struct gkr_ctx {
     uint32_t seq = 0;
     gkr::ReduceWs ws{};
     unsigned int *words = nullptr;         // [8] device words: [0] range-error flag, [4..6] support/flags scratch
-    gkr_fr *pinned = nullptr;              // small pinned staging (q coefficients, flags)
-    size_t pinned_elems = 0;
 
     // multi-GPU (comm.cpp): NCCL communicator, this rank, staging for the per-round partial sums
     void *nccl_comm = nullptr;

@@ -223,6 +223,20 @@ class Prover:
         finally:
             self.free_raw(ptr)
 
+    # ---- verify ---------------------------------------------------------------------------------------------
+    def verify(self, circuit: Circuit, proof, input_values, challenge=None):
+        """complete check of a proof (gkr_verify): returns (accepted, reason).  `proof` is a DenseProof (or any
+        object with the same fields) or the raw pointer returned by prove_raw; input_values is the input layer."""
+        if isinstance(proof, C.POINTER(_lib.ProofC)):
+            pc, keep = proof.contents, None
+        else:
+            pc, keep = _pack_proof(proof)
+        v = as_fr_array(input_values)
+        t, keep_cb = self._transcript(challenge)
+        ok = C.c_int(0)
+        _lib.check(self._L.gkr_verify(self._ctx, circuit.ptr, C.byref(pc), _vp(v), C.byref(t) if t else None, C.byref(ok)))
+        return bool(ok.value), (self._L.gkr_last_error() or b"").decode()
+
     # ---- standalone product sumcheck -------------------------------------------------------------------
     def dev_table_synth(self, seed: int, stream: int, n: int, first: int = 0, stride: int = 1) -> DevTable:
         """n elements of the synthetic stream, element i = stream element first + i*stride (device resident)"""
@@ -332,6 +346,53 @@ def _np_from(ptr, count, dtype):
     size = np.dtype(dtype).itemsize * count
     buf = (C.c_uint8 * size).from_address(ptr if isinstance(ptr, int) else C.addressof(ptr.contents))
     return np.frombuffer(buf, dtype=dtype, count=count).copy()
+
+
+def _pack_proof(dp):
+    """DenseProof (Python ints) -> flat gkr_proof struct + the numpy arrays that back it"""
+    n = len(dp.sumcheck_proofs)
+    ks = np.array(dp.k, np.uint32)
+    round_off = np.zeros(n + 1, np.uint64)
+    q_off = np.zeros(n + 1, np.uint64)
+    z_off = np.zeros(n + 2, np.uint64)
+    for i in range(n):
+        round_off[i + 1] = round_off[i] + len(dp.sumcheck_proofs[i])
+        q_off[i + 1] = q_off[i] + dp.k[i + 1] + 1
+    for i in range(n + 1):
+        z_off[i + 1] = z_off[i] + len(dp.z[i])
+    R = int(round_off[n])
+    msgs = np.zeros((max(R, 1), 3, 8), np.uint32)
+    mlen = np.zeros(max(R, 1), np.uint8)
+    j = 0
+    for layer in dp.sumcheck_proofs:
+        for m in layer:
+            if len(m) > 3:
+                raise ValueError("round message longer than 3 coefficients")
+            mlen[j] = len(m)
+            if m:
+                msgs[j, :len(m)] = ints_to_fr(m)
+            j += 1
+    flat = lambda rows: ints_to_fr([x for row in rows for x in row]) if any(len(r) for r in rows) else np.zeros((1, 8), np.uint32)  # noqa: E731
+    chal = flat(dp.sumcheck_r)
+    q = np.zeros((max(int(q_off[n]), 1), 8), np.uint32)
+    q_len = np.zeros(max(n, 1), np.uint32)
+    for i, row in enumerate(dp.q):
+        if len(row) > dp.k[i + 1] + 1:
+            raise ValueError("q longer than k+1 coefficients")
+        q_len[i] = len(row)
+        if row:
+            q[int(q_off[i]):int(q_off[i]) + len(row)] = ints_to_fr(row)
+    z = flat(dp.z)
+    r = ints_to_fr(dp.r) if dp.r else np.zeros((1, 8), np.uint32)
+    d = ints_to_fr(dp.d_coef)
+    inp = ints_to_fr(dp.input_coef)
+    keep = [ks, round_off, q_off, z_off, msgs, mlen, chal, q, q_len, z, r, d, inp]
+    u32p, u64p, u8p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)
+    pc = _lib.ProofC(n, dp.depth, ks.ctypes.data_as(u32p), R, round_off.ctypes.data_as(u64p), mlen.ctypes.data_as(u8p),
+                     msgs.ctypes.data, chal.ctypes.data, q_off.ctypes.data_as(u64p), q_len.ctypes.data_as(u32p), q.ctypes.data,
+                     z_off.ctypes.data_as(u64p), z.ctypes.data, r.ctypes.data, d.shape[0], d.ctypes.data, inp.shape[0],
+                     inp.ctypes.data)
+    return pc, keep
 
 
 def _unpack_proof(pc) -> DenseProof:

@@ -132,6 +132,18 @@ typedef struct {
 int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *w, const gkr_transcript *t, gkr_proof **out);
 void gkr_proof_free(gkr_proof *p);
 
+/* ---- verifier (complete check of the reference protocol; the reference's own verifiers are partial:
+ * gkr-verifier-circuits/circom/circom/verifier.circom:39-71 never evaluates add_i/mult_i nor the hashes,
+ * python/gkr.py:202-231 never ties the last sumcheck claim to q) -----------------------------------------
+ * Checks, per layer: g_j(0)+g_j(1) == claim, r_j == challenge(g_j), claim <- g_j(r_j);
+ * final claim == add_i(z,b*,c*)(q(0)+q(1)) + mult_i(z,b*,c*) q(0) q(1)  (predicates evaluated on the device);
+ * r*_i == challenge(last message); z_{i+1} == b* + r*(c*-b*); claim <- q_i(r*_i);
+ * and at the end W_depth(z_depth) == claim on the supplied input layer (device MLE evaluation).
+ * The starting claim is W_0(0..0) = d_coef[0].  `proof` may come from anywhere: only its arrays are read.
+ * *accepted = 1/0; on rejection gkr_last_error() names the first failing check.  transcript NULL => MiMC7. */
+int gkr_verify(gkr_ctx *ctx, const gkr_circuit *c, const gkr_proof *proof, const gkr_fr *input_values,
+               const gkr_transcript *t, int *accepted);
+
 /* ---- standalone sumcheck of a product of 3 multilinear tables (prove_sumcheck, sumcheck.rs:158-214) -
  * tables: n_tables (= 3) pointers to 2^n_vars canonical elements in HOST memory (on_device = 0) or
  * Montgomery-form DEVICE buffers created by gkr_dev_table_* (on_device = 1).

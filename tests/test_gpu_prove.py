@@ -112,6 +112,66 @@ def test_paranoid_mode_matches_claim_derivation(pv):
     pp.close()
 
 
+def test_gpu_verifier_accepts_and_rejects(pv):
+    """gkr_verify: accepts honest proofs (agreeing with the reference-protocol verifier of the oracle) and rejects a
+    tampered value in every field"""
+    import copy
+    from gkr_b200 import DenseLayer
+    rng = random.Random(2024)
+    for ks in ([2, 3, 2], [0, 2, 4], [5, 6, 5, 7]):
+        layers = random_circuit(rng, ks, "mixed")
+        inputs = [rng.randrange(P) for _ in range(1 << ks[-1])]
+        dl = dense_layers(layers)
+        c = pv.circuit([DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in dl])
+        w = pv.witness_eval(c, ints_to_fr(inputs))
+        proof = pv.prove(c, w)
+        ok, why = pv.verify(c, proof, ints_to_fr(inputs))
+        assert ok, why
+        assert verifier.verify(layers, proof, input_values=inputs)[0]
+        # the raw C proof verifies too
+        ptr = pv.prove_raw(c, w)
+        assert pv.verify(c, ptr, ints_to_fr(inputs))[0]
+        pv.free_raw(ptr)
+
+        def tampered(mutate):
+            bad = copy.deepcopy(proof)
+            mutate(bad)
+            got, reason = pv.verify(c, bad, ints_to_fr(inputs))
+            assert not got and reason.startswith("rejected"), reason
+            assert not verifier.verify(layers, bad, input_values=inputs)[0]
+
+        def bump(lst, i):
+            lst[i] = (lst[i] + 1) % P
+        tampered(lambda b: bump(b.sumcheck_proofs[0][0], -1))
+        tampered(lambda b: bump(b.sumcheck_proofs[-1][-1], 0))
+        tampered(lambda b: bump(b.sumcheck_r[0], 1))
+        tampered(lambda b: bump(b.q[-1], 0))
+        tampered(lambda b: bump(b.z[1], 0))
+        tampered(lambda b: bump(b.r, 0))
+        tampered(lambda b: bump(b.d_coef, 0))
+        bad_inputs = list(inputs)
+        bad_inputs[1] = (bad_inputs[1] + 1) % P
+        assert not pv.verify(c, proof, ints_to_fr(bad_inputs))[0]
+        w.close()
+
+
+def test_gpu_verifier_config2(pv):
+    """verify the 2^16 x 8 synthetic proof on the device (the Python verifier would need minutes)"""
+    k, n_layers, seed = 16, 8, 1
+    layers = syn.layered_circuit(seed, k, n_layers)
+    inputs = syn.input_values(seed, k)
+    c = pv.circuit(layers)
+    w = pv.witness_eval(c, inputs)
+    ptr = pv.prove_raw(c, w)
+    ok, why = pv.verify(c, ptr, inputs)
+    assert ok, why
+    bad = inputs.copy()
+    bad[12345, 0] ^= 1
+    assert not pv.verify(c, ptr, bad)[0]
+    pv.free_raw(ptr)
+    w.close()
+
+
 def test_prelaunch_off_matches(pv):
     """pre-launched (command-waiting) tail rounds vs plain per-round launches: same proof"""
     from gkr_b200 import Prover

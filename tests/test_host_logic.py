@@ -53,3 +53,18 @@ def test_synthetic_generators_match_oracle_definition():
         t, l, r = orc.synth_gates(seed, 2, 7, 512)
         assert (g.gtype == t).all() and (g.left == l).all() and (g.right == r).all()
     assert all(v < P for v in fr_to_ints(syn.values(9, 1, 2000)))
+
+
+def test_proof_pack_unpack_roundtrip():
+    """DenseProof <-> flat gkr_proof struct (the form gkr_verify consumes), on an oracle proof with ragged shapes"""
+    from gkr_b200.prover import _pack_proof, _unpack_proof
+    from tests.helpers import run_l1
+    rng = random.Random(1)
+    for ks, inputs in (([0, 2, 3], None), ([2, 3], [5] * 8)):
+        layers = random_circuit(rng, ks, "mixed")
+        vals = inputs or [rng.randrange(P) for _ in range(1 << ks[-1])]
+        dp, _ = run_l1(layers, vals)
+        pc, keep = _pack_proof(dp)
+        back = _unpack_proof(pc)
+        for f in ("sumcheck_proofs", "sumcheck_r", "q", "z", "r", "k", "depth", "d_coef", "input_coef"):
+            assert getattr(back, f) == getattr(dp, f), f
