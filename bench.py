@@ -341,6 +341,32 @@ def run_ours(args):
         except GkrError as e:
             sumcheck = {"n_vars": v, "error": str(e)}
 
+    # ---- the degree-2 GKR round kernels on HBM-sized tables (one 2^24-gate layer: 3 x 512 MiB per phase) ----------
+    gkr_large = None
+    if args.large_layer_k and world == 1:
+        try:
+            lk = args.large_layer_k
+            big_layers = syn.layered_circuit(seed, lk, 1)
+            big_c = pv.circuit(big_layers)
+            big_w = pv.witness_eval(big_c, syn.input_values(seed, lk))
+            for _ in range(2):
+                pv.free_raw(pv.prove_raw(big_c, big_w))
+            pv.profile(1)
+            pv.free_raw(pv.prove_raw(big_c, big_w))
+            bp = pv.profile(0)
+            big_w.close()
+            big_c.close()
+
+            def cls(n):
+                x = bp[n]
+                g = x["algo_bytes"] / (x["ms"] * 1e-3) / 1e9 if x["ms"] else 0.0
+                return {"launches": x["launches"], "ms": round(x["ms"], 4), "gbs": round(g, 1), "frac_of_hbm_peak": round(g / hbm_peak, 3)}
+            gkr_large = {"k": lk, "layers": 1, "tables": "3 x %d MiB per phase (larger than L2)" % ((32 << lk) >> 20),
+                         "gkr_round_first": cls("gkr_round"), "gkr_round_fused": cls("gkr_round_fused"),
+                         "wiring": cls("wiring"), "note": "launches of >= 2^16 pairs; CUDA events around every launch"}
+        except Exception as e:  # noqa: BLE001 - an OOM here must not lose the headline numbers
+            gkr_large = {"error": str(e)}
+
     # ---- integer-multiply ceiling of this device (register-resident Montgomery products) ------------------------
     gmul = pv.bench_field_mul(4, 4, 2000) / 1e9
     int_roof = {"gmul_per_s": gmul, "unit": "G Montgomery products/s (8x32-bit limbs, IMAD.WIDE)",
@@ -371,7 +397,7 @@ def run_ours(args):
                     "note": "pinned input layer -> H2D -> device circuit evaluation -> gkr_prove -> Proof on host"},
             "gpu_launches": int(launches_timed),
             "roofline": roofline, "cpu_baseline": cpu, "sumcheck": sumcheck, "clocks": clock_info,
-            "integer_roofline": int_roof,
+            "integer_roofline": int_roof, "gkr_rounds_large_tables": gkr_large,
             "kernel_classes": {n: {"launches": x["launches"], "ms": round(x["ms"], 4),
                                    "gbs": round(x["algo_bytes"] / (x["ms"] * 1e-3) / 1e9, 1) if x["ms"] else None}
                                for n, x in classes.items()},
@@ -392,6 +418,7 @@ def main():
     ap.add_argument("--k", type=int, default=20, help="log2 gates per layer (BASELINE config 3: 20)")
     ap.add_argument("--layers", type=int, default=16)
     ap.add_argument("--sumcheck-vars", type=int, default=28, help="standalone 3-table sumcheck size (0 = skip)")
+    ap.add_argument("--large-layer-k", type=int, default=24, help="also profile the GKR round kernels on one 2^k-gate layer (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
