@@ -10,6 +10,7 @@
 #include <immintrin.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <atomic>
 #include <cstring>
 #include <map>
@@ -593,7 +594,8 @@ struct ProofHolder {
 };
 extern "C" void gkr_proof_free(gkr_proof *p) {
     if (!p) return;
-    delete reinterpret_cast<ProofHolder *>(p);   // pub is the first member
+    // the public struct is the first member of its holder
+    delete reinterpret_cast<ProofHolder *>(reinterpret_cast<char *>(p) - offsetof(ProofHolder, pub));
 }
 
 // ------------------------------------------------------------------------------------------------
