@@ -213,7 +213,9 @@ extern "C" int gkr_bench_field_mul(gkr_ctx *ctx, int ilp, int blocks_per_sm, int
     if (!ctx || !mul_per_second || blocks_per_sm < 1 || blocks_per_sm > 8 || iters < 1) return GKR_ERR_INVALID;
     GKR_TRY(ctx->bind());
     GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
-    *mul_per_second = run_mul_bench(ilp, blocks_per_sm, iters, ctx->misc.as<Fr>(), ctx->stream);
+    // ilp: 1, 2, 4 = fr_mul; +16 = fr_mul_const; +32 = wide_mac  (e.g. 20 = fr_mul_const with 4 chains)
+    const int mode = (ilp & 32) ? 2 : (ilp & 16) ? 1 : 0;
+    *mul_per_second = run_mul_bench(ilp & 7, blocks_per_sm, iters, ctx->misc.as<Fr>(), ctx->stream, mode);
     ctx->stats.kernel_launches += 2;
     return ctx->check_launch("mul_bench");
 }

@@ -8,6 +8,9 @@
 
 namespace gkr {
 
+#ifndef GKR_PROD3_PAIRS
+#define GKR_PROD3_PAIRS 1         // pairs per loop iteration and thread in the degree-3 kernel (2 => 1 CTA/SM, 255 registers)
+#endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_gkr_round_cmd(const Fr *__restr
 // lazy accumulation pays once a thread sees several pairs: fewer, fatter CTAs (2 resident per SM)
 static inline bool use_lazy(uint64_t pairs) { return pairs >= ((uint64_t)1 << 20); }
 static inline int round_grid(uint64_t pairs, const ReduceWs &ws) {
-    const int cap = use_lazy(pairs) ? device_sm_count() * 2 : ws.max_blocks;
+    const int cap = use_lazy(pairs) ? device_sm_count() * (GKR_PROD3_PAIRS == 2 ? 1 : 2) : ws.max_blocks;
     return grid_for(pairs, cap < ws.max_blocks ? cap : ws.max_blocks);
 }
 
@@ -534,12 +537,12 @@ void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *
 // the host uses g(1) = claim - g(0)).  The host interpolates the four coefficients.
 // ------------------------------------------------------------------------------------------------
 template <bool FOLD, bool FULL, bool LAZY>
-__global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restrict__ Ain, const Fr *__restrict__ Bin,
-                                                             const Fr *__restrict__ Cin, Fr *__restrict__ Aout,
-                                                             Fr *__restrict__ Bout, Fr *__restrict__ Cout, FrConstMul r,
-                                                             uint64_t q, Fr *partials, unsigned int *counter,
-                                                             HostSlot *slot, uint32_t seq, Fr *dev_out) {
+__global__ void __launch_bounds__(kThreads, GKR_PROD3_PAIRS == 2 ? 1 : 2)
+    k_prod3_round(const Fr *__restrict__ Ain, const Fr *__restrict__ Bin, const Fr *__restrict__ Cin, Fr *__restrict__ Aout,
+                  Fr *__restrict__ Bout, Fr *__restrict__ Cout, FrConstMul r, uint64_t q, Fr *partials,
+                  unsigned int *counter, HostSlot *slot, uint32_t seq, Fr *dev_out) {
     constexpr int K = FULL ? 4 : 3;
+    constexpr int NP = GKR_PROD3_PAIRS;
     Fr acc[K];
     FrWide wide[LAZY ? K : 1];
 #pragma unroll
@@ -548,10 +551,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restric
 #pragma unroll
         for (int j = 0; j < K; ++j) wide_zero(wide[j]);
     }
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < q; i += (uint64_t)gridDim.x * blockDim.x) {
-        {
-            const uint64_t nx = i + (uint64_t)gridDim.x * blockDim.x;
-            if (!FOLD && nx < q) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < q; i0 += NP * stride) {
+        if (!FOLD) {
+            const uint64_t nx = i0 + NP * stride;
+            if (nx < q) {
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     prefetch_l2(Ain + nx + t * q);
@@ -560,8 +564,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restric
                 }
             }
         }
-        Fr t0, tm, tinf, t1;
-        {
+        // stage 1 for every pair of this iteration, then stage 2: independent instruction streams side by side
+        Fr t0[NP], tm[NP], tinf[NP], t1[NP];
+        bool live[NP];
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            const uint64_t i = i0 + u * stride;
+            live[u] = i < q;
+            if (!live[u]) continue;
             Fr a0, a1, b0, b1;
             if (FOLD) {
                 a0 = fold2(ld_fr(Ain + i), ld_fr(Ain + i + 2 * q), r);
@@ -576,38 +586,43 @@ __global__ void __launch_bounds__(kThreads, 2) k_prod3_round(const Fr *__restric
                 a0 = ld_fr(Ain + i); a1 = ld_fr(Ain + i + q);
                 b0 = ld_fr(Bin + i); b1 = ld_fr(Bin + i + q);
             }
-            t0 = fr_mul(a0, b0);
+            t0[u] = fr_mul(a0, b0);
             const Fr da = fr_sub(a1, a0), db = fr_sub(b1, b0);
-            tinf = fr_mul(da, db);
+            tinf[u] = fr_mul(da, db);
             if (FULL) {
                 // three products serve all four points: with X = a0 b1 + a1 b0 = t0 + t1 - tinf,
                 // (a0 - da)(b0 - db) = (2a0 - a1)(2b0 - b1) = 4 t0 - 2 X + t1 = 2 t0 - t1 + 2 tinf
-                t1 = fr_mul(a1, b1);
-                tm = fr_add(fr_sub(fr_dbl(t0), t1), fr_dbl(tinf));
+                t1[u] = fr_mul(a1, b1);
+                tm[u] = fr_add(fr_sub(fr_dbl(t0[u]), t1[u]), fr_dbl(tinf[u]));
             } else {
-                tm = fr_mul(fr_sub(a0, da), fr_sub(b0, db));      // value at X = -1 : lo - d
+                tm[u] = fr_mul(fr_sub(a0, da), fr_sub(b0, db));      // value at X = -1 : lo - d
             }
         }
-        Fr c0, c1;
-        if (FOLD) {
-            c0 = fold2(ld_fr(Cin + i), ld_fr(Cin + i + 2 * q), r);
-            c1 = fold2(ld_fr(Cin + i + q), ld_fr(Cin + i + 3 * q), r);
-            st_fr(Cout + i, c0);
-            st_fr(Cout + i + q, c1);
-        } else {
-            c0 = ld_fr(Cin + i); c1 = ld_fr(Cin + i + q);
-        }
-        const Fr dc = fr_sub(c1, c0);
-        if (LAZY) {
-            wide_mac(wide[0], t0, c0);
-            wide_mac(wide[1], tm, fr_sub(c0, dc));
-            wide_mac(wide[2], tinf, dc);
-            if (FULL) wide_mac(wide[K - 1], t1, c1);
-        } else {
-            acc[0] = fr_add(acc[0], fr_mul(t0, c0));
-            acc[1] = fr_add(acc[1], fr_mul(tm, fr_sub(c0, dc)));
-            acc[2] = fr_add(acc[2], fr_mul(tinf, dc));
-            if (FULL) acc[K - 1] = fr_add(acc[K - 1], fr_mul(t1, c1));
+#pragma unroll
+        for (int u = 0; u < NP; ++u) {
+            const uint64_t i = i0 + u * stride;
+            if (!live[u]) continue;
+            Fr c0, c1;
+            if (FOLD) {
+                c0 = fold2(ld_fr(Cin + i), ld_fr(Cin + i + 2 * q), r);
+                c1 = fold2(ld_fr(Cin + i + q), ld_fr(Cin + i + 3 * q), r);
+                st_fr(Cout + i, c0);
+                st_fr(Cout + i + q, c1);
+            } else {
+                c0 = ld_fr(Cin + i); c1 = ld_fr(Cin + i + q);
+            }
+            const Fr dc = fr_sub(c1, c0);
+            if (LAZY) {
+                wide_mac(wide[0], t0[u], c0);
+                wide_mac(wide[1], tm[u], fr_sub(c0, dc));
+                wide_mac(wide[2], tinf[u], dc);
+                if (FULL) wide_mac(wide[K - 1], t1[u], c1);
+            } else {
+                acc[0] = fr_add(acc[0], fr_mul(t0[u], c0));
+                acc[1] = fr_add(acc[1], fr_mul(tm[u], fr_sub(c0, dc)));
+                acc[2] = fr_add(acc[2], fr_mul(tinf[u], dc));
+                if (FULL) acc[K - 1] = fr_add(acc[K - 1], fr_mul(t1[u], c1));
+            }
         }
     }
     if (LAZY) {
@@ -886,32 +901,47 @@ void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const 
 // ------------------------------------------------------------------------------------------------
 // integer-pipe ceiling: back-to-back Montgomery products, ILP independent chains per thread
 // ------------------------------------------------------------------------------------------------
-template <int ILP>
-__global__ void __launch_bounds__(kThreads) k_mul_bench(Fr *out, int iters) {
+// MODE 0: fr_mul chains; 1: fr_mul_const chains (constant-bank operands); 2: wide_mac into one accumulator
+template <int ILP, int MODE>
+__global__ void __launch_bounds__(kThreads) k_mul_bench(Fr *out, int iters, FrConstMul K) {
     Fr x[ILP], y = fr_one();
     y.l[0] ^= threadIdx.x * 2654435761u;
     y.l[3] ^= blockIdx.x;
+    FrWide w;
+    wide_zero(w);
 #pragma unroll
     for (int j = 0; j < ILP; ++j) { x[j] = y; x[j].l[1] += j + 1; }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int j = 0; j < ILP; ++j) x[j] = fr_mul(x[j], y);
+        for (int j = 0; j < ILP; ++j) {
+            if (MODE == 0) x[j] = fr_mul(x[j], y);
+            else if (MODE == 1) x[j] = fr_mul_const(x[j], K);
+            else { wide_mac(w, x[j], y); x[j].l[0] += w.l[3]; }
+        }
     }
     Fr acc = x[0];
 #pragma unroll
     for (int j = 1; j < ILP; ++j) acc = fr_add(acc, x[j]);
+    if (MODE == 2) acc = fr_add(acc, wide_reduce(w));
     if (acc.l[7] == 0xffffffffu) st_fr(out + (blockIdx.x * (size_t)blockDim.x + threadIdx.x), acc);   // never true: values < p
 }
-double run_mul_bench(int ilp, int blocks_per_sm, int iters, Fr *scratch, cudaStream_t s) {
+double run_mul_bench(int ilp, int blocks_per_sm, int iters, Fr *scratch, cudaStream_t s, int mode) {
     const int grid = device_sm_count() * blocks_per_sm;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
+    FrConstMul K;
+    for (int j = 0; j < 8; ++j)
+        for (int i = 0; i < 8; ++i) K.c[j][i] = 0x9e3779b9u * (8 * j + i + 1);
+    for (int j = 0; j < 8; ++j) K.c[j][7] &= 0x0fffffffu;
+    const int eff_ilp = ilp == 1 ? 1 : ilp == 2 ? 2 : 4;
     for (int rep = 0; rep < 2; ++rep) {
         cudaEventRecord(e0, s);
-        if (ilp == 1) k_mul_bench<1><<<grid, kThreads, 0, s>>>(scratch, iters);
-        else if (ilp == 2) k_mul_bench<2><<<grid, kThreads, 0, s>>>(scratch, iters);
-        else k_mul_bench<4><<<grid, kThreads, 0, s>>>(scratch, iters);
+#define GKR_BENCH_LAUNCH(I, M) k_mul_bench<I, M><<<grid, kThreads, 0, s>>>(scratch, iters, K)
+        if (mode == 0) { if (eff_ilp == 1) GKR_BENCH_LAUNCH(1, 0); else if (eff_ilp == 2) GKR_BENCH_LAUNCH(2, 0); else GKR_BENCH_LAUNCH(4, 0); }
+        else if (mode == 1) { if (eff_ilp == 1) GKR_BENCH_LAUNCH(1, 1); else if (eff_ilp == 2) GKR_BENCH_LAUNCH(2, 1); else GKR_BENCH_LAUNCH(4, 1); }
+        else { if (eff_ilp == 1) GKR_BENCH_LAUNCH(1, 2); else if (eff_ilp == 2) GKR_BENCH_LAUNCH(2, 2); else GKR_BENCH_LAUNCH(4, 2); }
+#undef GKR_BENCH_LAUNCH
         cudaEventRecord(e1, s);
         cudaEventSynchronize(e1);
     }
@@ -919,7 +949,6 @@ double run_mul_bench(int ilp, int blocks_per_sm, int iters, Fr *scratch, cudaStr
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    const int eff_ilp = ilp == 1 ? 1 : ilp == 2 ? 2 : 4;
     return (double)grid * kThreads * eff_ilp * (double)iters / (ms * 1e-3);
 }
 

@@ -112,6 +112,7 @@ void launch_dot(const Fr *X, const Fr *Y, uint64_t n, const ReduceWs &ws, HostSl
 int device_sm_count();
 
 // field multiplications per second with `ilp` independent chains per thread and blocks_per_sm CTAs of 256 threads
-double run_mul_bench(int ilp, int blocks_per_sm, int iters, Fr *scratch, cudaStream_t s);
+// mode 0: fr_mul, 1: fr_mul_const, 2: wide_mac (lazy 512-bit multiply-accumulate)
+double run_mul_bench(int ilp, int blocks_per_sm, int iters, Fr *scratch, cudaStream_t s, int mode = 0);
 
 }  // namespace gkr

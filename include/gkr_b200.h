@@ -203,7 +203,8 @@ typedef struct {
 } gkr_profile;
 int gkr_ctx_profile(gkr_ctx *ctx, int enable, gkr_profile *out);
 /* integer-pipe ceiling of this device: Montgomery products per second in a register-resident loop
- * (ilp = 1, 2 or 4 independent chains per thread; blocks_per_sm CTAs of 256 threads per SM) */
+ * (ilp = 1, 2 or 4 independent chains per thread; add 16 to time fr_mul_const -- the constant-multiplier fold
+ * product -- or 32 to time wide_mac, the unreduced 512-bit multiply-accumulate; blocks_per_sm CTAs of 256 threads) */
 int gkr_bench_field_mul(gkr_ctx *ctx, int ilp, int blocks_per_sm, int iters, double *mul_per_second);
 
 #ifdef __cplusplus

@@ -13,4 +13,9 @@ for ilp in (1, 2, 4):
     for bps in (1, 2, 4, 8):
         out[f"ilp{ilp}_cta{bps}"] = round(pv.bench_field_mul(ilp, bps, 3000) / 1e9, 2)
 best = max(out.values())
-print(json.dumps({"gmul_per_s": out, "best_gmul_per_s": best}))
+other = {}
+for name, flag in (("fr_mul_const", 16), ("wide_mac", 32)):
+    for ilp in (1, 4):
+        for bps in (2, 4):
+            other[f"{name}_ilp{ilp}_cta{bps}"] = round(pv.bench_field_mul(flag + ilp, bps, 3000) / 1e9, 2)
+print(json.dumps({"gmul_per_s": out, "best_gmul_per_s": best, "other_ops_g_per_s": other}))
