@@ -8,6 +8,9 @@
 
 namespace gkr {
 
+#ifndef GKR_FOLD_PREFETCH
+#define GKR_FOLD_PREFETCH 0       // experiment: L2 prefetch of the next iteration in the fused degree-2 rounds too
+#endif
 #ifndef GKR_PROD3_PAIRS
 #define GKR_PROD3_PAIRS 1         // pairs per loop iteration and thread in the degree-3 kernel (2 => 1 CTA/SM, 255 registers)
 #endif
@@ -412,9 +415,9 @@ __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const
             // no-fold rounds are memory-bound: pull the next iteration's lines towards L2 (in the fused
             // rounds this raised DRAM reads by 32 % without a speed-up -- ncu r01 -- so it is off there)
             const uint64_t nx = i + (uint64_t)gridDim.x * blockDim.x;
-            if (!FOLD && nx < q) {
+            if ((!FOLD || GKR_FOLD_PREFETCH) && nx < q) {
 #pragma unroll
-                for (int t = 0; t < 2; ++t) {
+                for (int t = 0; t < (FOLD ? 4 : 2); ++t) {
                     prefetch_l2(Win + nx + t * q);
                     prefetch_l2(Hin + nx + t * q);
                     prefetch_l2(Ain + nx + t * q);

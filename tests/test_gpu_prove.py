@@ -172,6 +172,25 @@ def test_gpu_verifier_config2(pv):
     w.close()
 
 
+def test_concurrent_contexts_in_threads():
+    """one gkr_ctx per host thread, several at once on the same device (the reference proves sub-circuits under
+    rayon par_iter): every proof still equals the oracle's"""
+    from gkr_b200 import DenseLayer
+    from gkr_b200.batch import prove_many
+    rng = random.Random(31337)
+    jobs, wants = [], []
+    for n in range(24):
+        ks = rng.choice([[2, 3, 2], [4, 5, 4, 3], [1, 6, 6], [7, 8, 8, 7, 8]])
+        layers = random_circuit(rng, ks, "mixed")
+        inputs = [rng.randrange(P) for _ in range(1 << ks[-1])]
+        dl = dense_layers(layers)
+        jobs.append(([DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in dl], ints_to_fr(inputs)))
+        wants.append(run_l1(layers, inputs)[0])
+    got = prove_many(jobs, n_workers=6)
+    for a, b in zip(wants, got):
+        assert_same_dense(a, b)
+
+
 def test_prelaunch_off_matches(pv):
     """pre-launched (command-waiting) tail rounds vs plain per-round launches: same proof"""
     from gkr_b200 import Prover
