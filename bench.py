@@ -117,6 +117,25 @@ def cpu_sample_ms(k: int, layers: int, sample_layers: int, seed: int = 1):
     return dt * 1e3 * (layers / sl), orc.num_threads(), f"{sl} of {layers} layers of the same circuit, scaled x{layers / sl:g}"
 
 
+def literal_reference_seconds(ks=(5, 6, 7)):
+    """seconds for ONE layer of 2^k gates with the LITERAL restatement of the reference's term-list algorithm
+    (oracle/l0_reference.py, pure Python, 1 thread): documents its O(4^k) growth -- it cannot reach k = 16..20."""
+    import random
+
+    from oracle import l0_reference as l0
+    out = {}
+    rng = random.Random(1)
+    l0.mimc7_constants()
+    for k in ks:
+        gates = [(rng.randrange(2), rng.randrange(1 << k), rng.randrange(1 << k)) for _ in range(1 << k)]
+        circ = l0.build_reference_circuit([(k, gates)], k)
+        inp, _ = l0.calculate_input([(k, gates)], [rng.randrange(l0.P) for _ in range(1 << k)])
+        t0 = time.perf_counter()
+        l0.prove(circ, inp)
+        out[f"k={k}"] = round(time.perf_counter() - t0, 4)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -138,7 +157,8 @@ def run_reference(args):
         "config": {"workload": _workload_name(k, layers), "k": k, "layers": layers},
         "cpu_baseline": {"value": ms, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "dense CPU oracle (oracle/gkr_dense.c, OpenMP); the Rust reference cannot be built here "
-                                 "and its term-list algorithm is O(4^k) per round (infeasible at this size)"},
+                                 "and its term-list algorithm is O(4^k) per round (infeasible at this size)",
+                         "literal_reference_algorithm_seconds_per_layer": literal_reference_seconds()},
         "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -379,7 +399,8 @@ def run_ours(args):
         try:
             ms, cores, sample = cpu_sample_ms(k, layers, 1 if k >= 20 else 2)
             cpu = {"value": ms, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                   "note": "dense CPU oracle (oracle/gkr_dense.c); the Rust reference cannot be built here"}
+                   "note": "dense CPU oracle (oracle/gkr_dense.c); the Rust reference cannot be built here",
+                   "literal_reference_algorithm_seconds_per_layer": literal_reference_seconds()}
         except Exception as e:  # the oracle is a checker, never a dependency of the measured path
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
