@@ -115,9 +115,18 @@ int gkr_ctx::wait_slot(uint32_t s, const HostSlot **out) {
     const double t0 = now_seconds();
     volatile HostSlot *slot = slots_host + (s % kSlots);
     uint64_t spins = 0;
+    double next_check = t0 + 2.0;
     while (slot->seq != s) {
         _mm_pause();
-        if ((++spins & 0xFFFFF) == 0) {
+        if ((++spins & 0xFFF) != 0) continue;
+        const double now = now_seconds();
+        if (now < next_check) continue;
+        next_check = now + 2.0;
+        // Rare slow path.  While pre-launched kernels of this context are waiting for their challenges no CUDA
+        // call may be made here: another thread's implicitly synchronising call (cudaFree ...) can hold the driver
+        // lock until our kernel finishes, and our kernel finishes only once this thread hands it its challenge.
+        // Those kernels time out by themselves and publish the failure.
+        if (prelaunched_pending == 0) {
             cudaError_t e = cudaStreamQuery(stream);
             if (e != cudaSuccess && e != cudaErrorNotReady) {
                 set_last_error("stream error while waiting for a round result: %s", cudaGetErrorString(e));
@@ -131,10 +140,10 @@ int gkr_ctx::wait_slot(uint32_t s, const HostSlot **out) {
                     return GKR_ERR_INTERNAL;
                 }
             }
-            if (now_seconds() - t0 > 120.0) {
-                set_last_error("timed out waiting for round result %u", s);
-                return GKR_ERR_INTERNAL;
-            }
+        }
+        if (now - t0 > 120.0) {
+            set_last_error("timed out waiting for round result %u", s);
+            return GKR_ERR_INTERNAL;
         }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
@@ -379,6 +388,8 @@ struct LayerDev {
 };
 struct gkr_circuit {
     int device = 0;
+    gkr_ctx *owner = nullptr;     // device arrays come from / return to the owner's pool (no cudaFree per circuit)
+    std::vector<std::pair<void *, size_t>> allocs;
     int n_ranks = 1, rank = 0;    // communicator geometry the CSRs were built for
     std::vector<LayerDev> layers;
     std::vector<uint32_t> k;      // k_0 .. k_depth
@@ -409,8 +420,12 @@ static void build_csr(uint32_t n_rows, uint32_t n_gates, const uint32_t *key, co
 }
 
 template <typename T>
-static int dev_copy(gkr_ctx *ctx, T **dst, const T *src, size_t n) {
-    GKR_CUDA_TRY(cudaMalloc((void **)dst, std::max<size_t>(n, 1) * sizeof(T)));
+static int dev_copy(gkr_ctx *ctx, gkr_circuit *c, T **dst, const T *src, size_t n) {
+    // sizes rounded up to 256 B multiples so that the pool can recycle them across circuits of similar shape
+    const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) / 256 * 256;
+    *dst = static_cast<T *>(ctx->pool_get(bytes));
+    if (!*dst) return GKR_ERR_OOM;
+    c->allocs.emplace_back(*dst, bytes);
     GKR_CUDA_TRY(cudaMemcpyAsync(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     ctx->stats.h2d_bytes += n * sizeof(T);
     return GKR_OK;
@@ -418,11 +433,7 @@ static int dev_copy(gkr_ctx *ctx, T **dst, const T *src, size_t n) {
 
 extern "C" void gkr_circuit_destroy(gkr_circuit *c) {
     if (!c) return;
-    cudaSetDevice(c->device);
-    for (LayerDev &L : c->layers)
-        for (void *p : {(void *)L.type, (void *)L.left, (void *)L.right, (void *)L.rowptr1, (void *)L.gate1,
-                        (void *)L.other1, (void *)L.rowptr2, (void *)L.gate2, (void *)L.other2})
-            if (p) cudaFree(p);
+    for (auto &a : c->allocs) c->owner->pool_put(a.first, a.second);
     delete c;
 }
 
@@ -461,6 +472,7 @@ extern "C" int gkr_circuit_create(gkr_ctx *ctx, uint32_t n_layers, const gkr_lay
     std::unique_ptr<gkr_circuit, void (*)(gkr_circuit *)> c(new (std::nothrow) gkr_circuit(), gkr_circuit_destroy);
     if (!c) return GKR_ERR_OOM;
     c->device = ctx->device;
+    c->owner = ctx;
     c->n_ranks = ctx->nccl_comm ? ctx->n_ranks : 1;
     c->rank = ctx->nccl_comm ? ctx->rank : 0;
     uint32_t lb = 0;
@@ -474,24 +486,24 @@ extern "C" int gkr_circuit_create(gkr_ctx *ctx, uint32_t n_layers, const gkr_lay
         L.k_out = d.k_out; L.k_in = d.k_in; L.n_gates = d.n_gates;
         c->k.push_back(d.k_in);
         c->max_k = std::max(c->max_k, std::max(d.k_in, d.k_out));
-        GKR_TRY(dev_copy(ctx, &L.type, d.type, d.n_gates));
-        GKR_TRY(dev_copy(ctx, &L.left, d.left, d.n_gates));
-        GKR_TRY(dev_copy(ctx, &L.right, d.right, d.n_gates));
+        GKR_TRY(dev_copy(ctx, c.get(), &L.type, d.type, d.n_gates));
+        GKR_TRY(dev_copy(ctx, c.get(), &L.left, d.left, d.n_gates));
+        GKR_TRY(dev_copy(ctx, c.get(), &L.right, d.right, d.n_gates));
         const uint32_t rows = (uint32_t)1 << d.k_in;
         // a layer is table-sharded across the ranks when every rank keeps at least two rows of it
         L.sharded = c->n_ranks > 1 && d.k_in >= lb + 1;
         const uint32_t P = L.sharded ? (uint32_t)c->n_ranks : 1u, rk = L.sharded ? (uint32_t)c->rank : 0u;
         build_csr(rows, d.n_gates, d.left, d.right, d.type, P, rk, rowptr, gate, oth);
         L.n_edges1 = (uint32_t)gate.size();
-        GKR_TRY(dev_copy(ctx, &L.rowptr1, rowptr.data(), rowptr.size()));
-        GKR_TRY(dev_copy(ctx, &L.gate1, gate.data(), gate.size()));
-        GKR_TRY(dev_copy(ctx, &L.other1, oth.data(), oth.size()));
+        GKR_TRY(dev_copy(ctx, c.get(), &L.rowptr1, rowptr.data(), rowptr.size()));
+        GKR_TRY(dev_copy(ctx, c.get(), &L.gate1, gate.data(), gate.size()));
+        GKR_TRY(dev_copy(ctx, c.get(), &L.other1, oth.data(), oth.size()));
         GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));   // host vectors are reused below
         build_csr(rows, d.n_gates, d.right, d.left, d.type, P, rk, rowptr, gate, oth);
         L.n_edges2 = (uint32_t)gate.size();
-        GKR_TRY(dev_copy(ctx, &L.rowptr2, rowptr.data(), rowptr.size()));
-        GKR_TRY(dev_copy(ctx, &L.gate2, gate.data(), gate.size()));
-        GKR_TRY(dev_copy(ctx, &L.other2, oth.data(), oth.size()));
+        GKR_TRY(dev_copy(ctx, c.get(), &L.rowptr2, rowptr.data(), rowptr.size()));
+        GKR_TRY(dev_copy(ctx, c.get(), &L.gate2, gate.data(), gate.size()));
+        GKR_TRY(dev_copy(ctx, c.get(), &L.other2, oth.data(), oth.size()));
         GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     }
     *out = c.release();
@@ -800,6 +812,7 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
             for (Plan &p : plan)
                 if (p.launched && p.seq && !p.commanded && p.Ho) {
                     write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), nullptr, kCmdAbort);
+                    ctx->prelaunched_pending--;
                     any = true;
                 }
             if (any) cudaStreamSynchronize(ctx->stream);
@@ -834,6 +847,7 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
                 ctx->stats.kernel_launches += 1;
                 GKR_TRY(ctx->check_launch("gkr_round_cmd"));
                 f.launched = true;
+                ctx->prelaunched_pending++;
             }
         }
         const HostSlot *slot;
@@ -848,6 +862,7 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
             const FrConstMul rc = make_const_mul(st.r);
             write_cmd(ctx->cmds_host + (plan[j + 1].seq % gkr_ctx::kSlots), &rc, plan[j + 1].seq);
             plan[j + 1].commanded = true;
+            ctx->prelaunched_pending--;
         }
     }
     if (claim_out) *claim_out = st.claim;

@@ -11,6 +11,9 @@ namespace gkr {
 #ifndef GKR_FOLD_PREFETCH
 #define GKR_FOLD_PREFETCH 0       // experiment: L2 prefetch of the next iteration in the fused degree-2 rounds too
 #endif
+#ifndef GKR_LOAD_AHEAD
+#define GKR_LOAD_AHEAD 0          // experiment: issue the W and H loads of a fused degree-2 pair before any arithmetic
+#endif
 #ifndef GKR_PROD3_PAIRS
 #define GKR_PROD3_PAIRS 1         // pairs per loop iteration and thread in the degree-3 kernel (2 => 1 CTA/SM, 255 registers)
 #endif
@@ -425,6 +428,19 @@ __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const
             }
         }
         if (FOLD) {
+#if GKR_LOAD_AHEAD
+            // issue the eight W/H loads back to back before any arithmetic: more bytes in flight per warp
+            const Fr w0 = ld_fr(Win + i), w1 = ld_fr(Win + i + q), w2 = ld_fr(Win + i + 2 * q), w3 = ld_fr(Win + i + 3 * q);
+            const Fr h0 = ld_fr(Hin + i), h1 = ld_fr(Hin + i + q), h2 = ld_fr(Hin + i + 2 * q), h3 = ld_fr(Hin + i + 3 * q);
+            wl = fold2(w0, w2, r);
+            wh = fold2(w1, w3, r);
+            st_fr(Wout + i, wl);
+            st_fr(Wout + i + q, wh);
+            hl = fold2(h0, h2, r);
+            hh = fold2(h1, h3, r);
+            st_fr(Hout + i, hl);
+            st_fr(Hout + i + q, hh);
+#else
             wl = fold2(ld_fr(Win + i), ld_fr(Win + i + 2 * q), r);
             wh = fold2(ld_fr(Win + i + q), ld_fr(Win + i + 3 * q), r);
             st_fr(Wout + i, wl);
@@ -433,6 +449,7 @@ __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const
             hh = fold2(ld_fr(Hin + i + q), ld_fr(Hin + i + 3 * q), r);
             st_fr(Hout + i, hl);
             st_fr(Hout + i + q, hh);
+#endif
         } else {
             wl = ld_fr(Win + i); wh = ld_fr(Win + i + q);
             hl = ld_fr(Hin + i); hh = ld_fr(Hin + i + q);

@@ -108,6 +108,7 @@ struct gkr_ctx {
     gkr::HostCmd *cmds_host = nullptr;     // pinned + mapped: challenge tables for pre-launched round kernels
     gkr::HostCmd *cmds_dev = nullptr;
     bool prelaunch = true;                 // pre-launch the small-table rounds of a phase (option "prelaunch")
+    int prelaunched_pending = 0;           // launched kernels still waiting for their challenge (see wait_slot)
     uint32_t seq = 0;
     gkr::ReduceWs ws{};
     unsigned int *words = nullptr;         // [8] device words: [0] range-error flag, [4..6] support/flags scratch

@@ -85,9 +85,10 @@ class _Handle:
 
 
 class Circuit(_Handle):
-    def __init__(self, ptr, free, ks):
+    def __init__(self, ptr, free, ks, owner=None):
         super().__init__(ptr, free)
         self.k = list(ks)
+        self._owner = owner          # keeps the Prover (gkr_ctx) alive: the device arrays return to its pool
 
 
 class Witness(_Handle):
@@ -117,12 +118,13 @@ class Prover:
         self._ctx = ctx
         self.device = device
         self._witnesses = weakref.WeakSet()
+        self._circuits = weakref.WeakSet()
 
     def close(self):
-        """destroys the context; witnesses created from it must already be closed"""
+        """destroys the context after closing the circuits and witnesses created from it"""
         if getattr(self, "_ctx", None):
-            for w in list(getattr(self, "_witnesses", [])):
-                w.close()
+            for h in list(getattr(self, "_witnesses", [])) + list(getattr(self, "_circuits", [])):
+                h.close()
             self._L.gkr_ctx_destroy(self._ctx)
             self._ctx = None
 
@@ -159,7 +161,9 @@ class Prover:
         out = C.c_void_p()
         _lib.check(self._L.gkr_circuit_create(self._ctx, n, arr, C.byref(out)))
         ks = [layers[0].k_out] + [L.k_in for L in layers] if n else []
-        return Circuit(out, self._L.gkr_circuit_destroy, ks)
+        c = Circuit(out, self._L.gkr_circuit_destroy, ks, self)
+        self._circuits.add(c)
+        return c
 
     def witness(self, circuit: Circuit, layer_values) -> Witness:
         vals = [as_fr_array(v) for v in layer_values]

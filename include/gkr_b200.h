@@ -94,6 +94,7 @@ typedef struct {
 /* layers[0] is the output layer; layers[i].k_in == layers[i+1].k_out.  Copies everything it needs
  * (the caller may free its arrays on return) and builds the by-left / by-right CSR on the device. */
 int gkr_circuit_create(gkr_ctx *ctx, uint32_t n_layers, const gkr_layer_desc *layers, gkr_circuit **out);
+/* returns the device arrays to the creating context's pool: destroy circuits BEFORE their gkr_ctx */
 void gkr_circuit_destroy(gkr_circuit *c);
 
 /* ---- witness (replaces calculate_input, convert.rs:787-849) -------------------------------------- */
