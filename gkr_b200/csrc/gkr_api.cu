@@ -87,9 +87,44 @@ extern "C" const char *gkr_version(void) { return "gkr_b200 0.1 (sm_100a)"; }
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
+namespace gkr {
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap) return GKR_OK;
+    if (owner) {
+        const size_t want = (bytes + 255) / 256 * 256;
+        void *p = owner->pool_get(want);
+        if (!p) return GKR_ERR_OOM;
+        if (ptr) owner->pool_put(ptr, cap);
+        ptr = p;
+        cap = want;
+        return GKR_OK;
+    }
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&ptr, bytes);
+    if (e != cudaSuccess) {
+        set_last_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? GKR_ERR_OOM : GKR_ERR_CUDA;
+    }
+    cap = bytes;
+    return GKR_OK;
+}
+void DevBuf::release() {
+    if (ptr) {
+        if (owner) owner->pool_put(ptr, cap);
+        else cudaFree(ptr);
+    }
+    ptr = nullptr;
+    cap = 0;
+}
+}  // namespace gkr
+
 void *gkr_ctx::pool_get(size_t bytes) {
-    auto it = dev_pool.find(bytes);
-    if (it != dev_pool.end()) {
+    // best fit among cached blocks that are not wastefully larger than the request
+    auto it = dev_pool.lower_bound(bytes);
+    if (it != dev_pool.end() && it->first <= bytes + bytes / 4 + 4096) {
         void *p = it->second;
         dev_pool.erase(it);
         return p;
@@ -98,7 +133,10 @@ void *gkr_ctx::pool_get(size_t bytes) {
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e != cudaSuccess) {
         // give cached blocks back to the driver and retry once
-        for (auto &kv : dev_pool) cudaFree(kv.second);
+        for (auto &kv : dev_pool) {
+            cudaFree(kv.second);
+            block_size.erase(kv.second);
+        }
         dev_pool.clear();
         cudaGetLastError();
         e = cudaMalloc(&p, bytes);
@@ -108,7 +146,13 @@ void *gkr_ctx::pool_get(size_t bytes) {
         cudaGetLastError();
         return nullptr;
     }
+    block_size[p] = bytes;
     return p;
+}
+void gkr_ctx::pool_put(void *p, size_t /*requested*/) {
+    if (!p) return;
+    auto it = block_size.find(p);
+    dev_pool.emplace(it != block_size.end() ? it->second : 0, p);     // filed under its true size
 }
 
 int gkr_ctx::wait_slot(uint32_t s, const HostSlot **out) {
@@ -178,6 +222,7 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->slots_host, sizeof(HostSlot) * gkr_ctx::kSlots, cudaHostAllocMapped));
     std::memset((void *)ctx->slots_host, 0, sizeof(HostSlot) * gkr_ctx::kSlots);
     GKR_CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->slots_dev, (void *)ctx->slots_host, 0));
+    GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->pinned_words, 64, cudaHostAllocDefault));
     GKR_CUDA_TRY(cudaHostAlloc((void **)&ctx->cmds_host, sizeof(HostCmd) * gkr_ctx::kSlots, cudaHostAllocMapped));
     std::memset((void *)ctx->cmds_host, 0, sizeof(HostCmd) * gkr_ctx::kSlots);
     GKR_CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->cmds_dev, (void *)ctx->cmds_host, 0));
@@ -204,13 +249,15 @@ extern "C" void gkr_ctx_destroy(gkr_ctx *ctx) {
     for (DevBuf *b : {&ctx->eqz, &ctx->equ, &ctx->eq_scratch, &ctx->H, &ctx->A, &ctx->foldA, &ctx->foldB, &ctx->lineA,
                       &ctx->lineB, &ctx->mob, &ctx->misc, &ctx->stage, &ctx->aux_mob, &ctx->aux_stage, &ctx->qdev, &ctx->wP, &ctx->wQ, &ctx->shard_w, &ctx->shard_mini})
         b->release();
-    for (auto &kv : ctx->dev_pool) cudaFree(kv.second);
+    for (auto &kv : ctx->block_size) cudaFree(kv.first);     // every block the pool ever handed out
+    ctx->block_size.clear();
     ctx->dev_pool.clear();
     if (ctx->ws.partials) cudaFree(ctx->ws.partials);
     if (ctx->ws.counter) cudaFree(ctx->ws.counter);
     if (ctx->words) cudaFree(ctx->words);
     if (ctx->slots_host) cudaFreeHost((void *)ctx->slots_host);
     if (ctx->cmds_host) cudaFreeHost((void *)ctx->cmds_host);
+    if (ctx->pinned_words) cudaFreeHost(ctx->pinned_words);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -321,10 +368,9 @@ static int upload_table(gkr_ctx *ctx, const gkr_fr *host, uint64_t n, Fr *dev_ou
     launch_to_mont(ctx->stage.as<Fr>(), dev_out, n, ctx->words, ctx->stream);
     ctx->end_launch(KC_OTHER, 64.0 * n);
     GKR_TRY(ctx->check_launch("to_mont"));
-    unsigned int flag = 0;
-    GKR_CUDA_TRY(cudaMemcpyAsync(&flag, ctx->words, sizeof flag, cudaMemcpyDeviceToHost, ctx->stream));
+    GKR_CUDA_TRY(cudaMemcpyAsync(ctx->pinned_words, ctx->words, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
     GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    if (flag) {
+    if (ctx->pinned_words[0]) {
         cudaMemsetAsync(ctx->words, 0, sizeof(unsigned int), ctx->stream);
         set_last_error("a field element >= p was supplied");
         return GKR_ERR_RANGE;
@@ -1228,19 +1274,14 @@ extern "C" int gkr_dev_table_synth_strided(gkr_ctx *ctx, uint64_t seed, uint64_t
                                            uint64_t n, void **out) {
     if (!ctx || !out || n == 0) return GKR_ERR_INVALID;
     GKR_TRY(ctx->bind());
-    Fr *p = nullptr;
-    cudaError_t e = cudaMalloc((void **)&p, n * sizeof(Fr));
-    if (e != cudaSuccess) {
-        set_last_error("cudaMalloc(%llu elements) failed: %s", (unsigned long long)n, cudaGetErrorString(e));
-        cudaGetLastError();
-        return e == cudaErrorMemoryAllocation ? GKR_ERR_OOM : GKR_ERR_CUDA;
-    }
+    Fr *p = static_cast<Fr *>(ctx->pool_get(n * sizeof(Fr)));
+    if (!p) return GKR_ERR_OOM;
     ctx->begin_launch();
     launch_synth_values(seed, stream, first, stride, n, p, ctx->stream);
     ctx->end_launch(KC_OTHER, 32.0 * n);
     int rc = ctx->check_launch("synth_values");
     if (rc == GKR_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = GKR_ERR_CUDA;
-    if (rc != GKR_OK) { cudaFree(p); return rc; }
+    if (rc != GKR_OK) { ctx->pool_put(p, n * sizeof(Fr)); return rc; }
     *out = p;
     return GKR_OK;
 }
@@ -1250,10 +1291,10 @@ extern "C" int gkr_dev_table_synth(gkr_ctx *ctx, uint64_t seed, uint64_t stream,
 extern "C" int gkr_dev_table_upload(gkr_ctx *ctx, const gkr_fr *host, uint64_t n, void **out) {
     if (!ctx || !out || !host || n == 0) return GKR_ERR_INVALID;
     GKR_TRY(ctx->bind());
-    Fr *p = nullptr;
-    GKR_CUDA_TRY(cudaMalloc((void **)&p, n * sizeof(Fr)));
+    Fr *p = static_cast<Fr *>(ctx->pool_get(n * sizeof(Fr)));
+    if (!p) return GKR_ERR_OOM;
     int rc = upload_table(ctx, host, n, p);
-    if (rc != GKR_OK) { cudaFree(p); return rc; }
+    if (rc != GKR_OK) { ctx->pool_put(p, n * sizeof(Fr)); return rc; }
     *out = p;
     return GKR_OK;
 }
@@ -1264,8 +1305,7 @@ extern "C" int gkr_dev_table_download(gkr_ctx *ctx, const void *dev, uint64_t n,
 }
 extern "C" void gkr_dev_table_free(gkr_ctx *ctx, void *dev) {
     if (!ctx || !dev) return;
-    cudaSetDevice(ctx->device);
-    cudaFree(dev);
+    ctx->pool_put(dev, 0);       // recycled by later tables / workspaces of this context; freed with the context
 }
 
 // Shared driver of the product sumcheck.  T[i]: device tables holding this rank's shard (the whole table
@@ -1448,15 +1488,18 @@ extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_var
     const Fr *T[3];
     Fr *owned[3] = {nullptr, nullptr, nullptr};
     struct Cleanup {
+        gkr_ctx *ctx;
         Fr **p;
-        ~Cleanup() { for (int i = 0; i < 3; ++i) if (p[i]) cudaFree(p[i]); }
-    } cleanup{owned};
+        size_t bytes;
+        ~Cleanup() { for (int i = 0; i < 3; ++i) ctx->pool_put(p[i], bytes); }
+    } cleanup{ctx, owned, N * sizeof(Fr)};
     for (int i = 0; i < 3; ++i) {
         if (!tables[i]) return GKR_ERR_INVALID;
         if (on_device) {
             T[i] = static_cast<const Fr *>(tables[i]);
         } else {
-            GKR_CUDA_TRY(cudaMalloc((void **)&owned[i], N * sizeof(Fr)));
+            owned[i] = static_cast<Fr *>(ctx->pool_get(N * sizeof(Fr)));
+            if (!owned[i]) return GKR_ERR_OOM;
             GKR_TRY(upload_table(ctx, static_cast<const gkr_fr *>(tables[i]), N, owned[i]));
             T[i] = owned[i];
         }
@@ -1510,6 +1553,7 @@ extern "C" int gkr_fr_binop(gkr_ctx *ctx, int op, const gkr_fr *a, const gkr_fr 
     GKR_TRY(ctx->bind());
     GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
     DevBuf da, db;
+    da.owner = db.owner = ctx;
     struct Rel { DevBuf &a, &b; ~Rel() { a.release(); b.release(); } } rel{da, db};
     GKR_TRY(da.ensure(n * sizeof(Fr)));
     GKR_TRY(db.ensure(n * sizeof(Fr)));

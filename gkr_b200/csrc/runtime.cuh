@@ -46,29 +46,15 @@ constexpr uint64_t kPrelaunchPairs = (uint64_t)1 << 12;
 // remaining rounds run replicated on every rank (no per-round exchange for the many small late rounds)
 constexpr uint64_t kGatherEntries = (uint64_t)1 << 11;
 
-// grow-only device buffer
+// grow-only device buffer.  Buffers owned by a context take their memory from (and return it to) the
+// context's pool: steady-state proving never calls cudaFree, whose implicit device-wide synchronisation would
+// stall -- and, together with pre-launched kernels waiting for their host, could deadlock -- other contexts.
 struct DevBuf {
     void *ptr = nullptr;
     size_t cap = 0;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return GKR_OK;
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&ptr, bytes);
-        if (e != cudaSuccess) {
-            set_last_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
-            cudaGetLastError();
-            return e == cudaErrorMemoryAllocation ? GKR_ERR_OOM : GKR_ERR_CUDA;
-        }
-        cap = bytes;
-        return GKR_OK;
-    }
-    void release() {
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        cap = 0;
-    }
+    gkr_ctx *owner = nullptr;
+    int ensure(size_t bytes);
+    void release();
     template <typename T>
     T *as() const { return static_cast<T *>(ptr); }
 };
@@ -105,6 +91,7 @@ struct gkr_ctx {
     static constexpr int kSlots = 64;
     gkr::HostSlot *slots_host = nullptr;   // pinned + mapped
     gkr::HostSlot *slots_dev = nullptr;
+    unsigned int *pinned_words = nullptr;  // pinned landing zone for small device->host flags
     gkr::HostCmd *cmds_host = nullptr;     // pinned + mapped: challenge tables for pre-launched round kernels
     gkr::HostCmd *cmds_dev = nullptr;
     bool prelaunch = true;                 // pre-launch the small-table rounds of a phase (option "prelaunch")
@@ -119,11 +106,12 @@ struct gkr_ctx {
     Fr *comm_send = nullptr, *comm_recv = nullptr;
 
     // recycled device allocations for witness tables (cudaMalloc/cudaFree per proof serialise in the driver)
-    std::multimap<size_t, void *> dev_pool;
+    std::multimap<size_t, void *> dev_pool;          // free blocks by true size
+    std::map<void *, size_t> block_size;             // every block ever allocated through the pool
     void *pool_get(size_t bytes);
-    void pool_put(void *p, size_t bytes) { if (p) dev_pool.emplace(bytes, p); }
+    void pool_put(void *p, size_t bytes);
 
-    // workspaces
+    // workspaces (memory from the pool above)
     gkr::DevBuf eqz, equ, eq_scratch, H, A, foldA, foldB, lineA, lineB, mob, misc, stage, aux_mob, aux_stage, qdev, wP, wQ, shard_w, shard_mini;
 
     // accounting
@@ -133,6 +121,11 @@ struct gkr_ctx {
     gkr_profile prof{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
+    gkr_ctx() {
+        for (gkr::DevBuf *b : {&eqz, &equ, &eq_scratch, &H, &A, &foldA, &foldB, &lineA, &lineB, &mob, &misc, &stage, &aux_mob,
+                               &aux_stage, &qdev, &wP, &wQ, &shard_w, &shard_mini})
+            b->owner = this;
+    }
     int bind() const {
         cudaError_t e = cudaSetDevice(device);
         if (e != cudaSuccess) {
