@@ -58,7 +58,10 @@ void gkr_ctx_destroy(gkr_ctx *ctx);
  * g_j(0) + g_j(1) == g_{j-1}(r_{j-1}) on the host (default 0: g(1) is derived from the running claim);
  * "prelaunch" = 0 disables launching the small-table rounds of a phase ahead of their challenges (default 1:
  * those kernels wait up to ~30 s for each challenge in a mapped command block, so a transcript callback must
- * not block for longer than that) */
+ * not block for longer than that.  The library itself makes no implicitly synchronising CUDA call (cudaFree ...)
+ * while such kernels wait -- all its device memory is recycled through per-context pools -- but a host that calls
+ * cudaFree / cudaDeviceSynchronize on the same device from other threads during a proof can stall behind them;
+ * such hosts should set "prelaunch" = 0) */
 int gkr_ctx_set_option(gkr_ctx *ctx, const char *name, int value);
 /* the cudaStream_t every kernel of this context is launched on (for CUDA-event timing by the caller) */
 void *gkr_ctx_stream(gkr_ctx *ctx);
