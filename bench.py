@@ -237,6 +237,10 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # the proof is a serial chain of ~640 host hashes: bring the host core to its working clock before timing
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 0.5:
+        step_resident()
     clocks = Clocks(local) if rank == 0 else None
     pv.stats(reset=True)
     total_ms = timed(step_resident, args.steps, args.warmup)
