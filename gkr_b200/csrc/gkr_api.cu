@@ -282,6 +282,10 @@ extern "C" int gkr_ctx_set_option(gkr_ctx *ctx, const char *name, int value) {
         ctx->paranoid = value != 0;
         return GKR_OK;
     }
+    if (std::strcmp(name, "lookahead") == 0) {
+        ctx->lookahead = value != 0;
+        return GKR_OK;
+    }
     if (std::strcmp(name, "prelaunch") == 0) {
         ctx->prelaunch = value != 0;
         return GKR_OK;
@@ -693,10 +697,9 @@ struct RoundState {
     bool have_claim;
 };
 // host half of one round: published sums -> message (static length rule) -> challenge -> next claim
-static int consume_round(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, uint32_t j, bool full, const HostSlot *slot,
-                         RoundState &st, HFr *last_hash) {
+static int consume_values(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, uint32_t j, bool full, HFr x0, HFr x2, HFr x1,
+                          RoundState &st, HFr *last_hash) {
     const uint32_t k = io.k;
-    HFr x0 = to_host(slot->v[0]), x2 = to_host(slot->v[1]), x1 = full ? to_host(slot->v[2]) : hfr_zero();
     if (hf::geq_p(x0.l) || hf::geq_p(x2.l) || hf::geq_p(x1.l)) {
         set_last_error("device published an unreduced round value");
         return GKR_ERR_INTERNAL;
@@ -724,6 +727,12 @@ static int consume_round(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, uin
     st.claim = hfr_add(hfr_mul(hfr_add(hfr_mul(x2, st.r), c1), st.r), x0);      // g(r), Horner
     st.have_claim = true;
     return GKR_OK;
+}
+
+static int consume_round(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, uint32_t j, bool full, const HostSlot *slot,
+                         RoundState &st, HFr *last_hash) {
+    return consume_values(ctx, t, io, j, full, to_host(slot->v[0]), to_host(slot->v[1]),
+                          full ? to_host(slot->v[2]) : hfr_zero(), st, last_hash);
 }
 
 // Multi-GPU phase: H, W, A are this rank's shards (rows idx = i * P + rank).  The first k - log2(P) rounds
@@ -915,6 +924,143 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
     return GKR_OK;
 }
 
+// Phase with look-ahead rounds (default): while the host hashes round j's message, the device already holds the
+// next message as a quadratic in the challenge being hashed (k_gkr_poly), so a round costs max(hash, device)
+// instead of hash + device.  Kernel P_j (j = 1..k-1) folds T_{j-1} with r_{j-1} into T_j (P_1: no fold, T_1 = the
+// inputs) and publishes the six sums that give message j+1 as a polynomial in r_j.
+static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *last_hash, const HFr *claim_in,
+                          HFr *claim_out) {
+    const uint32_t k = io.k;
+    const uint64_t N = (uint64_t)1 << k;
+    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 2, 4)));
+    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 4, 4)));
+    GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
+    struct Plan {
+        const Fr *H, *W, *A;      // inputs of P_j
+        Fr *Ho, *Wo, *Ao;         // T_j (nullptr for P_1)
+        uint64_t n_in, quads;
+        uint32_t seq;
+        bool launched, commanded;
+    };
+    std::vector<Plan> plan(k);    // plan[j] for j = 1..k-1
+    const Fr *Wk1 = io.W;         // W table of T_{k-1} (4 entries), the last one a P kernel produces
+    {
+        const Fr *Hc = io.H, *Wc = io.W, *Ac = io.A;
+        uint64_t n = N;           // size of T_{j-1}
+        for (uint32_t j = 1; j + 1 <= k; ++j) {
+            Plan &p = plan[j];
+            p.H = Hc; p.W = Wc; p.A = Ac; p.n_in = n;
+            p.launched = p.commanded = false;
+            p.seq = 0;
+            if (j == 1) {
+                p.Ho = p.Wo = p.Ao = nullptr;
+                p.quads = n / 4;
+            } else {
+                DevBuf &dst = (j & 1) ? ctx->foldB : ctx->foldA;      // T_2 (N/2 entries) lives in foldA
+                const uint64_t half = n / 2;
+                p.Ho = dst.as<Fr>(); p.Wo = p.Ho + half; p.Ao = p.Wo + half;
+                p.quads = half / 4;
+                Hc = p.Ho; Wc = p.Wo; Ac = p.Ao;
+                n = half;
+            }
+        }
+        Wk1 = Wc;
+    }
+    struct AbortGuard {
+        gkr_ctx *ctx;
+        std::vector<Plan> &plan;
+        ~AbortGuard() {
+            bool any = false;
+            for (Plan &p : plan)
+                if (p.launched && p.seq && !p.commanded) {
+                    write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), nullptr, kCmdAbort);
+                    ctx->prelaunched_pending--;
+                    any = true;
+                }
+            if (any) cudaStreamSynchronize(ctx->stream);
+        }
+    } guard{ctx, plan};
+    const bool can_prelaunch = ctx->prelaunch && !ctx->profiling;
+    RoundState st{claim_in ? *claim_in : hfr_zero(), hfr_zero(), claim_in != nullptr};
+
+    // round 1 directly from the inputs, and P_1 right behind it
+    const uint32_t s1 = ctx->next_seq();
+    const bool full1 = !st.have_claim;
+    ctx->begin_launch();
+    launch_gkr_round(false, full1, io.H, io.W, io.A, nullptr, nullptr, nullptr, FrConstMul{}, N / 2, ctx->ws, ctx->slot_dev(s1), s1,
+                     ctx->stream);
+    ctx->end_launch(N / 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full1 ? 96.0 : 80.0) * N);
+    GKR_TRY(ctx->check_launch("gkr_round"));
+    auto start_poly = [&](uint32_t j) -> int {      // r_{j-1} (st.r) is known, or j == 1
+        Plan &p = plan[j];
+        if (p.launched) {
+            const FrConstMul rc = make_const_mul(st.r);
+            write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), &rc, p.seq);
+            p.commanded = true;
+            ctx->prelaunched_pending--;
+            return GKR_OK;
+        }
+        p.seq = ctx->next_seq();
+        const FrConstMul rc = j > 1 ? make_const_mul(st.r) : FrConstMul{};
+        ctx->begin_launch();
+        launch_gkr_poly(j > 1, p.H, p.W, p.A, p.Ho, p.Wo, p.Ao, rc, p.quads, ctx->ws, ctx->slot_dev(p.seq), p.seq, ctx->stream);
+        if (j == 1) ctx->end_launch(p.quads * 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, 80.0 * p.n_in);
+        else ctx->end_launch(p.quads * 2 >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 144.0 * p.n_in);
+        GKR_TRY(ctx->check_launch("gkr_poly"));
+        p.launched = p.commanded = true;
+        // the small-table kernels that follow are enqueued now and wait for their challenges on the device
+        if (can_prelaunch && j + 1 <= k - 1 && !plan[j + 1].launched && plan[j + 1].quads * 2 < kPrelaunchPairs) {
+            for (uint32_t u = j + 1; u + 1 <= k; ++u) {
+                Plan &f = plan[u];
+                f.seq = ctx->next_seq();
+                write_cmd(ctx->cmds_host + (f.seq % gkr_ctx::kSlots), nullptr, 0u);
+                launch_gkr_poly(true, f.H, f.W, f.A, f.Ho, f.Wo, f.Ao, FrConstMul{}, f.quads, ctx->ws, ctx->slot_dev(f.seq), f.seq,
+                                ctx->stream, ctx->cmds_dev + (f.seq % gkr_ctx::kSlots));
+                ctx->stats.kernel_launches += 1;
+                GKR_TRY(ctx->check_launch("gkr_poly_cmd"));
+                f.launched = true;
+                ctx->prelaunched_pending++;
+            }
+        }
+        return GKR_OK;
+    };
+    if (k >= 2) GKR_TRY(start_poly(1));
+    {
+        const HostSlot *slot;
+        GKR_TRY(ctx->wait_slot(s1, &slot));
+        GKR_TRY(consume_round(ctx, t, io, 0, full1, slot, st, last_hash));
+    }
+    for (uint32_t j = 2; j <= k; ++j) {
+        const HFr r_prev = st.r;                       // r_{j-1}
+        if (j + 1 <= k) GKR_TRY(start_poly(j));        // device: fold with r_{j-1}, prepare message j+1
+        const HostSlot *slot;
+        GKR_TRY(ctx->wait_slot(plan[j - 1].seq, &slot));
+        if (slot->aux[2] == 0xDEADu) {
+            set_last_error("pre-launched look-ahead kernel %u gave up waiting for its challenge", j - 1);
+            return GKR_ERR_INTERNAL;
+        }
+        const HFr Q0 = to_host(slot->v[0]), Q1 = to_host(slot->v[1]), Q2 = to_host(slot->v[2]);
+        const HFr E0 = to_host(slot->v[3]), E1 = to_host(slot->v[4]), E2 = to_host(slot->v[5]);
+        // message j at r_{j-1}: X0 = Q0 + (Q1-Q0-Q2) r + Q2 r^2,  X2 = E0 + (E1-E0-E2) r + E2 r^2
+        const HFr x0 = hfr_add(Q0, hfr_mul(r_prev, hfr_add(hfr_sub(hfr_sub(Q1, Q0), Q2), hfr_mul(Q2, r_prev))));
+        const HFr x2 = hfr_add(E0, hfr_mul(r_prev, hfr_add(hfr_sub(hfr_sub(E1, E0), E2), hfr_mul(E2, r_prev))));
+        GKR_TRY(consume_values(ctx, t, io, j - 1, false, x0, x2, hfr_zero(), st, last_hash));
+    }
+    // the W table of the last round (2 entries): fold T_{k-1}.W (4 entries) with r_{k-1}
+    if (k >= 2) {
+        Fr *w2 = ctx->misc.as<Fr>() + 16;
+        ctx->begin_launch();
+        launch_fold(Wk1, w2, make_const_mul(io.challenges[k - 2]), 2, ctx->stream);
+        ctx->end_launch(KC_OTHER, 192.0);
+        GKR_TRY(ctx->check_launch("fold"));
+        io.W_last = w2;
+    } else {
+        io.W_last = io.W;
+    }
+    if (claim_out) *claim_out = st.claim;
+    return GKR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // prove
 // ------------------------------------------------------------------------------------------------
@@ -1068,8 +1214,10 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         io.challenges = rs.data();
         io.msgs = &P->msgs[3 * ro]; io.msg_len = &P->msg_len[ro]; io.chal_out = &P->chal[ro];
         HFr claim = hfr_zero();
+        const bool lookahead = ctx->lookahead && !ctx->paranoid && !L.sharded;
         GKR_TRY(L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, nullptr, &claim)
-                          : run_phase(ctx, t, io, &last_hash, nullptr, &claim));
+                : lookahead ? run_phase_poly(ctx, t, io, &last_hash, nullptr, &claim)
+                            : run_phase(ctx, t, io, &last_hash, nullptr, &claim));
         // W(u): fold the last size-2 W table with r_k
         ctx->begin_launch();
         launch_fold(io.W_last, wu, make_const_mul(rs[k - 1]), 1, ctx->stream);
@@ -1086,7 +1234,8 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         io.challenges = rs.data() + k;
         io.msgs = &P->msgs[3 * (ro + k)]; io.msg_len = &P->msg_len[ro + k]; io.chal_out = &P->chal[ro + k];
         GKR_TRY(L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, &claim, &claim)
-                          : run_phase(ctx, t, io, &last_hash, &claim, &claim));
+                : lookahead ? run_phase_poly(ctx, t, io, &last_hash, &claim, &claim)
+                            : run_phase(ctx, t, io, &last_hash, &claim, &claim));
 
         // ---- q_i = W restricted to the line b* -> c* (poly.rs:469-500): needs only b*, c* => runs on the
         //      low-priority stream while the next layer's rounds proceed; collected after the last layer ----

@@ -482,6 +482,110 @@ __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const
     }
     grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, dev_out);
 }
+// ------------------------------------------------------------------------------------------------
+// Look-ahead round: the message of the NEXT round as a polynomial in the challenge that is not known yet.
+// With o0..o3 the four quarters of the (just folded) tables, the next fold gives lo = o0 + r'(o2-o0),
+// hi = o1 + r'(o3-o1), so both message sums are quadratics in r':
+//   X0(r') = sum (H_lo W_lo + A_lo)     = Q0 + (Q1 - Q0 - Q2) r' + Q2 r'^2
+//   X2(r') = sum (H_hi-H_lo)(W_hi-W_lo) = E0 + (E1 - E0 - E2) r' + E2 r'^2
+//   Q0 = sum H0 W0 + A0, Q1 = sum H2 W2 + A2, Q2 = sum (H2-H0)(W2-W0),
+//   E0 = sum (H1-H0)(W1-W0), E1 = sum (H3-H2)(W3-W2), E2 = sum [(H3-H2)-(H1-H0)][(W3-W2)-(W1-W0)]
+// The host evaluates them the moment it has hashed r', while the device is already folding with r' and
+// preparing the round after: the per-round cost becomes max(hash, device) instead of their sum.
+// FOLD: inputs have 8*q4 entries and are first folded with r into the 4*q4-entry outputs (one pass).
+// Published: v[0..5] = Q0, Q1, Q2, E0, E1, E2.
+// ------------------------------------------------------------------------------------------------
+template <bool FOLD, class KT>
+__device__ __forceinline__ void gkr_poly_body(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+                                              const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
+                                              Fr *__restrict__ Wout, Fr *__restrict__ Aout, const KT &r,
+                                              uint64_t q4, Fr *partials, unsigned int *counter, HostSlot *slot,
+                                              uint32_t seq) {
+    Fr acc[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[j] = fr_zero();
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < q4; i += (uint64_t)gridDim.x * blockDim.x) {
+        Fr w[4], h[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (FOLD) {
+                w[s] = fold2(ld_fr(Win + i + s * q4), ld_fr(Win + i + (s + 4) * q4), r);
+                st_fr(Wout + i + s * q4, w[s]);
+            } else {
+                w[s] = ld_fr(Win + i + s * q4);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            if (FOLD) {
+                h[s] = fold2(ld_fr(Hin + i + s * q4), ld_fr(Hin + i + (s + 4) * q4), r);
+                st_fr(Hout + i + s * q4, h[s]);
+            } else {
+                h[s] = ld_fr(Hin + i + s * q4);
+            }
+        }
+        acc[0] = fr_add(acc[0], fr_mul(h[0], w[0]));
+        acc[1] = fr_add(acc[1], fr_mul(h[2], w[2]));
+        acc[2] = fr_add(acc[2], fr_mul(fr_sub(h[2], h[0]), fr_sub(w[2], w[0])));
+        const Fr uh = fr_sub(h[1], h[0]), uw = fr_sub(w[1], w[0]);
+        const Fr th = fr_sub(h[3], h[2]), tw = fr_sub(w[3], w[2]);
+        acc[3] = fr_add(acc[3], fr_mul(uh, uw));
+        acc[4] = fr_add(acc[4], fr_mul(th, tw));
+        acc[5] = fr_add(acc[5], fr_mul(fr_sub(th, uh), fr_sub(tw, uw)));
+        // A only enters through its quarter sums
+        Fr a0, a2;
+        if (FOLD) {
+            a0 = fold2(ld_fr(Ain + i), ld_fr(Ain + i + 4 * q4), r);
+            const Fr a1 = fold2(ld_fr(Ain + i + q4), ld_fr(Ain + i + 5 * q4), r);
+            a2 = fold2(ld_fr(Ain + i + 2 * q4), ld_fr(Ain + i + 6 * q4), r);
+            const Fr a3 = fold2(ld_fr(Ain + i + 3 * q4), ld_fr(Ain + i + 7 * q4), r);
+            st_fr(Aout + i, a0);
+            st_fr(Aout + i + q4, a1);
+            st_fr(Aout + i + 2 * q4, a2);
+            st_fr(Aout + i + 3 * q4, a3);
+        } else {
+            a0 = ld_fr(Ain + i);
+            a2 = ld_fr(Ain + i + 2 * q4);
+        }
+        acc[0] = fr_add(acc[0], a0);
+        acc[1] = fr_add(acc[1], a2);
+    }
+    grid_sum_publish<6>(acc, partials, counter, slot, seq, 0u);
+}
+template <bool FOLD>
+__global__ void __launch_bounds__(kThreads, 2) k_gkr_poly(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+                                                          const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
+                                                          Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
+                                                          uint64_t q4, Fr *partials, unsigned int *counter,
+                                                          HostSlot *slot, uint32_t seq) {
+    gkr_poly_body<FOLD>(Hin, Win, Ain, Hout, Wout, Aout, r, q4, partials, counter, slot, seq);
+}
+__global__ void __launch_bounds__(kThreads, 2) k_gkr_poly_cmd(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+                                                              const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
+                                                              Fr *__restrict__ Wout, Fr *__restrict__ Aout,
+                                                              const HostCmd *cmd, uint64_t q4, Fr *partials,
+                                                              unsigned int *counter, HostSlot *slot, uint32_t seq) {
+    __shared__ uint32_t raw[80];
+    __shared__ int ok;
+    if (!wait_cmd(cmd, seq, raw, &ok)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            slot->aux[2] = 0xDEADu;
+            __threadfence_system();
+            slot->seq = seq;
+        }
+        return;
+    }
+    CmdConst r{raw};
+    gkr_poly_body<true>(Hin, Win, Ain, Hout, Wout, Aout, r, q4, partials, counter, slot, seq);
+}
+void launch_gkr_poly(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
+                     uint64_t quads, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s, const HostCmd *cmd) {
+    const int grid = grid_for(quads, ws.max_blocks);
+    if (cmd) k_gkr_poly_cmd<<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, cmd, quads, ws.partials, ws.counter, slot, seq);
+    else if (fold) k_gkr_poly<true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
+    else k_gkr_poly<false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
+}
+
 #ifndef GKR_ROUND_MINB
 #define GKR_ROUND_MINB 2          // resident CTAs/SM the non-lazy degree-2 round kernel is compiled for
 #endif

@@ -72,6 +72,12 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
                       const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
                       cudaStream_t s, const HostCmd *cmd = nullptr, Fr *dev_out = nullptr);
+// Look-ahead round (see kernels.cu): folds 8*quads-entry tables with r into 4*quads-entry ones (fold == true) and
+// publishes the six sums Q0, Q1, Q2, E0, E1, E2 from which the host evaluates the NEXT round's message at the next
+// challenge.  cmd != nullptr: pre-launched, waits for r in the command block.
+void launch_gkr_poly(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
+                     uint64_t quads, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq, cudaStream_t s,
+                     const HostCmd *cmd = nullptr);
 void launch_take_strided(const Fr *in, Fr *out, uint64_t first, uint64_t stride, uint64_t n, cudaStream_t s);
 // product-of-3 round (degree 3).  Publishes v[0] = g(0), v[1] = g(-1), v[2] = g(inf) (= X^3 coefficient) and
 // v[3] = g(1) when full == true.

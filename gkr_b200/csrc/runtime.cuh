@@ -94,6 +94,7 @@ struct gkr_ctx {
     unsigned int *pinned_words = nullptr;  // pinned landing zone for small device->host flags
     gkr::HostCmd *cmds_host = nullptr;     // pinned + mapped: challenge tables for pre-launched round kernels
     gkr::HostCmd *cmds_dev = nullptr;
+    bool lookahead = true;                 // look-ahead rounds: next message as a polynomial in the pending challenge
     bool prelaunch = true;                 // pre-launch the small-table rounds of a phase (option "prelaunch")
     int prelaunched_pending = 0;           // launched kernels still waiting for their challenge (see wait_slot)
     uint32_t seq = 0;

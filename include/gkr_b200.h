@@ -56,6 +56,8 @@ int gkr_ctx_create(int device, gkr_ctx **out);
 void gkr_ctx_destroy(gkr_ctx *ctx);
 /* options: "paranoid" = 1 makes every round also accumulate g(1) on the device and checks
  * g_j(0) + g_j(1) == g_{j-1}(r_{j-1}) on the host (default 0: g(1) is derived from the running claim);
+ * "lookahead" = 0 disables the look-ahead rounds (default 1: while the host hashes a round message the device
+ * already computes the next message as a quadratic in the pending challenge, so a round costs max(hash, device));
  * "prelaunch" = 0 disables launching the small-table rounds of a phase ahead of their challenges (default 1:
  * those kernels wait up to ~30 s for each challenge in a mapped command block, so a transcript callback must
  * not block for longer than that.  The library itself makes no implicitly synchronising CUDA call (cudaFree ...)

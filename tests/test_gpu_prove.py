@@ -204,6 +204,21 @@ def test_prelaunch_off_matches(pv):
     pn.close()
 
 
+def test_lookahead_off_matches(pv):
+    """look-ahead rounds (next message as a polynomial in the pending challenge) vs the plain round chain"""
+    from gkr_b200 import Prover
+    pn = Prover(0)
+    pn.set_option("lookahead", 0)
+    rng = random.Random(4321)
+    for ks in ([2, 1, 1], [1, 2, 3], [4, 3, 2], [11, 13, 12], [15, 15]):
+        layers = random_circuit(rng, ks, "mixed")
+        inputs = [rng.randrange(P) for _ in range(1 << ks[-1])]
+        a, b = _gpu_prove(pv, layers, inputs), _gpu_prove(pn, layers, inputs)
+        assert_same_dense(a, b)
+        assert_same_dense(run_l1(layers, inputs)[0], a)
+    pn.close()
+
+
 def test_custom_transcript_callback(pv):
     """the challenge callback (how a Rust host keeps mimc_rs) must see the same messages and drive the same proof"""
     rng = random.Random(5)
