@@ -924,10 +924,11 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
     return GKR_OK;
 }
 
-// Phase with look-ahead rounds (default): while the host hashes round j's message, the device already holds the
-// next message as a quadratic in the challenge being hashed (k_gkr_poly), so a round costs max(hash, device)
-// instead of hash + device.  Kernel P_j (j = 1..k-1) folds T_{j-1} with r_{j-1} into T_j (P_1: no fold, T_1 = the
-// inputs) and publishes the six sums that give message j+1 as a polynomial in r_j.
+// Phase with look-ahead rounds (default).  While the tables are large the device is the bottleneck and rounds run
+// as in run_phase (fused fold + direct message).  From level s on (tables of at most kLookaheadEntries entries) the
+// device stays one round ahead: kernel P_j folds T_{j-1} with r_{j-1} into T_j and publishes the six sums that give
+// message j+1 as a quadratic in r_j (k_gkr_poly; P_s has no fold, it reads T_s), so that when the host has hashed r_j
+// it evaluates message j+1 at once -- a round then costs max(hash, device) instead of hash + device.
 static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *last_hash, const HFr *claim_in,
                           HFr *claim_out) {
     const uint32_t k = io.k;
@@ -935,43 +936,34 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
     GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 2, 4)));
     GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 4, 4)));
     GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
-    struct Plan {
-        const Fr *H, *W, *A;      // inputs of P_j
-        Fr *Ho, *Wo, *Ao;         // T_j (nullptr for P_1)
-        uint64_t n_in, quads;
-        uint32_t seq;
-        bool launched, commanded;
+    // level j = 1..k: T_j has N / 2^(j-1) entries; T_1 = the inputs, T_j (j >= 2) ping-pongs between foldA / foldB
+    struct Level {
+        const Fr *H, *W, *A;
+        uint64_t n;
     };
-    std::vector<Plan> plan(k);    // plan[j] for j = 1..k-1
-    const Fr *Wk1 = io.W;         // W table of T_{k-1} (4 entries), the last one a P kernel produces
-    {
-        const Fr *Hc = io.H, *Wc = io.W, *Ac = io.A;
-        uint64_t n = N;           // size of T_{j-1}
-        for (uint32_t j = 1; j + 1 <= k; ++j) {
-            Plan &p = plan[j];
-            p.H = Hc; p.W = Wc; p.A = Ac; p.n_in = n;
-            p.launched = p.commanded = false;
-            p.seq = 0;
-            if (j == 1) {
-                p.Ho = p.Wo = p.Ao = nullptr;
-                p.quads = n / 4;
-            } else {
-                DevBuf &dst = (j & 1) ? ctx->foldB : ctx->foldA;      // T_2 (N/2 entries) lives in foldA
-                const uint64_t half = n / 2;
-                p.Ho = dst.as<Fr>(); p.Wo = p.Ho + half; p.Ao = p.Wo + half;
-                p.quads = half / 4;
-                Hc = p.Ho; Wc = p.Wo; Ac = p.Ao;
-                n = half;
-            }
-        }
-        Wk1 = Wc;
+    std::vector<Level> T(k + 1);
+    T[1] = Level{io.H, io.W, io.A, N};
+    for (uint32_t j = 2; j <= k; ++j) {
+        DevBuf &dst = (j & 1) ? ctx->foldB : ctx->foldA;      // T_2 (N/2 entries) lives in foldA
+        const uint64_t n = N >> (j - 1);
+        Fr *h = dst.as<Fr>();
+        T[j] = Level{h, h + n, h + 2 * n, n};
     }
+    // s = first level small enough for look-ahead rounds (and with at least 4 entries); k + 1 if there is none
+    uint32_t s = k + 1;
+    for (uint32_t j = 1; j + 1 <= k; ++j)
+        if (T[j].n <= kLookaheadEntries) { s = j; break; }
+    struct Poly {                 // P_j, j = s..k-1
+        uint32_t seq = 0;
+        bool launched = false, commanded = false;
+    };
+    std::vector<Poly> P(k + 1);
     struct AbortGuard {
         gkr_ctx *ctx;
-        std::vector<Plan> &plan;
+        std::vector<Poly> &P;
         ~AbortGuard() {
             bool any = false;
-            for (Plan &p : plan)
+            for (Poly &p : P)
                 if (p.launched && p.seq && !p.commanded) {
                     write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), nullptr, kCmdAbort);
                     ctx->prelaunched_pending--;
@@ -979,20 +971,15 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
                 }
             if (any) cudaStreamSynchronize(ctx->stream);
         }
-    } guard{ctx, plan};
+    } guard{ctx, P};
     const bool can_prelaunch = ctx->prelaunch && !ctx->profiling;
     RoundState st{claim_in ? *claim_in : hfr_zero(), hfr_zero(), claim_in != nullptr};
 
-    // round 1 directly from the inputs, and P_1 right behind it
-    const uint32_t s1 = ctx->next_seq();
-    const bool full1 = !st.have_claim;
-    ctx->begin_launch();
-    launch_gkr_round(false, full1, io.H, io.W, io.A, nullptr, nullptr, nullptr, FrConstMul{}, N / 2, ctx->ws, ctx->slot_dev(s1), s1,
-                     ctx->stream);
-    ctx->end_launch(N / 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full1 ? 96.0 : 80.0) * N);
-    GKR_TRY(ctx->check_launch("gkr_round"));
-    auto start_poly = [&](uint32_t j) -> int {      // r_{j-1} (st.r) is known, or j == 1
-        Plan &p = plan[j];
+    auto start_poly = [&](uint32_t j) -> int {      // j == s: reads T_s; j > s: folds T_{j-1} with r_{j-1} = st.r into T_j
+        Poly &p = P[j];
+        const bool fold = j > s;
+        const Level &in = fold ? T[j - 1] : T[j];
+        const uint64_t quads = T[j].n / 4;
         if (p.launched) {
             const FrConstMul rc = make_const_mul(st.r);
             write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), &rc, p.seq);
@@ -1001,21 +988,23 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
             return GKR_OK;
         }
         p.seq = ctx->next_seq();
-        const FrConstMul rc = j > 1 ? make_const_mul(st.r) : FrConstMul{};
+        const FrConstMul rc = fold ? make_const_mul(st.r) : FrConstMul{};
         ctx->begin_launch();
-        launch_gkr_poly(j > 1, p.H, p.W, p.A, p.Ho, p.Wo, p.Ao, rc, p.quads, ctx->ws, ctx->slot_dev(p.seq), p.seq, ctx->stream);
-        if (j == 1) ctx->end_launch(p.quads * 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, 80.0 * p.n_in);
-        else ctx->end_launch(p.quads * 2 >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 144.0 * p.n_in);
+        launch_gkr_poly(fold, in.H, in.W, in.A, const_cast<Fr *>(T[j].H), const_cast<Fr *>(T[j].W), const_cast<Fr *>(T[j].A), rc,
+                        quads, ctx->ws, ctx->slot_dev(p.seq), p.seq, ctx->stream);
+        ctx->end_launch(quads * 2 >= kTailPairs ? (fold ? KC_ROUND_FUSED : KC_ROUND) : KC_ROUND_TAIL,
+                        fold ? 144.0 * in.n : 80.0 * in.n);
         GKR_TRY(ctx->check_launch("gkr_poly"));
         p.launched = p.commanded = true;
         // the small-table kernels that follow are enqueued now and wait for their challenges on the device
-        if (can_prelaunch && j + 1 <= k - 1 && !plan[j + 1].launched && plan[j + 1].quads * 2 < kPrelaunchPairs) {
+        if (can_prelaunch && j + 1 <= k - 1 && !P[j + 1].launched && T[j + 1].n / 2 < kPrelaunchPairs) {
             for (uint32_t u = j + 1; u + 1 <= k; ++u) {
-                Plan &f = plan[u];
+                Poly &f = P[u];
                 f.seq = ctx->next_seq();
                 write_cmd(ctx->cmds_host + (f.seq % gkr_ctx::kSlots), nullptr, 0u);
-                launch_gkr_poly(true, f.H, f.W, f.A, f.Ho, f.Wo, f.Ao, FrConstMul{}, f.quads, ctx->ws, ctx->slot_dev(f.seq), f.seq,
-                                ctx->stream, ctx->cmds_dev + (f.seq % gkr_ctx::kSlots));
+                launch_gkr_poly(true, T[u - 1].H, T[u - 1].W, T[u - 1].A, const_cast<Fr *>(T[u].H), const_cast<Fr *>(T[u].W),
+                                const_cast<Fr *>(T[u].A), FrConstMul{}, T[u].n / 4, ctx->ws, ctx->slot_dev(f.seq), f.seq, ctx->stream,
+                                ctx->cmds_dev + (f.seq % gkr_ctx::kSlots));
                 ctx->stats.kernel_launches += 1;
                 GKR_TRY(ctx->check_launch("gkr_poly_cmd"));
                 f.launched = true;
@@ -1024,17 +1013,34 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         }
         return GKR_OK;
     };
-    if (k >= 2) GKR_TRY(start_poly(1));
-    {
+
+    // direct rounds 1 .. min(s, k): fused fold + message, exactly as in run_phase
+    const uint32_t last_direct = s <= k ? s : k;
+    for (uint32_t j = 1; j <= last_direct; ++j) {
+        const uint32_t sq = ctx->next_seq();
+        const bool full = !st.have_claim;
+        ctx->begin_launch();
+        if (j == 1) {
+            launch_gkr_round(false, full, T[1].H, T[1].W, T[1].A, nullptr, nullptr, nullptr, FrConstMul{}, N / 2, ctx->ws,
+                             ctx->slot_dev(sq), sq, ctx->stream);
+            ctx->end_launch(N / 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full ? 96.0 : 80.0) * N);
+        } else {
+            launch_gkr_round(true, full, T[j - 1].H, T[j - 1].W, T[j - 1].A, const_cast<Fr *>(T[j].H), const_cast<Fr *>(T[j].W),
+                             const_cast<Fr *>(T[j].A), make_const_mul(st.r), T[j].n / 2, ctx->ws, ctx->slot_dev(sq), sq, ctx->stream);
+            ctx->end_launch(T[j].n / 2 >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 144.0 * T[j - 1].n);
+        }
+        GKR_TRY(ctx->check_launch("gkr_round"));
+        if (j == s) GKR_TRY(start_poly(s));           // right behind the kernel that produced T_s: prepares message s+1
         const HostSlot *slot;
-        GKR_TRY(ctx->wait_slot(s1, &slot));
-        GKR_TRY(consume_round(ctx, t, io, 0, full1, slot, st, last_hash));
+        GKR_TRY(ctx->wait_slot(sq, &slot));
+        GKR_TRY(consume_round(ctx, t, io, j - 1, full, slot, st, last_hash));
     }
-    for (uint32_t j = 2; j <= k; ++j) {
+    // look-ahead rounds s+1 .. k
+    for (uint32_t j = s + 1; j <= k; ++j) {
         const HFr r_prev = st.r;                       // r_{j-1}
         if (j + 1 <= k) GKR_TRY(start_poly(j));        // device: fold with r_{j-1}, prepare message j+1
         const HostSlot *slot;
-        GKR_TRY(ctx->wait_slot(plan[j - 1].seq, &slot));
+        GKR_TRY(ctx->wait_slot(P[j - 1].seq, &slot));
         if (slot->aux[2] == 0xDEADu) {
             set_last_error("pre-launched look-ahead kernel %u gave up waiting for its challenge", j - 1);
             return GKR_ERR_INTERNAL;
@@ -1046,16 +1052,17 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         const HFr x2 = hfr_add(E0, hfr_mul(r_prev, hfr_add(hfr_sub(hfr_sub(E1, E0), E2), hfr_mul(E2, r_prev))));
         GKR_TRY(consume_values(ctx, t, io, j - 1, false, x0, x2, hfr_zero(), st, last_hash));
     }
-    // the W table of the last round (2 entries): fold T_{k-1}.W (4 entries) with r_{k-1}
-    if (k >= 2) {
+    // the W table of the last round (T_k, 2 entries)
+    if (s <= k - 1 && k >= 2) {
+        // T_k was never materialised by the look-ahead kernels: fold T_{k-1}.W (4 entries) with r_{k-1}
         Fr *w2 = ctx->misc.as<Fr>() + 16;
         ctx->begin_launch();
-        launch_fold(Wk1, w2, make_const_mul(io.challenges[k - 2]), 2, ctx->stream);
+        launch_fold(T[k - 1].W, w2, make_const_mul(io.challenges[k - 2]), 2, ctx->stream);
         ctx->end_launch(KC_OTHER, 192.0);
         GKR_TRY(ctx->check_launch("fold"));
         io.W_last = w2;
     } else {
-        io.W_last = io.W;
+        io.W_last = T[k].W;       // produced by the last direct round (or the inputs when k == 1)
     }
     if (claim_out) *claim_out = st.claim;
     return GKR_OK;
