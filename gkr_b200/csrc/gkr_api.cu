@@ -155,7 +155,51 @@ void gkr_ctx::pool_put(void *p, size_t /*requested*/) {
     dev_pool.emplace(it != block_size.end() ? it->second : 0, p);     // filed under its true size
 }
 
+// GKR_TRACE=1: per-site host time of gkr_prove, printed to stderr after every proof (development aid)
+namespace {
+enum TraceSite { TS_WAIT_DIRECT = 0, TS_WAIT_AHEAD, TS_WAIT_SHAPE, TS_WAIT_OTHER, TS_SETUP_LAUNCH, TS_LINE_LAUNCH, TS_AUX_SYNC,
+                 TS_START_POLY, TS_CONSUME, TS_DIRECT_LAUNCH, TS_N };
+const char *const kTraceNames[TS_N] = {"wait_direct", "wait_lookahead", "wait_shape", "wait_other", "setup_launch", "line_launch",
+                                       "aux_sync", "start_poly", "consume(hash)", "direct_launch"};
+const bool g_trace = getenv("GKR_TRACE") != nullptr;
+thread_local int g_wait_site = TS_WAIT_OTHER;
+thread_local double g_trace_t[TS_N];
+thread_local uint64_t g_trace_n[TS_N];
+thread_local uint64_t g_dev_idle_ns, g_dev_busy_ns, g_dev_gap_ns, g_dev_n, g_dev_gap_n;
+thread_local double g_wait_by_log2[40];
+struct TraceScope {
+    int site;
+    double t0;
+    explicit TraceScope(int s) : site(s), t0(g_trace ? now_seconds() : 0.0) {}
+    ~TraceScope() {
+        if (g_trace) {
+            g_trace_t[site] += now_seconds() - t0;
+            g_trace_n[site]++;
+        }
+    }
+};
+void trace_report() {
+    if (!g_trace) return;
+    fprintf(stderr, "[gkr trace]");
+    for (int i = 0; i < TS_N; ++i) {
+        fprintf(stderr, " %s=%.3fms/%llu", kTraceNames[i], g_trace_t[i] * 1e3, (unsigned long long)g_trace_n[i]);
+        g_trace_t[i] = 0;
+        g_trace_n[i] = 0;
+    }
+    fprintf(stderr, " | tail levels: n=%llu idle(wait cmd)=%.2fus busy=%.2fus fence.sys=%.2fus\n",
+            (unsigned long long)g_dev_n, g_dev_n ? g_dev_idle_ns * 1e-3 / g_dev_n : 0.0, g_dev_n ? g_dev_busy_ns * 1e-3 / g_dev_n : 0.0,
+            g_dev_gap_n ? g_dev_gap_ns * 1e-3 / g_dev_gap_n : 0.0);
+    g_dev_idle_ns = g_dev_busy_ns = g_dev_gap_ns = g_dev_n = g_dev_gap_n = 0;
+    fprintf(stderr, "[gkr trace] look-ahead wait by log2(table entries) in us per round:");
+    for (int i = 0; i < 40; ++i)
+        if (g_wait_by_log2[i] > 0) fprintf(stderr, " %d:%.1f", i, g_wait_by_log2[i] * 1e6 / 32);
+    fprintf(stderr, "\n");
+    for (double &v : g_wait_by_log2) v = 0;
+}
+}  // namespace
+
 int gkr_ctx::wait_slot(uint32_t s, const HostSlot **out) {
+    TraceScope trace_scope(g_wait_site);
     const double t0 = now_seconds();
     volatile HostSlot *slot = slots_host + (s % kSlots);
     uint64_t spins = 0;
@@ -924,6 +968,14 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
     return GKR_OK;
 }
 
+// tuning knob for experiments: GKR_LOOKAHEAD_LOG2 overrides kLookaheadEntries
+static uint64_t lookahead_entries() {
+    static const uint64_t v = [] {
+        const char *e = getenv("GKR_LOOKAHEAD_LOG2");
+        return e ? (uint64_t)1 << atoi(e) : kLookaheadEntries;
+    }();
+    return v;
+}
 // Phase with look-ahead rounds (default).  While the tables are large the device is the bottleneck and rounds run
 // as in run_phase (fused fold + direct message).  From level s on (tables of at most kLookaheadEntries entries) the
 // device stays one round ahead: kernel P_j folds T_{j-1} with r_{j-1} into T_j and publishes the six sums that give
@@ -952,7 +1004,7 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
     // s = first level small enough for look-ahead rounds (and with at least 4 entries); k + 1 if there is none
     uint32_t s = k + 1;
     for (uint32_t j = 1; j + 1 <= k; ++j)
-        if (T[j].n <= kLookaheadEntries) { s = j; break; }
+        if (T[j].n <= lookahead_entries()) { s = j; break; }
     struct Poly {                 // P_j, j = s..k-1
         uint32_t seq = 0;
         bool launched = false, commanded = false;
@@ -975,6 +1027,15 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
     const bool can_prelaunch = ctx->prelaunch && !ctx->profiling;
     RoundState st{claim_in ? *claim_in : hfr_zero(), hfr_zero(), claim_in != nullptr};
 
+    auto tail_args = [&](uint32_t u0, uint32_t n_levels, uint32_t seq0) {
+        PolyTailArgs a{};
+        a.H0 = T[u0 - 1].H; a.W0 = T[u0 - 1].W; a.A0 = T[u0 - 1].A;
+        a.buf_even = ctx->foldA.as<Fr>(); a.buf_odd = ctx->foldB.as<Fr>();
+        a.N = N; a.u0 = u0; a.n_levels = n_levels;
+        a.cmds = ctx->cmds_dev; a.slots = ctx->slots_dev; a.n_slots = gkr_ctx::kSlots; a.seq0 = seq0;
+        a.trace = g_trace ? 1u : 0u;
+        return a;
+    };
     auto start_poly = [&](uint32_t j) -> int {      // j == s: reads T_s; j > s: folds T_{j-1} with r_{j-1} = st.r into T_j
         Poly &p = P[j];
         const bool fold = j > s;
@@ -990,8 +1051,14 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         p.seq = ctx->next_seq();
         const FrConstMul rc = fold ? make_const_mul(st.r) : FrConstMul{};
         ctx->begin_launch();
-        launch_gkr_poly(fold, in.H, in.W, in.A, const_cast<Fr *>(T[j].H), const_cast<Fr *>(T[j].W), const_cast<Fr *>(T[j].A), rc,
-                        quads, ctx->ws, ctx->slot_dev(p.seq), p.seq, ctx->stream);
+        if (fold && quads <= (uint64_t)gkr_poly_tail_max_quads()) {
+            // the tail kernel always reads its challenge from a command block: fill it first, then launch
+            write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), &rc, p.seq);
+            launch_gkr_poly_tail(tail_args(j, 1, p.seq), ctx->stream);
+        } else {
+            launch_gkr_poly(fold, in.H, in.W, in.A, const_cast<Fr *>(T[j].H), const_cast<Fr *>(T[j].W), const_cast<Fr *>(T[j].A), rc,
+                            quads, ctx->ws, ctx->slot_dev(p.seq), p.seq, ctx->stream);
+        }
         ctx->end_launch(quads * 2 >= kTailPairs ? (fold ? KC_ROUND_FUSED : KC_ROUND) : KC_ROUND_TAIL,
                         fold ? 144.0 * in.n : 80.0 * in.n);
         GKR_TRY(ctx->check_launch("gkr_poly"));
@@ -999,12 +1066,28 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         // the small-table kernels that follow are enqueued now and wait for their challenges on the device
         if (can_prelaunch && j + 1 <= k - 1 && !P[j + 1].launched && T[j + 1].n / 2 < kPrelaunchPairs) {
             for (uint32_t u = j + 1; u + 1 <= k; ++u) {
+                if (T[u].n / 4 <= (uint64_t)gkr_poly_tail_max_quads()) {
+                    // every remaining level in ONE single-CTA kernel (consecutive sequence numbers)
+                    const uint32_t n_levels = k - u;
+                    uint32_t seq0 = 0;
+                    for (uint32_t v = u; v + 1 <= k; ++v) {
+                        P[v].seq = ctx->next_seq();
+                        if (v == u) seq0 = P[v].seq;
+                        write_cmd(ctx->cmds_host + (P[v].seq % gkr_ctx::kSlots), nullptr, 0u);
+                        P[v].launched = true;
+                        ctx->prelaunched_pending++;
+                    }
+                    launch_gkr_poly_tail(tail_args(u, n_levels, seq0), ctx->stream);
+                    ctx->stats.kernel_launches += 1;
+                    GKR_TRY(ctx->check_launch("gkr_poly_tail"));
+                    break;
+                }
                 Poly &f = P[u];
                 f.seq = ctx->next_seq();
                 write_cmd(ctx->cmds_host + (f.seq % gkr_ctx::kSlots), nullptr, 0u);
                 launch_gkr_poly(true, T[u - 1].H, T[u - 1].W, T[u - 1].A, const_cast<Fr *>(T[u].H), const_cast<Fr *>(T[u].W),
-                                const_cast<Fr *>(T[u].A), FrConstMul{}, T[u].n / 4, ctx->ws, ctx->slot_dev(f.seq), f.seq, ctx->stream,
-                                ctx->cmds_dev + (f.seq % gkr_ctx::kSlots));
+                                const_cast<Fr *>(T[u].A), FrConstMul{}, T[u].n / 4, ctx->ws, ctx->slot_dev(f.seq), f.seq,
+                                ctx->stream, ctx->cmds_dev + (f.seq % gkr_ctx::kSlots));
                 ctx->stats.kernel_launches += 1;
                 GKR_TRY(ctx->check_launch("gkr_poly_cmd"));
                 f.launched = true;
@@ -1019,6 +1102,7 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
     for (uint32_t j = 1; j <= last_direct; ++j) {
         const uint32_t sq = ctx->next_seq();
         const bool full = !st.have_claim;
+        const double t_launch0 = g_trace ? now_seconds() : 0.0;
         ctx->begin_launch();
         if (j == 1) {
             launch_gkr_round(false, full, T[1].H, T[1].W, T[1].A, nullptr, nullptr, nullptr, FrConstMul{}, N / 2, ctx->ws,
@@ -1030,20 +1114,49 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
             ctx->end_launch(T[j].n / 2 >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 144.0 * T[j - 1].n);
         }
         GKR_TRY(ctx->check_launch("gkr_round"));
+        if (g_trace) { g_trace_t[TS_DIRECT_LAUNCH] += now_seconds() - t_launch0; g_trace_n[TS_DIRECT_LAUNCH]++; }
         if (j == s) GKR_TRY(start_poly(s));           // right behind the kernel that produced T_s: prepares message s+1
         const HostSlot *slot;
+        g_wait_site = TS_WAIT_DIRECT;
         GKR_TRY(ctx->wait_slot(sq, &slot));
+        g_wait_site = TS_WAIT_OTHER;
+        TraceScope ts_consume(TS_CONSUME);
         GKR_TRY(consume_round(ctx, t, io, j - 1, full, slot, st, last_hash));
     }
     // look-ahead rounds s+1 .. k
     for (uint32_t j = s + 1; j <= k; ++j) {
         const HFr r_prev = st.r;                       // r_{j-1}
-        if (j + 1 <= k) GKR_TRY(start_poly(j));        // device: fold with r_{j-1}, prepare message j+1
+        if (j + 1 <= k) {                              // device: fold with r_{j-1}, prepare message j+1
+            TraceScope ts_start(TS_START_POLY);
+            GKR_TRY(start_poly(j));
+        }
         const HostSlot *slot;
+        g_wait_site = TS_WAIT_AHEAD;
+        const double t_w0 = g_trace ? now_seconds() : 0.0;
         GKR_TRY(ctx->wait_slot(P[j - 1].seq, &slot));
+        g_wait_site = TS_WAIT_OTHER;
+        if (g_trace) {
+            int lg = 0;
+            while (((uint64_t)1 << lg) < T[j - 1].n) ++lg;
+            g_wait_by_log2[lg] += now_seconds() - t_w0;
+        }
+        TraceScope ts_consume(TS_CONSUME);
         if (slot->aux[2] == 0xDEADu) {
             set_last_error("pre-launched look-ahead kernel %u gave up waiting for its challenge", j - 1);
             return GKR_ERR_INTERNAL;
+        }
+        if (g_trace && T[j - 1].n / 4 <= (uint64_t)gkr_poly_tail_max_quads() && j - 1 > s) {
+            auto u64 = [&](int i) { return (uint64_t)slot->aux[i] | ((uint64_t)slot->aux[i + 1] << 32); };
+            static thread_local uint64_t prev_pub = 0;
+            const uint64_t te = u64(4), tc = u64(6), tp = u64(8);
+            if (tp > te && te) {
+                g_dev_idle_ns += tc - te;
+                g_dev_busy_ns += tp - tc;
+                const uint64_t td = u64(10);       // previous level: fence finished
+                if (prev_pub && td > prev_pub && td - prev_pub < 1000000) { g_dev_gap_ns += td - prev_pub; g_dev_gap_n++; }
+                g_dev_n++;
+            }
+            prev_pub = tp;
         }
         const HFr Q0 = to_host(slot->v[0]), Q1 = to_host(slot->v[1]), Q2 = to_host(slot->v[2]);
         const HFr E0 = to_host(slot->v[3]), E1 = to_host(slot->v[4]), E2 = to_host(slot->v[5]);
@@ -1174,6 +1287,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         Fr *wu = ctx->misc.as<Fr>();
 
         // static shape of W_{i+1}: non-zero top coefficient => depends on every variable, degree k
+        const double t_setup0 = g_trace ? now_seconds() : 0.0;
         const uint32_t s_alt = ctx->next_seq();
         ctx->begin_launch();
         launch_alt_sum(W, N, ctx->ws, ctx->slot_dev(s_alt), s_alt, ctx->stream);
@@ -1198,11 +1312,14 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
                              ctx->wQ.as<Fr>(), H, A, Nrows, ctx->stream);
         ctx->end_launch(KC_WIRING, 76.0 * L.n_edges1 + 64.0 * Nrows, 2);
         GKR_TRY(ctx->check_launch("wiring_phase1"));
+        if (g_trace) { g_trace_t[TS_SETUP_LAUNCH] += now_seconds() - t_setup0; g_trace_n[TS_SETUP_LAUNCH]++; }
 
         uint32_t dep_mask = (uint32_t)(N - 1), max_deg = k;
         {
             const HostSlot *slot;
+            g_wait_site = TS_WAIT_SHAPE;
             GKR_TRY(ctx->wait_slot(s_alt, &slot));
+            g_wait_site = TS_WAIT_OTHER;
             if (slot->aux[1] == 0) {
                 // degenerate W: exact shape from the full Moebius transform
                 GKR_CUDA_TRY(cudaMemcpyAsync(ctx->mob.ptr, W, N * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1226,6 +1343,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
                 : lookahead ? run_phase_poly(ctx, t, io, &last_hash, nullptr, &claim)
                             : run_phase(ctx, t, io, &last_hash, nullptr, &claim));
         // W(u): fold the last size-2 W table with r_k
+        const double t_setup1 = g_trace ? now_seconds() : 0.0;
         ctx->begin_launch();
         launch_fold(io.W_last, wu, make_const_mul(rs[k - 1]), 1, ctx->stream);
         ctx->end_launch(KC_OTHER, 96.0);
@@ -1238,6 +1356,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
                              ctx->wP.as<Fr>(), H, A, Nrows, ctx->stream);
         ctx->end_launch(KC_WIRING, 76.0 * L.n_edges2 + 64.0 * Nrows, 2);
         GKR_TRY(ctx->check_launch("wiring_phase2"));
+        if (g_trace) { g_trace_t[TS_SETUP_LAUNCH] += now_seconds() - t_setup1; g_trace_n[TS_SETUP_LAUNCH]++; }
         io.challenges = rs.data() + k;
         io.msgs = &P->msgs[3 * (ro + k)]; io.msg_len = &P->msg_len[ro + k]; io.chal_out = &P->chal[ro + k];
         GKR_TRY(L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, &claim, &claim)
@@ -1247,6 +1366,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         // ---- q_i = W restricted to the line b* -> c* (poly.rs:469-500): needs only b*, c* => runs on the
         //      low-priority stream while the next layer's rounds proceed; collected after the last layer ----
         {
+            TraceScope ts_line(TS_LINE_LAUNCH);
             const Fr *cur = W;
             uint64_t cnt = N;
             for (uint32_t j = 0; j < k; ++j) {
@@ -1277,7 +1397,10 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         z.swap(znext);
     }
     // collect the q_i (ascending on the staging buffer -> descending, truncated to the static length)
-    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->aux));
+    {
+        TraceScope ts_aux(TS_AUX_SYNC);
+        GKR_CUDA_TRY(cudaStreamSynchronize(ctx->aux));
+    }
     for (uint32_t li = 0; li < n_layers; ++li) {
         const uint32_t k = c->k[li + 1], len = P->q_len[li];
         const gkr_fr *asc = P->q_stage + P->q_off[li];
@@ -1294,6 +1417,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
     // z_0 entries are zero already
     P->finish();
     *out = &P.release()->pub;
+    trace_report();
     return GKR_OK;
 }
 

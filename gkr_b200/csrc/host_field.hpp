@@ -43,14 +43,24 @@ inline bool hfr_is_zero(const HFr &a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3
 inline bool hfr_eq(const HFr &a, const HFr &b) { return std::memcmp(a.l, b.l, 32) == 0; }
 
 inline HFr hfr_add(const HFr &a, const HFr &b) {
-    HFr r;
+    // branch-free: for transcript data the comparison is a coin flip, and a mispredicted branch flushes the
+    // multiplier chain in flight behind it
+    uint64_t s[4], d[4];
     uint64_t carry = 0;
     for (int i = 0; i < 4; ++i) {
-        hf::u128 s = (hf::u128)a.l[i] + b.l[i] + carry;
-        r.l[i] = (uint64_t)s;
-        carry = (uint64_t)(s >> 64);
+        hf::u128 t = (hf::u128)a.l[i] + b.l[i] + carry;
+        s[i] = (uint64_t)t;
+        carry = (uint64_t)(t >> 64);
     }
-    if (hf::geq_p(r.l)) hf::sub_p(r.l);
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+        hf::u128 t = (hf::u128)s[i] - hf::P[i] - borrow;
+        d[i] = (uint64_t)t;
+        borrow = (uint64_t)(t >> 64) & 1;
+    }
+    const uint64_t keep = (uint64_t)0 - borrow;      // all ones when s < p
+    HFr r;
+    for (int i = 0; i < 4; ++i) r.l[i] = (s[i] & keep) | (d[i] & ~keep);
     return r;
 }
 inline HFr hfr_sub(const HFr &a, const HFr &b) {
@@ -103,6 +113,7 @@ inline HFr hfr_mul(const HFr &a, const HFr &b) {
     return r;
 }
 inline HFr hfr_sqr(const HFr &a) { return hfr_mul(a, a); }
+
 
 // canonical 32-byte little-endian value <-> Montgomery.  from_canonical returns false if value >= p.
 inline bool hfr_from_canonical(HFr *out, const void *bytes32) {

@@ -137,12 +137,11 @@ __device__ __forceinline__ void block_sum(Fr (&acc)[K], Fr (*smem)[kWarps]) {
 // Grid-wide sum of K accumulators; the last CTA to arrive publishes the canonical totals.
 // If dev_out != nullptr (multi-GPU: the totals still have to be combined across ranks) the last CTA
 // stores the Montgomery totals there and nothing is published to the host.
+// second half of grid_sum_publish: thread 0 of every CTA holds the CTA totals in acc
 template <int K>
-__device__ __forceinline__ void grid_sum_publish(Fr (&acc)[K], Fr *partials, unsigned int *counter,
-                                                 HostSlot *slot, uint32_t seq, uint32_t aux0, Fr *dev_out = nullptr) {
-    __shared__ Fr red[K][kWarps];
+__device__ __forceinline__ void grid_publish_cta_totals(Fr (&acc)[K], Fr (*red)[kWarps], Fr *partials, unsigned int *counter,
+                                                        HostSlot *slot, uint32_t seq, uint32_t aux0, Fr *dev_out = nullptr) {
     __shared__ bool is_last;
-    block_sum<K>(acc, red);
     if (gridDim.x > 1) {
         if (threadIdx.x == 0) {
 #pragma unroll
@@ -183,6 +182,13 @@ __device__ __forceinline__ void grid_sum_publish(Fr (&acc)[K], Fr *partials, uns
         __threadfence_system();
         slot->seq = seq;
     }
+}
+template <int K>
+__device__ __forceinline__ void grid_sum_publish(Fr (&acc)[K], Fr *partials, unsigned int *counter,
+                                                 HostSlot *slot, uint32_t seq, uint32_t aux0, Fr *dev_out = nullptr) {
+    __shared__ Fr red[K][kWarps];
+    block_sum<K>(acc, red);
+    grid_publish_cta_totals<K>(acc, red, partials, counter, slot, seq, aux0, dev_out);
 }
 
 static inline int grid_for(uint64_t work_items, int max_blocks) {
@@ -495,63 +501,82 @@ __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const
 // FOLD: inputs have 8*q4 entries and are first folded with r into the 4*q4-entry outputs (one pass).
 // Published: v[0..5] = Q0, Q1, Q2, E0, E1, E2.
 // ------------------------------------------------------------------------------------------------
+// Work split: a CTA handles chunks of 64 quads with four threads per quad -- thread (s, il), s = t / 64 warp-uniform,
+// folds quarter s of the three tables (coalesced: a warp touches 32 consecutive entries) and leaves it in shared
+// memory; then the warps of class s compute their share of the six products (s=0: Q0,E0; 1: Q1,E1; 2: Q2; 3: E2).
+// Per-thread chains are 4x shorter than one-thread-per-quad, which is what the latency-bound small tables need.
+constexpr int kPolyChunk = 64;
 template <bool FOLD, class KT>
 __device__ __forceinline__ void gkr_poly_body(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
                                               const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                               Fr *__restrict__ Wout, Fr *__restrict__ Aout, const KT &r,
                                               uint64_t q4, Fr *partials, unsigned int *counter, HostSlot *slot,
                                               uint32_t seq) {
+    __shared__ Fr sh[3][4][kPolyChunk];
+    __shared__ Fr red[6][kWarps];
+    __shared__ Fr wred[kWarps][2];
+    const uint32_t t = threadIdx.x, s = t / kPolyChunk, il = t % kPolyChunk;
+    Fr accA = fr_zero(), accB = fr_zero();
+    const uint64_t n_chunks = (q4 + kPolyChunk - 1) / kPolyChunk;
+    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const uint64_t i = c * kPolyChunk + il;
+        const bool active = i < q4;
+        if (active) {
+            const uint64_t e = i + s * q4;
+            Fr h, w, a;
+            if (FOLD) {
+                h = fold2(ld_fr(Hin + e), ld_fr(Hin + e + 4 * q4), r);
+                w = fold2(ld_fr(Win + e), ld_fr(Win + e + 4 * q4), r);
+                a = fold2(ld_fr(Ain + e), ld_fr(Ain + e + 4 * q4), r);
+                st_fr(Hout + e, h);
+                st_fr(Wout + e, w);
+                st_fr(Aout + e, a);
+            } else {
+                h = ld_fr(Hin + e);
+                w = ld_fr(Win + e);
+                a = (s & 1) ? fr_zero() : ld_fr(Ain + e);      // A only enters through quarters 0 and 2
+            }
+            sh[0][s][il] = h;
+            sh[1][s][il] = w;
+            sh[2][s][il] = a;
+        }
+        __syncthreads();
+        if (active) {
+            auto H = [&](int q) { return sh[0][q][il]; };
+            auto W = [&](int q) { return sh[1][q][il]; };
+            if (s == 0) {
+                accA = fr_add(accA, fr_add(fr_mul(H(0), W(0)), sh[2][0][il]));
+                accB = fr_add(accB, fr_mul(fr_sub(H(1), H(0)), fr_sub(W(1), W(0))));
+            } else if (s == 1) {
+                accA = fr_add(accA, fr_add(fr_mul(H(2), W(2)), sh[2][2][il]));
+                accB = fr_add(accB, fr_mul(fr_sub(H(3), H(2)), fr_sub(W(3), W(2))));
+            } else if (s == 2) {
+                accA = fr_add(accA, fr_mul(fr_sub(H(2), H(0)), fr_sub(W(2), W(0))));
+            } else {
+                accA = fr_add(accA, fr_mul(fr_sub(fr_sub(H(3), H(2)), fr_sub(H(1), H(0))),
+                                           fr_sub(fr_sub(W(3), W(2)), fr_sub(W(1), W(0)))));
+            }
+        }
+        __syncthreads();
+    }
+    const Fr wa = warp_sum(accA), wb = warp_sum(accB);
+    const int lane = t & 31, warp = t >> 5;
+    if (lane == 0) { wred[warp][0] = wa; wred[warp][1] = wb; }
+    __syncthreads();
     Fr acc[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) acc[j] = fr_zero();
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < q4; i += (uint64_t)gridDim.x * blockDim.x) {
-        Fr w[4], h[4];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            if (FOLD) {
-                w[s] = fold2(ld_fr(Win + i + s * q4), ld_fr(Win + i + (s + 4) * q4), r);
-                st_fr(Wout + i + s * q4, w[s]);
-            } else {
-                w[s] = ld_fr(Win + i + s * q4);
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            if (FOLD) {
-                h[s] = fold2(ld_fr(Hin + i + s * q4), ld_fr(Hin + i + (s + 4) * q4), r);
-                st_fr(Hout + i + s * q4, h[s]);
-            } else {
-                h[s] = ld_fr(Hin + i + s * q4);
-            }
-        }
-        acc[0] = fr_add(acc[0], fr_mul(h[0], w[0]));
-        acc[1] = fr_add(acc[1], fr_mul(h[2], w[2]));
-        acc[2] = fr_add(acc[2], fr_mul(fr_sub(h[2], h[0]), fr_sub(w[2], w[0])));
-        const Fr uh = fr_sub(h[1], h[0]), uw = fr_sub(w[1], w[0]);
-        const Fr th = fr_sub(h[3], h[2]), tw = fr_sub(w[3], w[2]);
-        acc[3] = fr_add(acc[3], fr_mul(uh, uw));
-        acc[4] = fr_add(acc[4], fr_mul(th, tw));
-        acc[5] = fr_add(acc[5], fr_mul(fr_sub(th, uh), fr_sub(tw, uw)));
-        // A only enters through its quarter sums
-        Fr a0, a2;
-        if (FOLD) {
-            a0 = fold2(ld_fr(Ain + i), ld_fr(Ain + i + 4 * q4), r);
-            const Fr a1 = fold2(ld_fr(Ain + i + q4), ld_fr(Ain + i + 5 * q4), r);
-            a2 = fold2(ld_fr(Ain + i + 2 * q4), ld_fr(Ain + i + 6 * q4), r);
-            const Fr a3 = fold2(ld_fr(Ain + i + 3 * q4), ld_fr(Ain + i + 7 * q4), r);
-            st_fr(Aout + i, a0);
-            st_fr(Aout + i + q4, a1);
-            st_fr(Aout + i + 2 * q4, a2);
-            st_fr(Aout + i + 3 * q4, a3);
-        } else {
-            a0 = ld_fr(Ain + i);
-            a2 = ld_fr(Ain + i + 2 * q4);
-        }
-        acc[0] = fr_add(acc[0], a0);
-        acc[1] = fr_add(acc[1], a2);
+    if (t == 0) {                                        // warps 2s, 2s+1 belong to class s
+        acc[0] = fr_add(wred[0][0], wred[1][0]);
+        acc[3] = fr_add(wred[0][1], wred[1][1]);
+        acc[1] = fr_add(wred[2][0], wred[3][0]);
+        acc[4] = fr_add(wred[2][1], wred[3][1]);
+        acc[2] = fr_add(wred[4][0], wred[5][0]);
+        acc[5] = fr_add(wred[6][0], wred[7][0]);
     }
-    grid_sum_publish<6>(acc, partials, counter, slot, seq, 0u);
+    grid_publish_cta_totals<6>(acc, red, partials, counter, slot, seq, 0u);
 }
+static_assert(kThreads == 4 * kPolyChunk, "gkr_poly_body maps four threads to each quad of a chunk");
 template <bool FOLD>
 __global__ void __launch_bounds__(kThreads, 2) k_gkr_poly(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
                                                           const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
@@ -578,9 +603,143 @@ __global__ void __launch_bounds__(kThreads, 2) k_gkr_poly_cmd(const Fr *__restri
     CmdConst r{raw};
     gkr_poly_body<true>(Hin, Win, Ain, Hout, Wout, Aout, r, q4, partials, counter, slot, seq);
 }
+// Tail of a phase with look-ahead rounds, tables of at most 1024 entries (quads <= 256): ONE CTA runs `n_levels`
+// consecutive rounds, waiting for each challenge in its command block.  Four threads per quad (thread 4i+s folds
+// quarter s of the three tables); the folded tables stay in shared memory for the next level (and are also written
+// to global memory for the caller); each thread then computes at most two of the six products, and the sums are
+// reduced with shuffles that keep the four s-classes apart.  A round takes ~5 us after its challenge arrives, and a
+// whole tail costs the host one launch.
+constexpr int kTailQuads = 128;
+template <int THREADS>       // register budget follows the block size: 255 / 128 / 64 per thread
+__global__ void __launch_bounds__(THREADS, 1) k_gkr_poly_tail_cmd(PolyTailArgs a) {
+    extern __shared__ uint4 tail_smem[];
+    __shared__ uint32_t raw[80];
+    __shared__ int ok;
+    __shared__ Fr red[32][4][2];
+    const uint32_t n_first = (uint32_t)(a.N >> (a.u0 - 1));
+    Fr *X = reinterpret_cast<Fr *>(tail_smem);          // tables of levels u0, u0+2, ..: 3 * n_first entries
+    Fr *Y = X + 3 * (size_t)n_first;                    // tables of levels u0+1, u0+3, ..: 3 * n_first / 2 entries
+    const uint32_t t = threadIdx.x, i = t >> 2, sq = t & 3;
+    const int lane = t & 31, warp = t >> 5, nw = blockDim.x >> 5;
+    unsigned long long t_prev_done = 0;
+    for (uint32_t lv = 0; lv < a.n_levels; ++lv) {
+        const uint32_t u = a.u0 + lv, n = (uint32_t)(a.N >> (u - 1)), q4 = n / 4;
+        const uint32_t seq = a.seq0 + lv;
+        HostSlot *slot = a.slots + (seq % a.n_slots);
+        unsigned long long t_enter = 0, t_cmd = 0;
+        if (a.trace && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_enter));
+        if (!wait_cmd(a.cmds + (seq % a.n_slots), seq, raw, &ok)) {
+            if (t == 0) {
+                slot->aux[2] = 0xDEADu;
+                __threadfence_system();
+                slot->seq = seq;
+            }
+            return;
+        }
+        if (a.trace && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_cmd));
+        const CmdConst r{raw};
+        Fr *out_s = (lv & 1) ? Y : X;
+        const Fr *in_s = (lv & 1) ? X : Y;
+        Fr *gout = (u & 1) ? a.buf_odd : a.buf_even;
+        const bool active = i < q4;
+        if (active) {
+            const uint32_t e = i + sq * q4;             // entry of T_u; folds entries e and e + n of T_{u-1}
+            Fr h, w, av;
+            if (lv == 0) {
+                h = fold2(ld_fr(a.H0 + e), ld_fr(a.H0 + e + n), r);
+                w = fold2(ld_fr(a.W0 + e), ld_fr(a.W0 + e + n), r);
+                av = fold2(ld_fr(a.A0 + e), ld_fr(a.A0 + e + n), r);
+            } else {
+                h = fold2(in_s[e], in_s[e + n], r);
+                w = fold2(in_s[2 * n + e], in_s[2 * n + e + n], r);
+                av = fold2(in_s[4 * n + e], in_s[4 * n + e + n], r);
+            }
+            st_fr(gout + e, h);
+            st_fr(gout + n + e, w);
+            st_fr(gout + 2 * n + e, av);
+            out_s[e] = h;
+            out_s[n + e] = w;
+            out_s[2 * n + e] = av;
+        }
+        __syncthreads();
+        Fr A = fr_zero(), B = fr_zero();
+        if (active) {
+            auto H = [&](int q) { return out_s[q * q4 + i]; };
+            auto W = [&](int q) { return out_s[n + q * q4 + i]; };
+            if (sq == 0) {                                   // Q0, E0
+                A = fr_add(fr_mul(H(0), W(0)), out_s[2 * n + i]);
+                B = fr_mul(fr_sub(H(1), H(0)), fr_sub(W(1), W(0)));
+            } else if (sq == 1) {                            // Q1, E1
+                A = fr_add(fr_mul(H(2), W(2)), out_s[2 * n + 2 * q4 + i]);
+                B = fr_mul(fr_sub(H(3), H(2)), fr_sub(W(3), W(2)));
+            } else if (sq == 2) {                            // Q2
+                A = fr_mul(fr_sub(H(2), H(0)), fr_sub(W(2), W(0)));
+            } else {                                         // E2
+                A = fr_mul(fr_sub(fr_sub(H(3), H(2)), fr_sub(H(1), H(0))), fr_sub(fr_sub(W(3), W(2)), fr_sub(W(1), W(0))));
+            }
+        }
+        // lanes with equal (lane & 3) belong to the same class: reduce with offsets 16, 8, 4 only
+#pragma unroll
+        for (int off = 16; off >= 4; off >>= 1) {
+            Fr oa, ob;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                oa.l[l] = __shfl_xor_sync(0xffffffffu, A.l[l], off);
+                ob.l[l] = __shfl_xor_sync(0xffffffffu, B.l[l], off);
+            }
+            A = fr_add(A, oa);
+            B = fr_add(B, ob);
+        }
+        if (lane < 4) { red[warp][lane][0] = A; red[warp][lane][1] = B; }
+        __syncthreads();
+        if (t < 8) {
+            const int cls = t & 3, which = t >> 2;
+            Fr acc = fr_zero();
+            for (int wv = 0; wv < nw; ++wv) acc = fr_add(acc, red[wv][cls][which]);
+            // published order: Q0, Q1, Q2, E0, E1, E2
+            const int idx = which == 0 ? (cls == 0 ? 0 : cls == 1 ? 1 : cls == 2 ? 2 : 5) : (cls == 0 ? 3 : cls == 1 ? 4 : -1);
+            if (idx >= 0) st_fr(&slot->v[idx], acc);
+        }
+        __syncthreads();
+        if (t == 0) {
+            slot->aux[1] = 0;
+            slot->aux[2] = 0;
+            if (a.trace) {                           // device timeline of this level (ns): enter, command seen, publishing
+                unsigned long long t_pub;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_pub));
+                slot->aux[4] = (uint32_t)t_enter; slot->aux[5] = (uint32_t)(t_enter >> 32);
+                slot->aux[6] = (uint32_t)t_cmd; slot->aux[7] = (uint32_t)(t_cmd >> 32);
+                slot->aux[8] = (uint32_t)t_pub; slot->aux[9] = (uint32_t)(t_pub >> 32);
+                slot->aux[10] = (uint32_t)t_prev_done; slot->aux[11] = (uint32_t)(t_prev_done >> 32);
+            }
+            __threadfence_system();
+            slot->seq = seq;
+            if (a.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_prev_done));
+        }
+        // (the barrier above also protects raw / red / the level tables against the next level's writers)
+    }
+}
+void launch_gkr_poly_tail(const PolyTailArgs &a, cudaStream_t s) {
+    static bool once = false;
+    const size_t max_smem = (size_t)(4 * kTailQuads) * 144;
+    if (!once) {
+        cudaFuncSetAttribute(k_gkr_poly_tail_cmd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+        cudaFuncSetAttribute(k_gkr_poly_tail_cmd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+        once = true;
+    }
+    const uint64_t n_first = a.N >> (a.u0 - 1);
+    const unsigned threads = (unsigned)((n_first + 31) / 32 * 32);           // 4 threads per quad = 1 per entry
+    const size_t smem = (size_t)n_first * 144;                              // (3 n + 3 n / 2) * 32 B
+    if (threads <= 256)
+        k_gkr_poly_tail_cmd<256><<<1, threads, smem, s>>>(a);
+    else
+        k_gkr_poly_tail_cmd<512><<<1, threads, smem, s>>>(a);
+}
+int gkr_poly_tail_max_quads() { return kTailQuads; }
+
 void launch_gkr_poly(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
                      uint64_t quads, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s, const HostCmd *cmd) {
-    const int grid = grid_for(quads, ws.max_blocks);
+    const int grid = grid_for(4 * quads, ws.max_blocks);      // 64 quads per CTA pass
     if (cmd) k_gkr_poly_cmd<<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, cmd, quads, ws.partials, ws.counter, slot, seq);
     else if (fold) k_gkr_poly<true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
     else k_gkr_poly<false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);

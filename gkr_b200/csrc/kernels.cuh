@@ -78,6 +78,22 @@ void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *
 void launch_gkr_poly(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
                      uint64_t quads, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq, cudaStream_t s,
                      const HostCmd *cmd = nullptr);
+// single-CTA tail of a look-ahead phase: levels u0 .. u0 + n_levels - 1 (T_u has N >> (u-1) entries per table, at most
+// 4 * gkr_poly_tail_max_quads() for u0); level u folds T_{u-1} (the first from H0/W0/A0, later ones from shared memory)
+// with the challenge in command block seq0 + (u - u0), writes T_u to buf_even / buf_odd (by parity of u; tables at
+// offsets 0, n, 2n) and publishes the six look-ahead sums to slot seq0 + (u - u0)
+struct PolyTailArgs {
+    const Fr *H0, *W0, *A0;
+    Fr *buf_even, *buf_odd;
+    uint64_t N;
+    uint32_t u0, n_levels;
+    const HostCmd *cmds;
+    HostSlot *slots;
+    uint32_t n_slots, seq0;
+    uint32_t trace;            // also publish a device timeline of each level (development aid)
+};
+void launch_gkr_poly_tail(const PolyTailArgs &a, cudaStream_t s);
+int gkr_poly_tail_max_quads();
 void launch_take_strided(const Fr *in, Fr *out, uint64_t first, uint64_t stride, uint64_t n, cudaStream_t s);
 // product-of-3 round (degree 3).  Publishes v[0] = g(0), v[1] = g(-1), v[2] = g(inf) (= X^3 coefficient) and
 // v[3] = g(1) when full == true.

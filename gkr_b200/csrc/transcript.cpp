@@ -78,7 +78,6 @@ inline HFr seventh_power(const HFr &t) {
     const HFr t4 = hfr_sqr(t2);
     return hfr_mul(t3, t4);
 }
-
 }  // namespace
 
 void keccak256(const uint8_t *data, size_t len, uint8_t out[32]) {
@@ -107,6 +106,8 @@ void keccak256(const uint8_t *data, size_t len, uint8_t out[32]) {
 
 HFr mimc7_hash(const HFr &x, const HFr &key) {
     std::call_once(g_once, init_constants);
+    // (lazily reduced products -- no conditional subtraction on the chain -- were measured slower on the GPU
+    //  box's Xeon: 22.1 vs 21.3 us per 3-element multi_hash; the chain is bound by the multiplier latency)
     HFr h = seventh_power(hfr_add(x, key));
     for (int i = 1; i < kRounds; ++i) h = seventh_power(hfr_add(hfr_add(h, key), g_constants[i]));
     return hfr_add(h, key);
