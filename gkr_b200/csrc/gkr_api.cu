@@ -719,6 +719,7 @@ struct PhaseIO {
     gkr_fr *chal_out;          // out: [k] canonical
     const Fr *W_last;          // out: device pointer to the size-2 W table of the last round
     uint32_t shard_bits = 0;   // > 0: H, W, A hold this rank's shard (2^(k - shard_bits) rows each)
+    uint32_t first_round_seq = 0;   // != 0: round 1 was already launched (fused with the wiring sums) under this sequence number
 };
 
 // host -> waiting kernel: payload first, then the five line tags (x86 keeps the store order)
@@ -1063,36 +1064,22 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
                         fold ? 144.0 * in.n : 80.0 * in.n);
         GKR_TRY(ctx->check_launch("gkr_poly"));
         p.launched = p.commanded = true;
-        // the small-table kernels that follow are enqueued now and wait for their challenges on the device
-        if (can_prelaunch && j + 1 <= k - 1 && !P[j + 1].launched && T[j + 1].n / 2 < kPrelaunchPairs) {
-            for (uint32_t u = j + 1; u + 1 <= k; ++u) {
-                if (T[u].n / 4 <= (uint64_t)gkr_poly_tail_max_quads()) {
-                    // every remaining level in ONE single-CTA kernel (consecutive sequence numbers)
-                    const uint32_t n_levels = k - u;
-                    uint32_t seq0 = 0;
-                    for (uint32_t v = u; v + 1 <= k; ++v) {
-                        P[v].seq = ctx->next_seq();
-                        if (v == u) seq0 = P[v].seq;
-                        write_cmd(ctx->cmds_host + (P[v].seq % gkr_ctx::kSlots), nullptr, 0u);
-                        P[v].launched = true;
-                        ctx->prelaunched_pending++;
-                    }
-                    launch_gkr_poly_tail(tail_args(u, n_levels, seq0), ctx->stream);
-                    ctx->stats.kernel_launches += 1;
-                    GKR_TRY(ctx->check_launch("gkr_poly_tail"));
-                    break;
-                }
-                Poly &f = P[u];
-                f.seq = ctx->next_seq();
-                write_cmd(ctx->cmds_host + (f.seq % gkr_ctx::kSlots), nullptr, 0u);
-                launch_gkr_poly(true, T[u - 1].H, T[u - 1].W, T[u - 1].A, const_cast<Fr *>(T[u].H), const_cast<Fr *>(T[u].W),
-                                const_cast<Fr *>(T[u].A), FrConstMul{}, T[u].n / 4, ctx->ws, ctx->slot_dev(f.seq), f.seq,
-                                ctx->stream, ctx->cmds_dev + (f.seq % gkr_ctx::kSlots));
-                ctx->stats.kernel_launches += 1;
-                GKR_TRY(ctx->check_launch("gkr_poly_cmd"));
-                f.launched = true;
+        // once the next level fits the single-CTA tail kernel, every remaining level is enqueued now as ONE kernel
+        // that waits for its challenges on the device (consecutive sequence numbers).  Multi-CTA levels are not
+        // pre-launched: many CTAs polling host memory at once were measured to delay the command by 25 us.
+        if (can_prelaunch && j + 1 <= k - 1 && !P[j + 1].launched && T[j + 1].n / 4 <= (uint64_t)gkr_poly_tail_max_quads()) {
+            const uint32_t u = j + 1, n_levels = k - u;
+            uint32_t seq0 = 0;
+            for (uint32_t v = u; v + 1 <= k; ++v) {
+                P[v].seq = ctx->next_seq();
+                if (v == u) seq0 = P[v].seq;
+                write_cmd(ctx->cmds_host + (P[v].seq % gkr_ctx::kSlots), nullptr, 0u);
+                P[v].launched = true;
                 ctx->prelaunched_pending++;
             }
+            launch_gkr_poly_tail(tail_args(u, n_levels, seq0), ctx->stream);
+            ctx->stats.kernel_launches += 1;
+            GKR_TRY(ctx->check_launch("gkr_poly_tail"));
         }
         return GKR_OK;
     };
@@ -1100,11 +1087,14 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
     // direct rounds 1 .. min(s, k): fused fold + message, exactly as in run_phase
     const uint32_t last_direct = s <= k ? s : k;
     for (uint32_t j = 1; j <= last_direct; ++j) {
-        const uint32_t sq = ctx->next_seq();
+        const bool fused_first = j == 1 && io.first_round_seq != 0;
+        const uint32_t sq = fused_first ? io.first_round_seq : ctx->next_seq();
         const bool full = !st.have_claim;
         const double t_launch0 = g_trace ? now_seconds() : 0.0;
         ctx->begin_launch();
-        if (j == 1) {
+        if (fused_first) {
+            // launched by the caller together with the wiring sums (launch_wiring_round1)
+        } else if (j == 1) {
             launch_gkr_round(false, full, T[1].H, T[1].W, T[1].A, nullptr, nullptr, nullptr, FrConstMul{}, N / 2, ctx->ws,
                              ctx->slot_dev(sq), sq, ctx->stream);
             ctx->end_launch(N / 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full ? 96.0 : 80.0) * N);
@@ -1114,7 +1104,7 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
             ctx->end_launch(T[j].n / 2 >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 144.0 * T[j - 1].n);
         }
         GKR_TRY(ctx->check_launch("gkr_round"));
-        if (g_trace) { g_trace_t[TS_DIRECT_LAUNCH] += now_seconds() - t_launch0; g_trace_n[TS_DIRECT_LAUNCH]++; }
+        if (g_trace && !fused_first) { g_trace_t[TS_DIRECT_LAUNCH] += now_seconds() - t_launch0; g_trace_n[TS_DIRECT_LAUNCH]++; }
         if (j == s) GKR_TRY(start_poly(s));           // right behind the kernel that produced T_s: prepares message s+1
         const HostSlot *slot;
         g_wait_site = TS_WAIT_DIRECT;
@@ -1307,10 +1297,21 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
             Wrounds = ctx->shard_w.as<Fr>();
         }
         GKR_TRY(eq_table_dev(ctx, z.data(), L.k_out, ctx->eqz.as<Fr>()));
+        const bool lookahead = ctx->lookahead && !ctx->paranoid && !L.sharded;
+        // single pass: wiring sums + first round of the phase (needs whole 32-row blocks in both halves)
+        const bool fuse_wiring = lookahead && N >= 64;
+        uint32_t seq_first = 0;
         ctx->begin_launch();
-        launch_wiring_phase1(L.rowptr1, L.gate1, L.other1, L.n_edges1, ctx->eqz.as<Fr>(), W, ctx->wP.as<Fr>(),
-                             ctx->wQ.as<Fr>(), H, A, Nrows, ctx->stream);
-        ctx->end_launch(KC_WIRING, 76.0 * L.n_edges1 + 64.0 * Nrows, 2);
+        if (fuse_wiring) {
+            seq_first = ctx->next_seq();
+            launch_wiring_round1(false, true, L.rowptr1, L.gate1, L.other1, ctx->eqz.as<Fr>(), W, nullptr, Wrounds, H, A, N, ctx->ws,
+                                 ctx->slot_dev(seq_first), seq_first, ctx->stream);
+            ctx->end_launch(KC_WIRING, 76.0 * L.n_edges1 + 96.0 * N);
+        } else {
+            launch_wiring_phase1(L.rowptr1, L.gate1, L.other1, L.n_edges1, ctx->eqz.as<Fr>(), W, ctx->wP.as<Fr>(),
+                                 ctx->wQ.as<Fr>(), H, A, Nrows, ctx->stream);
+            ctx->end_launch(KC_WIRING, 76.0 * L.n_edges1 + 64.0 * Nrows, 2);
+        }
         GKR_TRY(ctx->check_launch("wiring_phase1"));
         if (g_trace) { g_trace_t[TS_SETUP_LAUNCH] += now_seconds() - t_setup0; g_trace_n[TS_SETUP_LAUNCH]++; }
 
@@ -1337,8 +1338,8 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         io.shard_bits = L.sharded ? shard_bits : 0;
         io.challenges = rs.data();
         io.msgs = &P->msgs[3 * ro]; io.msg_len = &P->msg_len[ro]; io.chal_out = &P->chal[ro];
+        io.first_round_seq = seq_first;
         HFr claim = hfr_zero();
-        const bool lookahead = ctx->lookahead && !ctx->paranoid && !L.sharded;
         GKR_TRY(L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, nullptr, &claim)
                 : lookahead ? run_phase_poly(ctx, t, io, &last_hash, nullptr, &claim)
                             : run_phase(ctx, t, io, &last_hash, nullptr, &claim));
@@ -1352,10 +1353,18 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         // ---- phase 2: variables c ----
         GKR_TRY(eq_table_dev(ctx, rs.data(), k, ctx->equ.as<Fr>()));
         ctx->begin_launch();
-        launch_wiring_phase2(L.rowptr2, L.gate2, L.other2, L.n_edges2, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu,
-                             ctx->wP.as<Fr>(), H, A, Nrows, ctx->stream);
-        ctx->end_launch(KC_WIRING, 76.0 * L.n_edges2 + 64.0 * Nrows, 2);
+        if (fuse_wiring) {
+            seq_first = ctx->next_seq();
+            launch_wiring_round1(true, false, L.rowptr2, L.gate2, L.other2, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu, Wrounds, H, A, N,
+                                 ctx->ws, ctx->slot_dev(seq_first), seq_first, ctx->stream);
+            ctx->end_launch(KC_WIRING, 76.0 * L.n_edges2 + 96.0 * N);
+        } else {
+            launch_wiring_phase2(L.rowptr2, L.gate2, L.other2, L.n_edges2, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu,
+                                 ctx->wP.as<Fr>(), H, A, Nrows, ctx->stream);
+            ctx->end_launch(KC_WIRING, 76.0 * L.n_edges2 + 64.0 * Nrows, 2);
+        }
         GKR_TRY(ctx->check_launch("wiring_phase2"));
+        io.first_round_seq = seq_first;
         if (g_trace) { g_trace_t[TS_SETUP_LAUNCH] += now_seconds() - t_setup1; g_trace_n[TS_SETUP_LAUNCH]++; }
         io.challenges = rs.data() + k;
         io.msgs = &P->msgs[3 * (ro + k)]; io.msg_len = &P->msg_len[ro + k]; io.chal_out = &P->chal[ro + k];

@@ -394,6 +394,132 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Wiring sums fused with the first sumcheck round of the phase (single pass, no P/Q arrays in global memory).
+// A warp owns 32 consecutive rows b and their partners b + N/2 (the pair the first round folds).  For each of
+// the two row blocks it walks the block's contiguous CSR edge range 32 edges at a time -- one edge per lane: two
+// gathers and one product, staged in shared memory -- and every lane then adds the staged values of its own row
+// segment.  With both rows in registers the lane stores H and A and accumulates the first-round sums
+//   X0 = sum H_lo W_lo + A_lo,  X2 = sum (H_hi - H_lo)(W_hi - W_lo),  X1 = sum H_hi W_hi + A_hi (FULL only),
+// published exactly as k_gkr_round<false, FULL> would.  Rows with very many edges serialise inside their warp.
+// ------------------------------------------------------------------------------------------------
+#ifndef GKR_WIRING_MINB
+#define GKR_WIRING_MINB 2
+#endif
+// one staged edge: gathers + product, written to the warp's staging arrays at position pos
+template <bool PHASE2>
+__device__ __forceinline__ void wiring_stage_edge(uint32_t g, uint32_t o, const Fr *__restrict__ X, const Fr *__restrict__ Y,
+                                                  Fr *stU, Fr *stV, int pos) {
+    const Fr x = ld_fr(X + g), y = ld_fr(Y + (o & 0x7fffffffu));
+    const Fr p = fr_mul(x, y);
+    const bool is_mul = o >> 31;
+    if (PHASE2) {                    // u: sum over add gates of p, v: sum over mult gates of p
+        stU[pos] = is_mul ? fr_zero() : p;
+        stV[pos] = is_mul ? p : fr_zero();
+    } else {                         // u: what multiplies W(b) (H), v: the constant part (A)
+        stU[pos] = is_mul ? p : x;
+        stV[pos] = is_mul ? fr_zero() : p;
+    }
+}
+constexpr int kWiringChunk = 64;     // edges staged per pass: two per lane, four gathers in flight per lane
+template <bool PHASE2>
+__device__ __forceinline__ void wiring_row_block(const uint32_t *__restrict__ csr_gate, const uint32_t *__restrict__ csr_other,
+                                                 const Fr *__restrict__ X, const Fr *__restrict__ Y, uint32_t e0, uint32_t e1,
+                                                 Fr *stU, Fr *stV, Fr &u, Fr &v) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t E0 = __shfl_sync(0xffffffffu, e0, 0), E1 = __shfl_sync(0xffffffffu, e1, 31);
+    u = fr_zero();
+    v = fr_zero();
+    for (uint32_t cs = E0; cs < E1; cs += kWiringChunk) {
+        const uint32_t ea = cs + lane, eb = cs + 32 + lane;
+        uint32_t ga = 0, oa = 0, gb = 0, ob = 0;
+        if (ea < E1) { ga = csr_gate[ea]; oa = csr_other[ea]; }
+        if (eb < E1) { gb = csr_gate[eb]; ob = csr_other[eb]; }
+        if (ea < E1) wiring_stage_edge<PHASE2>(ga, oa, X, Y, stU, stV, lane);
+        if (eb < E1) wiring_stage_edge<PHASE2>(gb, ob, X, Y, stU, stV, 32 + lane);
+        __syncwarp();
+        const uint32_t lo = e0 > cs ? e0 : cs, hi = e1 < cs + kWiringChunk ? e1 : cs + kWiringChunk;
+        for (uint32_t q = lo; q < hi; ++q) {
+            u = fr_add(u, stU[q - cs]);
+            v = fr_add(v, stV[q - cs]);
+        }
+        __syncwarp();
+    }
+}
+template <bool PHASE2, bool FULL>
+__global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
+    k_wiring_round1(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ csr_gate, const uint32_t *__restrict__ csr_other,
+                    const Fr *__restrict__ X, const Fr *__restrict__ Y, const Fr *__restrict__ wu_ptr, const Fr *__restrict__ Wtab,
+                    Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n, Fr *partials, unsigned int *counter, HostSlot *slot,
+                    uint32_t seq) {
+    constexpr int K = FULL ? 3 : 2;
+    __shared__ Fr stage[kWarps][2][kWiringChunk];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Fr *stU = stage[warp][0], *stV = stage[warp][1];
+    const uint64_t half = n / 2, n_blocks = half / 32;
+    Fr wu = fr_zero();
+    if (PHASE2) wu = ld_fr(wu_ptr);
+    Fr acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = fr_zero();
+    // row extents of the next block pair are loaded one iteration ahead, and the W entries of the current one before
+    // its edges are walked: fewer dependent memory round trips per block pair
+    const uint64_t blk_first = blockIdx.x * (uint64_t)kWarps + warp, blk_step = (uint64_t)gridDim.x * kWarps;
+    uint32_t nL0 = 0, nL1 = 0, nH0 = 0, nH1 = 0;
+    if (blk_first < n_blocks) {
+        const uint64_t r = blk_first * 32 + lane;
+        nL0 = rowptr[r]; nL1 = rowptr[r + 1]; nH0 = rowptr[r + half]; nH1 = rowptr[r + half + 1];
+    }
+    for (uint64_t blk = blk_first; blk < n_blocks; blk += blk_step) {
+        const uint64_t rowL = blk * 32 + lane, rowH = rowL + half;
+        const uint32_t eL0 = nL0, eL1 = nL1, eH0 = nH0, eH1 = nH1;
+        if (blk + blk_step < n_blocks) {
+            const uint64_t r = (blk + blk_step) * 32 + lane;
+            nL0 = rowptr[r]; nL1 = rowptr[r + 1]; nH0 = rowptr[r + half]; nH1 = rowptr[r + half + 1];
+        }
+        const Fr wl = ld_fr(Wtab + rowL), wh = ld_fr(Wtab + rowH);
+        Fr h[2], a[2];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t e0 = side ? eH0 : eL0, e1 = side ? eH1 : eL1;
+            Fr u, v;
+            wiring_row_block<PHASE2>(csr_gate, csr_other, X, Y, e0, e1, stU, stV, u, v);
+            if (PHASE2) {                    // H2 = S_add + W(u) S_mul, A2 = W(u) S_add
+                h[side] = u;
+                a[side] = fr_zero();
+                if (e1 > e0) {
+                    h[side] = fr_add(u, fr_mul(wu, v));
+                    a[side] = fr_mul(wu, u);
+                }
+            } else {
+                h[side] = u;
+                a[side] = v;
+            }
+            st_fr(H + (side ? rowH : rowL), h[side]);
+            st_fr(A + (side ? rowH : rowL), a[side]);
+        }
+        acc[0] = fr_add(acc[0], fr_add(fr_mul(h[0], wl), a[0]));
+        acc[1] = fr_add(acc[1], fr_mul(fr_sub(h[1], h[0]), fr_sub(wh, wl)));
+        if (FULL) acc[K - 1] = fr_add(acc[K - 1], fr_add(fr_mul(h[1], wh), a[1]));
+    }
+    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u);
+}
+void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
+                          const Fr *X, const Fr *Y, const Fr *wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
+                          HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    const uint64_t n_blocks = n / 64;
+    int grid = (int)((n_blocks + kWarps - 1) / kWarps);
+    const int resident = device_sm_count() * GKR_WIRING_MINB;      // one wave: block pairs are uneven, a second wave only adds a tail
+    if (grid > resident) grid = resident;
+    if (grid > ws.max_blocks) grid = ws.max_blocks;
+    if (grid < 1) grid = 1;
+#define GKR_WR1(P2, F) \
+    k_wiring_round1<P2, F><<<grid, kThreads, 0, s>>>(rowptr, csr_gate, csr_other, X, Y, wu, Wtab, H, A, n, ws.partials, ws.counter, slot, seq)
+    if (phase2) { if (full) GKR_WR1(true, true); else GKR_WR1(true, false); }
+    else { if (full) GKR_WR1(false, true); else GKR_WR1(false, false); }
+#undef GKR_WR1
+}
+
+// ------------------------------------------------------------------------------------------------
 // GKR sumcheck round, degree 2:  g(X) = sum_i (H_lo + X dH)(W_lo + X dW) + (A_lo + X dA)
 //   X0 = g(0) = sum H_lo W_lo + A_lo ;  X2 = sum dH dW ;  X1 = g(1) = sum H_hi W_hi + A_hi
 //   message = [X2, X1 - X0 - X2, X0]  (rust/src/gkr/sumcheck.rs:80-85,125-130 build the same coefficients)

@@ -60,6 +60,11 @@ void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 // CSR by right operand: row c lists (gate, left|type<<31); wu = W(u) on device
 void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, uint32_t n_edges,
                           const Fr *eqz, const Fr *equ, const Fr *wu, Fr *P, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
+// wiring sums of a phase fused with its first sumcheck round (n >= 64 rows): writes H, A and publishes the round's
+// sums like launch_gkr_round(fold = false, full, ...) would.  phase2: Y = equ and wu = W(u); else Y = W, wu unused.
+void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
+                          const Fr *X, const Fr *Y, const Fr *wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
+                          HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
 
 // ---- sumcheck rounds --------------------------------------------------------------------------
 // GKR round (degree 2) on (H, W, A).  Publishes v[0] = g(0), v[1] = X^2 coefficient, and v[2] = g(1)

@@ -44,7 +44,7 @@ constexpr uint64_t kTailPairs = (uint64_t)1 << 16;
 constexpr uint64_t kPrelaunchPairs = (uint64_t)1 << 12;
 // tables of at most this many entries are handled by look-ahead rounds (device one round ahead of the host hash);
 // larger ones are device-bound and keep the cheaper direct rounds
-constexpr uint64_t kLookaheadEntries = (uint64_t)1 << 15;
+constexpr uint64_t kLookaheadEntries = (uint64_t)1 << 18;
 // multi-GPU: once a rank's shard is down to this many entries per table the shards are all-gathered and the
 // remaining rounds run replicated on every rank (no per-round exchange for the many small late rounds)
 constexpr uint64_t kGatherEntries = (uint64_t)1 << 11;
