@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -16,6 +17,7 @@
 #include "kernels.cuh"
 
 struct gkr_ctx;
+struct gkr_aux_worker;
 
 namespace gkr {
 
@@ -91,6 +93,13 @@ struct gkr_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;         // latency-critical round kernels (high priority)
     cudaStream_t aux = nullptr;            // bulk work off the critical path: Moebius of d/input_func, q_i line folds, D2H
+    gkr_aux_worker *aux_worker = nullptr;  // helper thread that enqueues the line folds (created on first use)
+    // bulk jobs wait here until the proving thread has queued the large kernels of the next phase; they are then
+    // handed to the helper thread behind an event on the main stream, so that they run in the device's idle time
+    // during the small-table rounds instead of competing with the large kernels
+    std::vector<std::function<int()>> aux_pending;
+    cudaEvent_t gate_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned gate_idx = 0;
     static constexpr int kSlots = 64;
     gkr::HostSlot *slots_host = nullptr;   // pinned + mapped
     gkr::HostSlot *slots_dev = nullptr;
