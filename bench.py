@@ -61,7 +61,7 @@ class Clocks:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                                          "-lms", "250", "-i", str(index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -237,11 +237,13 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # the proof is a serial chain of ~640 host hashes: bring the host core to its working clock before timing
-    t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 0.5:
-        step_resident()
+    # the proof is a serial chain of ~640 host hashes: bring the host core to its working clock before timing, and
+    # start the clock sampler first -- nvidia-smi's start-up (NVML init, ~0.5 s of host and driver time) otherwise
+    # lands in the first timed steps and inflates them by several ms
     clocks = Clocks(local) if rank == 0 else None
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < 1.5:
+        step_resident()
     pv.stats(reset=True)
     total_ms = timed(step_resident, args.steps, args.warmup)
     st = pv.stats(reset=True)

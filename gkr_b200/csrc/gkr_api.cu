@@ -358,6 +358,8 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     std::unique_ptr<gkr_ctx> ctx(new (std::nothrow) gkr_ctx());
     if (!ctx) return GKR_ERR_OOM;
     ctx->device = device;
+    // profilers that serialise kernels (ncu) cannot run kernels that wait for the host: GKR_NO_PRELAUNCH=1
+    if (getenv("GKR_NO_PRELAUNCH")) ctx->prelaunch = false;
     GKR_TRY(ctx->bind());
     int prio_lo = 0, prio_hi = 0;
     GKR_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));

@@ -703,6 +703,99 @@ __device__ __forceinline__ void gkr_poly_body(const Fr *__restrict__ Hin, const 
     grid_publish_cta_totals<6>(acc, red, partials, counter, slot, seq, 0u);
 }
 static_assert(kThreads == 4 * kPolyChunk, "gkr_poly_body maps four threads to each quad of a chunk");
+// Large tables: two threads per quad and no shared memory or CTA barriers (the four-thread form above is bound by
+// its barriers once the launch has many chunks per CTA).  Lane pair (2m, 2m+1) of a warp owns quad i: the even lane
+// folds quarters 0, 1 and the odd lane quarters 2, 3.  Each lane computes the product of its first quarter (Q0 | Q1)
+// and of its quarter difference (E0 | E1); the two cross terms need one exchange of 2 field elements per lane:
+// the odd lane sends (H2, W2) and gets (H1-H0, W1-W0): Q2 on the even lane, E2 on the odd one.
+template <bool FOLD, class KT>
+__device__ __forceinline__ void gkr_poly2_body(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+                                               const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
+                                               Fr *__restrict__ Wout, Fr *__restrict__ Aout, const KT &r,
+                                               uint64_t q4, Fr *partials, unsigned int *counter, HostSlot *slot,
+                                               uint32_t seq) {
+    __shared__ Fr red[6][kWarps];
+    __shared__ Fr wred[kWarps][2][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t odd = lane & 1;
+    Fr acc[3];                                           // even lanes: Q0, E0, Q2; odd lanes: Q1, E1, E2
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc[j] = fr_zero();
+    const uint64_t warp_global = blockIdx.x * (uint64_t)kWarps + warp, n_warps = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t base = warp_global * 16; base < q4; base += n_warps * 16) {
+        const uint64_t i = base + (lane >> 1);
+        const bool active = i < q4;
+        Fr h0 = fr_zero(), h1 = fr_zero(), w0 = fr_zero(), w1 = fr_zero(), a0 = fr_zero();
+        if (active) {
+            const uint64_t e0 = i + (2 * odd) * q4, e1 = e0 + q4;
+            if (FOLD) {
+                w0 = fold2(ld_fr(Win + e0), ld_fr(Win + e0 + 4 * q4), r);
+                w1 = fold2(ld_fr(Win + e1), ld_fr(Win + e1 + 4 * q4), r);
+                st_fr(Wout + e0, w0);
+                st_fr(Wout + e1, w1);
+                h0 = fold2(ld_fr(Hin + e0), ld_fr(Hin + e0 + 4 * q4), r);
+                h1 = fold2(ld_fr(Hin + e1), ld_fr(Hin + e1 + 4 * q4), r);
+                st_fr(Hout + e0, h0);
+                st_fr(Hout + e1, h1);
+                a0 = fold2(ld_fr(Ain + e0), ld_fr(Ain + e0 + 4 * q4), r);
+                const Fr a1 = fold2(ld_fr(Ain + e1), ld_fr(Ain + e1 + 4 * q4), r);
+                st_fr(Aout + e0, a0);
+                st_fr(Aout + e1, a1);
+            } else {
+                w0 = ld_fr(Win + e0); w1 = ld_fr(Win + e1);
+                h0 = ld_fr(Hin + e0); h1 = ld_fr(Hin + e1);
+                a0 = ld_fr(Ain + e0);
+            }
+        }
+        const Fr uh = fr_sub(h1, h0), uw = fr_sub(w1, w0);
+        acc[0] = fr_add(acc[0], fr_add(fr_mul(h0, w0), a0));
+        acc[1] = fr_add(acc[1], fr_mul(uh, uw));
+        Fr rh, rw;
+#pragma unroll
+        for (int l = 0; l < 8; ++l) {
+            rh.l[l] = __shfl_xor_sync(0xffffffffu, odd ? h0.l[l] : uh.l[l], 1);
+            rw.l[l] = __shfl_xor_sync(0xffffffffu, odd ? w0.l[l] : uw.l[l], 1);
+        }
+        // even: (H2 - H0)(W2 - W0) with (H2, W2) received; odd: [(H3-H2) - (H1-H0)] [(W3-W2) - (W1-W0)] with the (H1-H0, W1-W0) received
+        const Fr dh = odd ? fr_sub(uh, rh) : fr_sub(rh, h0), dw = odd ? fr_sub(uw, rw) : fr_sub(rw, w0);
+        acc[2] = fr_add(acc[2], fr_mul(dh, dw));
+    }
+    // sums over the lanes of equal parity
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+        for (int off = 16; off >= 2; off >>= 1) {
+            Fr o;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) o.l[l] = __shfl_xor_sync(0xffffffffu, acc[j].l[l], off);
+            acc[j] = fr_add(acc[j], o);
+        }
+        if (lane < 2) wred[warp][lane][j] = acc[j];
+    }
+    __syncthreads();
+    Fr tot[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) tot[j] = fr_zero();
+    if (threadIdx.x == 0) {
+        for (int wv = 0; wv < kWarps; ++wv) {
+            tot[0] = fr_add(tot[0], wred[wv][0][0]);     // Q0
+            tot[3] = fr_add(tot[3], wred[wv][0][1]);     // E0
+            tot[2] = fr_add(tot[2], wred[wv][0][2]);     // Q2
+            tot[1] = fr_add(tot[1], wred[wv][1][0]);     // Q1
+            tot[4] = fr_add(tot[4], wred[wv][1][1]);     // E1
+            tot[5] = fr_add(tot[5], wred[wv][1][2]);     // E2
+        }
+    }
+    grid_publish_cta_totals<6>(tot, red, partials, counter, slot, seq, 0u);
+}
+template <bool FOLD>
+__global__ void __launch_bounds__(kThreads, 2) k_gkr_poly2(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
+                                                           const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
+                                                           Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
+                                                           uint64_t q4, Fr *partials, unsigned int *counter,
+                                                           HostSlot *slot, uint32_t seq) {
+    gkr_poly2_body<FOLD>(Hin, Win, Ain, Hout, Wout, Aout, r, q4, partials, counter, slot, seq);
+}
 template <bool FOLD>
 __global__ void __launch_bounds__(kThreads, 2) k_gkr_poly(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
                                                           const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
@@ -865,6 +958,16 @@ int gkr_poly_tail_max_quads() { return kTailQuads; }
 
 void launch_gkr_poly(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
                      uint64_t quads, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s, const HostCmd *cmd) {
+    static const uint64_t poly2_min = [] {               // tables from this many quads up use the two-thread form
+        const char *e = getenv("GKR_POLY2_MIN_LOG2");
+        return (uint64_t)1 << (e ? atoi(e) : 13);
+    }();
+    if (!cmd && quads >= poly2_min) {
+        const int grid2 = grid_for(2 * quads, ws.max_blocks);
+        if (fold) k_gkr_poly2<true><<<grid2, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
+        else k_gkr_poly2<false><<<grid2, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
+        return;
+    }
     const int grid = grid_for(4 * quads, ws.max_blocks);      // 64 quads per CTA pass
     if (cmd) k_gkr_poly_cmd<<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, cmd, quads, ws.partials, ws.counter, slot, seq);
     else if (fold) k_gkr_poly<true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);

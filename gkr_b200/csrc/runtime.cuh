@@ -45,8 +45,9 @@ constexpr uint64_t kTailPairs = (uint64_t)1 << 16;
 // rounds below this many pairs are launched ahead of their challenge and wait for it in a mapped command block
 constexpr uint64_t kPrelaunchPairs = (uint64_t)1 << 12;
 // tables of at most this many entries are handled by look-ahead rounds (device one round ahead of the host hash);
-// larger ones are device-bound and keep the cheaper direct rounds
-constexpr uint64_t kLookaheadEntries = (uint64_t)1 << 18;
+// larger ones are device-bound and keep the slightly cheaper direct rounds (measured on 2^20-gate layers:
+// 2^18: 25.6 ms, 2^19: 25.5 ms, 2^20: 25.8 ms per 16-layer proof -- flat, the large rounds are device-bound either way)
+constexpr uint64_t kLookaheadEntries = (uint64_t)1 << 19;
 // multi-GPU: once a rank's shard is down to this many entries per table the shards are all-gathered and the
 // remaining rounds run replicated on every rank (no per-round exchange for the many small late rounds)
 constexpr uint64_t kGatherEntries = (uint64_t)1 << 11;
