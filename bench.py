@@ -30,6 +30,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own banner / debug lines (printed to stdout when the environment sets
+# NCCL_DEBUG) go to stderr instead
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 
