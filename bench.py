@@ -391,8 +391,11 @@ def run_ours(args):
                 g = x["algo_bytes"] / (x["ms"] * 1e-3) / 1e9 if x["ms"] else 0.0
                 return {"launches": x["launches"], "ms": round(x["ms"], 4), "gbs": round(g, 1), "frac_of_hbm_peak": round(g / hbm_peak, 3)}
             gkr_large = {"k": lk, "layers": 1, "tables": "3 x %d MiB per phase (larger than L2)" % ((32 << lk) >> 20),
-                         "gkr_round_first": cls("gkr_round"), "gkr_round_fused": cls("gkr_round_fused"),
-                         "wiring": cls("wiring"), "note": "launches of >= 2^16 pairs; CUDA events around every launch"}
+                         "gkr_round_fused": cls("gkr_round_fused"), "lookahead_start_nofold": cls("gkr_round"),
+                         "wiring_plus_first_round": cls("wiring"),
+                         "note": "launches of >= 2^16 pairs; CUDA events around every launch. gkr_round_fused = direct "
+                                 "fused rounds above 2^19 entries + look-ahead rounds below (fold + next message as a "
+                                 "polynomial); the first round of each phase is fused into the wiring-sum kernel"}
         except Exception as e:  # noqa: BLE001 - an OOM here must not lose the headline numbers
             gkr_large = {"error": str(e)}
 
