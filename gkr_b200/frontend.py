@@ -1,0 +1,437 @@
+"""Front end of the reference: iden3 `.r1cs` / `.wtns` / `.sym` readers and the
+R1CS -> expression trees -> layered add/mult circuit compiler, restated from
+
+  rust/src/convert.rs:9-10      DEPTH_LIMIT, WIDTH_LIMIT
+  rust/src/convert.rs:108-152   merge_nodes, get_k
+  rust/src/convert.rs:154-358   compile            (trees -> IntermediateLayer{node_types, operand_index} per sub-circuit)
+  rust/src/convert.rs:360-632   convert_constraints_to_nodes   (one tree per constraint:  A*B - C  or  (-A)*B + C)
+  rust/src/convert.rs:634-671   Output, make_output
+  rust/src/convert.rs:793-811   input layer values from the witness
+  rust/src/convert.rs:851-871   parse_sym
+  rust/src/aggregator.rs:399-404   how the three files are read
+
+so that pre-generated circom artefacts can drive the device prover without the Rust toolchain.  The output is the
+dense boundary of the C ABI (`DenseLayer` lists + input-layer values), i.e. exactly the data the reference holds in
+`IntermediateLayer` before it expands it into term lists (convert.rs:704-777).
+
+The binary formats are those of the reference's un-vendored, unpinned git dependencies `r1cs-file` / `wtns-file`
+(github.com/jeong0982/zeropool-utils, rust/Cargo.toml:16-17), which implement the public iden3 specifications:
+  r1cs: magic "r1cs", u32 version (1), u32 n_sections, sections {u32 type, u64 size, payload}:
+        1 header  = u32 field_size, prime[field_size] LE, u32 n_wires, n_pub_out, n_pub_in, n_prv_in, u64 n_labels,
+                    u32 n_constraints
+        2 constraints = per constraint three linear combinations {u32 n, n x (u32 wire, coeff[field_size] LE)}
+        3 wire -> label map = n_wires x u64
+  wtns: magic "wtns", u32 version (2), u32 n_sections (2): 1 header = u32 field_size, prime, u32 n_witness;
+        2 data = n_witness x value[field_size] LE
+Parity with the Rust binary is unpinned (no toolchain, no circom here); the restatement is literal, including the
+places where the reference does not terminate (see `merge_nodes`).
+
+Host-side Python: string / graph work, not on the device path.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .field import P
+
+DEPTH_LIMIT = 10          # convert.rs:9  (only used by the symbol-table substitution, which the reference disables)
+WIDTH_LIMIT = 20          # convert.rs:10
+
+
+class FrontendError(ValueError):
+    pass
+
+
+# ------------------------------------------------------------------------------------------------
+# file formats
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class R1csHeader:
+    field_size: int
+    prime: int
+    n_wires: int
+    n_pub_out: int
+    n_pub_in: int
+    n_prv_in: int
+    n_labels: int
+    n_constraints: int
+
+
+@dataclass
+class R1cs:
+    """constraints[i] = (A, B, C), each a list of (coeff, wire) in file order -- the tuple order of the crate
+    (`for (coeff, x_i) in a`, convert.rs:492)"""
+    header: R1csHeader
+    constraints: list
+    wire_map: list = field(default_factory=list)
+    version: int = 1
+
+
+def _sections(data: bytes, magic: bytes):
+    if len(data) < 12 or data[:4] != magic:
+        raise FrontendError(f"not a {magic.decode()} file")
+    version, n_sections = struct.unpack_from("<II", data, 4)
+    off = 12
+    out = []
+    for _ in range(n_sections):
+        if off + 12 > len(data):
+            raise FrontendError("truncated section header")
+        ty, size = struct.unpack_from("<IQ", data, off)
+        off += 12
+        if off + size > len(data):
+            raise FrontendError("truncated section")
+        out.append((ty, data[off:off + size]))
+        off += size
+    return version, out
+
+
+def read_r1cs(data: bytes) -> R1cs:
+    version, secs = _sections(data, b"r1cs")
+    if version != 1:
+        raise FrontendError(f"unsupported r1cs version {version}")
+    by_type = {}
+    for ty, payload in secs:
+        by_type.setdefault(ty, payload)
+    if 1 not in by_type or 2 not in by_type:
+        raise FrontendError("r1cs file lacks the header or the constraint section")
+    h = by_type[1]
+    fs = struct.unpack_from("<I", h, 0)[0]
+    if fs != 32:
+        raise FrontendError(f"field size {fs}: the reference reads R1csFile::<32> only")
+    prime = int.from_bytes(h[4:4 + fs], "little")
+    n_wires, n_pub_out, n_pub_in, n_prv_in, n_labels, n_constraints = struct.unpack_from("<IIIIQI", h, 4 + fs)
+    if prime != P:
+        raise FrontendError("r1cs prime is not the BN254 scalar field")
+    header = R1csHeader(fs, prime, n_wires, n_pub_out, n_pub_in, n_prv_in, n_labels, n_constraints)
+    body = by_type[2]
+    off = 0
+    constraints = []
+    for _ in range(n_constraints):
+        lcs = []
+        for _ in range(3):
+            n = struct.unpack_from("<I", body, off)[0]
+            off += 4
+            lc = []
+            for _ in range(n):
+                wire = struct.unpack_from("<I", body, off)[0]
+                coeff = int.from_bytes(body[off + 4:off + 4 + fs], "little")
+                off += 4 + fs
+                if coeff >= P or wire >= n_wires:
+                    raise FrontendError("constraint term out of range")
+                lc.append((coeff, wire))
+            lcs.append(lc)
+        constraints.append(tuple(lcs))
+    wire_map = []
+    if 3 in by_type:
+        wire_map = list(struct.unpack_from(f"<{len(by_type[3]) // 8}Q", by_type[3], 0))
+    return R1cs(header, constraints, wire_map, version)
+
+
+def write_r1cs(r: R1cs) -> bytes:
+    """inverse of read_r1cs (used by the tests and to build fixtures without circom)"""
+    h = r.header
+    head = struct.pack("<I", 32) + h.prime.to_bytes(32, "little") + struct.pack(
+        "<IIIIQI", h.n_wires, h.n_pub_out, h.n_pub_in, h.n_prv_in, h.n_labels, len(r.constraints))
+    body = bytearray()
+    for lcs in r.constraints:
+        for lc in lcs:
+            body += struct.pack("<I", len(lc))
+            for coeff, wire in lc:
+                body += struct.pack("<I", wire) + int(coeff).to_bytes(32, "little")
+    wmap = struct.pack(f"<{len(r.wire_map)}Q", *r.wire_map)
+    out = bytearray(b"r1cs" + struct.pack("<II", 1, 3))
+    for ty, payload in ((1, head), (2, bytes(body)), (3, wmap)):
+        out += struct.pack("<IQ", ty, len(payload)) + payload
+    return bytes(out)
+
+
+def read_wtns(data: bytes) -> list:
+    version, secs = _sections(data, b"wtns")
+    if version != 2:
+        raise FrontendError(f"unsupported wtns version {version}")
+    by_type = dict(secs)
+    if 1 not in by_type or 2 not in by_type:
+        raise FrontendError("wtns file lacks the header or the data section")
+    h = by_type[1]
+    fs = struct.unpack_from("<I", h, 0)[0]
+    if fs != 32:
+        raise FrontendError(f"field size {fs}: the reference reads WtnsFile::<32> only")
+    prime = int.from_bytes(h[4:4 + fs], "little")
+    n = struct.unpack_from("<I", h, 4 + fs)[0]
+    if prime != P:
+        raise FrontendError("wtns prime is not the BN254 scalar field")
+    d = by_type[2]
+    if len(d) < n * fs:
+        raise FrontendError("truncated witness")
+    vals = [int.from_bytes(d[i * fs:(i + 1) * fs], "little") for i in range(n)]
+    if any(v >= P for v in vals):
+        raise FrontendError("witness value out of range")      # Fr::from_repr(..).unwrap() panics (convert.rs:806)
+    return vals
+
+
+def write_wtns(values) -> bytes:
+    head = struct.pack("<I", 32) + P.to_bytes(32, "little") + struct.pack("<I", len(values))
+    data = b"".join(int(v).to_bytes(32, "little") for v in values)
+    out = bytearray(b"wtns" + struct.pack("<II", 2, 2))
+    for ty, payload in ((1, head), (2, data)):
+        out += struct.pack("<IQ", ty, len(payload)) + payload
+    return bytes(out)
+
+
+def parse_sym(text: str, num_public: int) -> list:
+    """convert.rs:851-871: the name after `main.` of the first num_public lines (`#s,#w,#c,main.name`)"""
+    res = []
+    if num_public == 0:
+        return res
+    for line in text.splitlines():
+        cols = line.split(",")
+        res.append(cols[3].split(".")[1])
+        if len(res) == num_public:
+            break
+    return res
+
+
+@dataclass
+class Output:                       # convert.rs:634-651
+    wire_map: dict
+    name_map: dict
+
+    def get_name(self, w):
+        return self.name_map.get(w)
+
+
+def make_output(witness, sym_names) -> Output:      # convert.rs:653-667
+    out = Output({}, {})
+    for i, name in enumerate(sym_names):
+        out.wire_map[i + 1] = witness[i + 1]
+        out.name_map[i + 1] = name
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# expression trees.  A node is a tuple: ("V", value) | ("X", wire) | ("A", left, right) | ("M", left, right);
+# tuple equality is the reference's structural PartialEq (convert.rs:33-56; its left/right presence test is
+# vacuous because inner nodes always have both children).
+# ------------------------------------------------------------------------------------------------
+ZERO_NODE = ("V", 0)
+ONE = 1
+MINUS_ONE = P - 1
+
+
+def depth(node) -> int:             # convert.rs:85-89 (a leaf has depth 1)
+    if node[0] in ("V", "X"):
+        return 1
+    return max(depth(node[1]), depth(node[2])) + 1
+
+
+def merge_nodes(nodes):
+    """convert.rs:108-139: balanced tree of additions.  On an EMPTY list the reference recurses forever
+    (`merge_nodes(vec![])` calls itself with an empty vector): rejected here with an error instead."""
+    if len(nodes) == 0:
+        raise FrontendError("empty linear combination: the reference does not terminate on it (merge_nodes, convert.rs:108-139)")
+    if len(nodes) == 1:
+        return nodes[0]
+    new = [("A", nodes[2 * i], nodes[2 * i + 1]) for i in range(len(nodes) // 2)]
+    if len(nodes) % 2 == 1:
+        return ("A", merge_nodes(new), nodes[-1])
+    return merge_nodes(new)
+
+
+def get_k(n: int) -> int:           # convert.rs:141-152
+    if n <= 0:
+        raise FrontendError("get_k(0)")
+    k = n.bit_length() - 1
+    return k if n & (n - 1) == 0 else k + 1
+
+
+def _count_mult(lc):                # convert.rs:363-378
+    a = b = 0
+    for coeff, _ in lc:
+        if coeff == ONE:
+            b += 1
+        elif coeff == MINUS_ONE:
+            a += 1
+        else:
+            a += 1
+            b += 1
+    return a, b
+
+
+def _term(coeff, wire, unit):
+    """coeff * x_wire, with the multiplication elided when coeff == unit"""
+    if coeff == unit:
+        return ("X", wire)
+    return ("M", ("V", coeff), ("X", wire))
+
+
+def constraints_to_nodes(r1cs: R1cs):
+    """convert.rs:360-632.  The symbol-table substitution is disabled in the reference (the only call of
+    `update_symbol_table` is commented out, :565), so the table stays empty, no lookup ever hits, `used` stays empty
+    and every constraint becomes its own single-tree sub-circuit:
+        neg = false:  A * B + (-C)        neg = true:  (-A) * B + C
+    where neg picks the form with fewer constant multiplications (:478-486)."""
+    nodes = []
+    for a, b, c in r1cs.constraints:
+        cnt_a, cnt_b, cnt_c = _count_mult(a), _count_mult(b), _count_mult(c)
+        mult_cnt = cnt_a[0] + cnt_b[0] + cnt_c[1]
+        m_mult_cnt = cnt_a[1] + cnt_b[1] + cnt_c[0]
+        neg = mult_cnt > m_mult_cnt
+        if neg:
+            node_a = [_term((P - coeff) % P, w, ONE) if coeff != MINUS_ONE else ("X", w) for coeff, w in a]
+        else:
+            node_a = [_term(coeff, w, ONE) for coeff, w in a]
+        node_b = [_term(coeff, w, ONE) for coeff, w in b]
+        if node_a and node_b:
+            a_times_b = ("M", merge_nodes(node_a), merge_nodes(node_b))
+            if neg:
+                node_c = [_term(coeff, w, ONE) for coeff, w in c]
+            else:
+                node_c = [_term((P - coeff) % P, w, ONE) if coeff != MINUS_ONE else ("X", w) for coeff, w in c]
+            nodes.append(("A", a_times_b, merge_nodes(node_c)))
+        else:
+            # `[] * [] - C = 0`: the reference merges node_c BEFORE filling it (:620-623), i.e. an empty list
+            nodes.append(merge_nodes([]))
+    return [[n] for n in nodes]
+
+
+@dataclass
+class IntermediateLayer:            # convert.rs:102-106
+    node_types: list                # "A" | "M"
+    operand_index: list             # (left, right) into the next layer
+
+
+def compile_nodes(groups):
+    """convert.rs:154-358: sort the sub-circuits by height (stable), merge neighbours pairwise until at most
+    WIDTH_LIMIT remain, then peel each group layer by layer.  Returns (layers per group, input nodes per group)."""
+    nodes_sorted = sorted(groups, key=lambda g: max((depth(n) for n in g), default=0))      # sort_by is stable
+    width = len(nodes_sorted)
+    while width > WIDTH_LIMIT:
+        new_nodes = [nodes_sorted[2 * i] + nodes_sorted[2 * i + 1] for i in range(width // 2)]
+        if width % 2 == 1:
+            new_nodes.append(nodes_sorted[width - 1])
+        nodes_sorted = new_nodes
+        width = len(nodes_sorted)
+    total, total_inputs = [], []
+    for one_circuit in nodes_sorted:
+        layers = []
+        height = max((depth(n) for n in one_circuit), default=0)
+        if height == 0:
+            return [layers], []                                   # :193-195
+        inputs = []
+        current = list(one_circuit)
+        for d in range(height + 1):
+            full = 1 << get_k(len(current))
+            current = current + [ZERO_NODE] * (full - len(current))
+            if d == height:
+                if any(n[0] not in ("V", "X") for n in current):
+                    raise FrontendError("input layer holds an operation")
+                inputs = current
+                break
+            nxt = []
+            first_pos = {}                                        # node -> first index in nxt (= `.position()`)
+            used = {}
+            zero_index = None
+            node_types, operand_index = [], []
+
+            def push(node):
+                nxt.append(node)
+                first_pos.setdefault(node, len(nxt) - 1)
+                return len(nxt) - 1
+
+            for node in current:
+                if node[0] in ("A", "M"):
+                    if d == height - 1:
+                        raise FrontendError("Unsupported")        # :219-221
+                    node_types.append(node[0])
+                    left, right = node[1], node[2]
+                    li = first_pos[left] if left in first_pos else push(left)
+                    ri = first_pos[right] if right in first_pos else push(right)
+                    operand_index.append((li, ri))
+                else:
+                    e = node
+                    node_types.append("A")
+                    if e in used:
+                        operand_index.append((used[e], zero_index))
+                        continue
+                    if zero_index is None:
+                        zero_index = push(ZERO_NODE)
+                    if e == ZERO_NODE:
+                        used[e] = zero_index
+                        operand_index.append((zero_index, zero_index))
+                    else:
+                        used[e] = len(nxt)
+                        operand_index.append((len(nxt), zero_index))
+                        push(e)
+            layers.append(IntermediateLayer(node_types, operand_index))
+            current = nxt
+        total.append(layers)
+        total_inputs.append(inputs)
+    return total, total_inputs
+
+
+# ------------------------------------------------------------------------------------------------
+# dense boundary
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class SubCircuit:
+    layers: list                    # prover.DenseLayer, output layer first
+    input_values: np.ndarray        # (2^input_k, 8) uint32, canonical
+    k: list                         # k_0 .. k_depth
+
+
+def input_layer_values(input_nodes, witness):
+    """convert.rs:793-811"""
+    vals = []
+    for node in input_nodes:
+        if node[0] == "V":
+            vals.append(node[1])
+        elif node[0] == "X":
+            if node[1] >= len(witness):
+                raise FrontendError(f"wire {node[1]} is not in the witness")
+            vals.append(witness[node[1]])
+        else:
+            raise FrontendError("Input value should be an expression")
+    return vals
+
+
+def to_dense(layers, input_nodes, witness) -> SubCircuit:
+    from .field import ints_to_fr
+    from .prover import DenseLayer
+    ks = [get_k(len(L.node_types)) for L in layers] + [get_k(len(input_nodes))]
+    dense = []
+    for i, L in enumerate(layers):
+        dense.append(DenseLayer(ks[i], ks[i + 1],
+                                np.array([0 if t == "A" else 1 for t in L.node_types], np.uint8),
+                                np.array([o[0] for o in L.operand_index], np.uint32),
+                                np.array([o[1] for o in L.operand_index], np.uint32)))
+    return SubCircuit(dense, ints_to_fr(input_layer_values(input_nodes, witness)), ks)
+
+
+def convert_r1cs_wtns_gkr(r1cs: R1cs, witness, sym_text: str = ""):
+    """convert.rs:673-785 up to the dense boundary: (sub-circuits, public Output)"""
+    all_layers, all_inputs = compile_nodes(constraints_to_nodes(r1cs))
+    out = make_output(witness, parse_sym(sym_text, r1cs.header.n_pub_in + r1cs.header.n_pub_out))
+    subs = [to_dense(layers, inputs, witness) for layers, inputs in zip(all_layers, all_inputs)]
+    return subs, out
+
+
+def prove_r1cs(prover, r1cs: R1cs, witness, sym_text: str = ""):
+    """aggregator.rs:399-416 without the circom shell-outs: one device proof per sub-circuit.  The reference asserts
+    that the first output of every sub-circuit evaluates to zero (convert.rs:838); here every output must."""
+    subs, out = convert_r1cs_wtns_gkr(r1cs, witness, sym_text)
+    proofs = []
+    for sc in subs:
+        c = prover.circuit(sc.layers)
+        w = prover.witness_eval(c, sc.input_values)
+        try:
+            d = prover.witness_layer(c, w, 0)
+            if np.any(d):
+                raise FrontendError("the witness does not satisfy the constraints of this sub-circuit")
+            proofs.append(prover.prove(c, w))
+        finally:
+            w.close()
+            c.close()
+    return proofs, subs, out

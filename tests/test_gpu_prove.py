@@ -219,6 +219,38 @@ def test_lookahead_off_matches(pv):
     pn.close()
 
 
+def _skewed_circuit(rng, ks, hubs):
+    """layers whose gates read a few hub wires very often (rows with thousands of CSR edges) and leave most rows
+    without any edge: the multi-pass and empty-row paths of the fused wiring kernel"""
+    layers = []
+    for i in range(len(ks) - 1):
+        k_out, k_in = ks[i], ks[i + 1]
+        n_in = 1 << k_in
+        hub = [rng.randrange(n_in) for _ in range(hubs)]
+        gates = []
+        for _ in range(1 << k_out):
+            ty = rng.randrange(2)
+            left = rng.choice(hub) if rng.random() < 0.7 else rng.randrange(n_in)
+            right = rng.choice(hub) if rng.random() < 0.5 else rng.randrange(n_in)
+            gates.append((ty, left, right))
+        layers.append((k_out, k_in, gates))
+    return layers
+
+
+@pytest.mark.parametrize("ks", [[6, 6], [7, 6, 7], [10, 11, 10], [13, 12, 13]])
+def test_skewed_fan_out_and_boundary_sizes(pv, ks):
+    """hub wires (row segments far longer than one 64-edge pass, both halves of the table), empty rows, and the
+    smallest sizes that take the fused wiring kernel (N = 64) / the single-CTA tail kernel"""
+    rng = random.Random(1000 + sum(ks))
+    layers = _skewed_circuit(rng, ks, hubs=3)
+    inputs = [rng.randrange(P) for _ in range(1 << ks[-1])]
+    want, _ = run_l1(layers, inputs)
+    got = _gpu_prove(pv, layers, inputs)
+    assert_same_dense(want, got)
+    ok, why = verifier.verify(layers, got, input_values=inputs)
+    assert ok, why
+
+
 def test_custom_transcript_callback(pv):
     """the challenge callback (how a Rust host keeps mimc_rs) must see the same messages and drive the same proof"""
     rng = random.Random(5)
