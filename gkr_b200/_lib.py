@@ -64,7 +64,7 @@ class Profile(C.Structure):
 
 # every symbol include/gkr_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
-    "gkr_ctx_create", "gkr_ctx_destroy", "gkr_ctx_stream", "gkr_ctx_sync", "gkr_ctx_set_option", "gkr_last_error", "gkr_version", "gkr_mimc7_multi_hash", "gkr_mimc7_hash",
+    "gkr_ctx_create", "gkr_ctx_destroy", "gkr_ctx_stream", "gkr_ctx_sync", "gkr_ctx_set_option", "gkr_last_error", "gkr_version", "gkr_mimc7_multi_hash", "gkr_mimc7_hash", "gkr_mimc7_round_constant",
     "gkr_circuit_create", "gkr_circuit_destroy", "gkr_witness_create", "gkr_witness_eval", "gkr_witness_layer",
     "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_verify", "gkr_sumcheck_prod", "gkr_dev_table_synth", "gkr_dev_table_synth_strided", "gkr_comm_unique_id", "gkr_comm_init", "gkr_comm_destroy",
     "gkr_sumcheck_prod_sharded",
@@ -104,6 +104,7 @@ def lib():
     L.gkr_ctx_set_option.argtypes = [vp, C.c_char_p, i32]
     L.gkr_mimc7_multi_hash.argtypes = [vp, u32, vp, vp]
     L.gkr_mimc7_hash.argtypes = [vp, vp, vp]
+    L.gkr_mimc7_round_constant.argtypes = [u32, vp]
     L.gkr_circuit_create.argtypes = [vp, u32, C.POINTER(LayerDesc), C.POINTER(vp)]
     L.gkr_circuit_destroy.argtypes = [vp]
     L.gkr_circuit_destroy.restype = None

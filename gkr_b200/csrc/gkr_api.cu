@@ -502,6 +502,12 @@ extern "C" int gkr_mimc7_multi_hash(const gkr_fr *msg, uint32_t n, const gkr_fr 
     hfr_to_canonical(out, mimc7_multi_hash(m.data(), n, k));
     return GKR_OK;
 }
+extern "C" int gkr_mimc7_round_constant(uint32_t i, gkr_fr *out) {
+    HFr c;
+    if (!out || !mimc7_round_constant(i, &c)) return GKR_ERR_INVALID;
+    hfr_to_canonical(out, c);
+    return GKR_OK;
+}
 extern "C" int gkr_mimc7_hash(const gkr_fr *x, const gkr_fr *key, gkr_fr *out) {
     if (!x || !key || !out) return GKR_ERR_INVALID;
     HFr a, k;

@@ -113,6 +113,13 @@ HFr mimc7_hash(const HFr &x, const HFr &key) {
     return hfr_add(h, key);
 }
 
+bool mimc7_round_constant(unsigned i, HFr *out) {
+    std::call_once(g_once, init_constants);
+    if (i >= (unsigned)kRounds) return false;
+    *out = g_constants[i];
+    return true;
+}
+
 HFr mimc7_multi_hash(const HFr *msg, size_t n, const HFr &key) {
     HFr r = key;
     for (size_t i = 0; i < n; ++i) r = hfr_add(hfr_add(r, msg[i]), mimc7_hash(msg[i], r));

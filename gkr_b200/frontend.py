@@ -297,6 +297,61 @@ def constraints_to_nodes(r1cs: R1cs):
     return [[n] for n in nodes]
 
 
+def mimc7_round_constants(rounds: int = 91) -> list:
+    """c_0..c_{rounds-1} of MiMC7 from the library's transcript (gkr_mimc7_round_constant)"""
+    import ctypes as C
+    from ._lib import check, lib
+    out = np.zeros(8, np.uint32)
+    vals = []
+    for i in range(rounds):
+        check(lib().gkr_mimc7_round_constant(C.c_uint32(i), out.ctypes.data_as(C.c_void_p)))
+        vals.append(int.from_bytes(out.tobytes(), "little"))
+    return vals
+
+
+def mimc7_constraint_system(x_in: int, negated: bool = True):
+    """The constraint system circom emits for rust/t.circom (circomlib MiMC7(91), k = 0, linear constraints
+    substituted away): per round t2 = t*t, t4 = t2*t2, t6 = t4*t2, t7 = t6*t  => 364 constraints; wires: 0 = one,
+    1 = out (public), 2 = in1 (public), 3 = in2, then the products.  circom writes `c <== a*b` as (-a)*b = -c: that
+    form is used for every other constraint so that both sign branches of the compiler are exercised.  Built by hand
+    because circom / circomlib are not available here: an approximation of the real artefact, flagged as such
+    (SURVEY.md section 8(d)).  Returns (R1cs, witness values)."""
+    c = mimc7_round_constants(91)
+    wires = [1, 0, x_in % P, 3]
+    one_w, out_w, in1_w = 0, 1, 2
+    cons = []
+
+    def mul(a_lc, b_lc, val, out_wire=None):
+        if out_wire is None:
+            wires.append(val)
+            out_wire = len(wires) - 1
+        else:
+            wires[out_wire] = val
+        if negated and len(cons) % 2 == 0:
+            cons.append(([((P - k) % P, x) for k, x in a_lc], list(b_lc), [(MINUS_ONE, out_wire)]))
+        else:
+            cons.append((list(a_lc), list(b_lc), [(1, out_wire)]))
+        return out_wire
+
+    t_lc, t_val = [(1, in1_w)], x_in % P
+    for i in range(91):
+        t2 = t_val * t_val % P
+        w2 = mul(t_lc, t_lc, t2)
+        t4 = t2 * t2 % P
+        w4 = mul([(1, w2)], [(1, w2)], t4)
+        t6 = t4 * t2 % P
+        w6 = mul([(1, w4)], [(1, w2)], t6)
+        t7 = t6 * t_val % P
+        if i < 90:
+            w7 = mul([(1, w6)], t_lc, t7)
+            t_lc, t_val = [(c[i + 1], one_w), (1, w7)], (t7 + c[i + 1]) % P
+        else:
+            mul([(1, w6)], t_lc, t7, out_w)
+    n = len(wires)
+    header = R1csHeader(32, P, n, 1, 1, 1, n, len(cons))
+    return R1cs(header, cons, list(range(n))), wires
+
+
 @dataclass
 class IntermediateLayer:            # convert.rs:102-106
     node_types: list                # "A" | "M"

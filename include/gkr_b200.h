@@ -85,6 +85,9 @@ typedef struct {
 /* built-in transcript, exposed for hosts/tests: out = multi_hash(msg[0..n), key) ; hash(x, key) */
 int gkr_mimc7_multi_hash(const gkr_fr *msg, uint32_t n, const gkr_fr *key, gkr_fr *out);
 int gkr_mimc7_hash(const gkr_fr *x, const gkr_fr *key, gkr_fr *out);
+/* round constant c_i of MiMC7-91 (c_0 = 0, c_i = keccak256^{i+1}("mimc") mod p), i < 91: what circomlib's MiMC7 template
+   (rust/t.circom:9) bakes into its constraints; used to build that constraint system without circom */
+int gkr_mimc7_round_constant(uint32_t i, gkr_fr *out);
 
 /* ---- circuit (replaces the add_i/mult_i/wire emission of convert.rs:704-777) ------------------- */
 typedef struct {

@@ -30,44 +30,11 @@ def _satisfied(r, w):
 
 
 def mimc7_r1cs(x_in, negated=True):
-    """the constraint system circom emits for rust/t.circom (MiMC7(91), k = 0, linear constraints substituted away):
-    4 multiplications per round = 364 constraints.  circom writes  t2 <== t*t  as (-t)*t = -t2: used for every other
-    constraint so that both sign branches of the compiler are exercised.  An approximation of the real artefact
-    (no circom here), flagged as such."""
-    c = l0.mimc7_constants(91)
-    wires = [1, 0, x_in % P, 3]                         # one, out (filled below), in1, in2
-    ONE, OUT, IN1 = 0, 1, 2
-    cons = []
-
-    def mul(a_lc, b_lc, val, out_wire=None):
-        if out_wire is None:
-            wires.append(val)
-            out_wire = len(wires) - 1
-        else:
-            wires[out_wire] = val
-        if negated and len(cons) % 2 == 0:
-            cons.append(([((P - k) % P, x) for k, x in a_lc], list(b_lc), [(M1, out_wire)]))
-        else:
-            cons.append((list(a_lc), list(b_lc), [(1, out_wire)]))
-        return out_wire
-
-    t_lc, t_val = [(1, IN1)], x_in % P
-    for i in range(91):
-        t2 = t_val * t_val % P
-        w2 = mul(t_lc, t_lc, t2)
-        t4 = t2 * t2 % P
-        w4 = mul([(1, w2)], [(1, w2)], t4)
-        t6 = t4 * t2 % P
-        w6 = mul([(1, w4)], [(1, w2)], t6)
-        t7 = t6 * t_val % P
-        if i < 90:
-            w7 = mul([(1, w6)], t_lc, t7)
-            t_lc, t_val = [(c[i + 1], ONE), (1, w7)], (t7 + c[i + 1]) % P
-        else:
-            mul([(1, w6)], t_lc, t7, OUT)
-    r = _r1cs(cons, len(wires))
+    """product builder (frontend.mimc7_constraint_system) cross-checked against the oracle's MiMC7"""
+    r, wires = fe.mimc7_constraint_system(x_in, negated)
+    assert fe.mimc7_round_constants(91) == l0.mimc7_constants(91)
     assert _satisfied(r, wires)
-    assert wires[OUT] == l0.mimc7_hash(x_in, 0)
+    assert wires[1] == l0.mimc7_hash(x_in, 0)
     return r, wires
 
 
