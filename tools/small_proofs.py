@@ -29,3 +29,12 @@ for rep in range(3):
     print(f"rep {rep}: 12 sub-circuits: circuit {1e3 * t_c:.2f} ms, witness {1e3 * t_w:.2f} ms, prove {1e3 * t_p:.2f} ms", flush=True)
 st = pv.stats()
 print({k: st[k] for k in ("kernel_launches", "transcript_seconds", "wait_seconds") if k in st})
+pv.stats(reset=True)
+pv.profile(1)
+sc = subs[5]
+c = pv.circuit(sc.layers)
+wt = pv.witness_eval(c, sc.input_values)
+pv.free_raw(pv.prove_raw(c, wt))
+prof = pv.profile(0)
+print("one 5-layer sub-circuit, k =", sc.k, {n: (d["launches"], round(d["ms"], 3)) for n, d in prof.items() if d["launches"]},
+      "stats launches:", pv.stats()["kernel_launches"])
