@@ -963,7 +963,11 @@ void launch_gkr_poly(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout,
         return (uint64_t)1 << (e ? atoi(e) : 13);
     }();
     if (!cmd && quads >= poly2_min) {
-        const int grid2 = grid_for(2 * quads, ws.max_blocks);
+        static const int cap2 = [] {                         // experiment knob: CTAs per SM for the two-thread form
+            const char *e = getenv("GKR_POLY2_CTAS_PER_SM");
+            return device_sm_count() * (e ? atoi(e) : 2);     // one resident wave (2 vs 4 per SM: 25.25 vs 25.37 ms per proof)
+        }();
+        const int grid2 = grid_for(2 * quads, cap2 < ws.max_blocks ? cap2 : ws.max_blocks);
         if (fold) k_gkr_poly2<true><<<grid2, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
         else k_gkr_poly2<false><<<grid2, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
         return;
