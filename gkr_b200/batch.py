@@ -65,6 +65,61 @@ class ProverPool:
         self.close()
 
 
+def timed_prove_stage(jobs, n_workers: int = 4, device: int = 0, warmup: int = 4) -> float:
+    """Wall-clock seconds of the GKR stage alone for a batch: what the reference times around its
+    `par_iter().map(prover::prove)` (rust/src/aggregator.rs:406-418), i.e. circuits and inputs already built.
+    Jobs are dealt statically to n_workers threads, each with its own Prover; every thread first uploads its circuits
+    and evaluates its witnesses (untimed), then all threads start proving together."""
+    import time
+
+    jobs = list(jobs)
+    n_workers = max(1, min(n_workers, len(jobs)))
+    ready = threading.Barrier(n_workers + 1)
+    done = threading.Barrier(n_workers + 1)
+    errors = []
+
+    def worker(wid):
+        handles = []
+        pv = None
+        ok = False
+        try:
+            pv = Prover(device)
+            for layers, vals in jobs[wid::n_workers]:
+                c = pv.circuit(layers)
+                handles.append((c, pv.witness_eval(c, vals)))
+            for c, w in handles[:warmup]:
+                pv.free_raw(pv.prove_raw(c, w))
+            ok = True
+        except Exception as e:  # noqa: BLE001 - reported to the caller below
+            errors.append(e)
+        ready.wait()
+        try:
+            if ok:
+                for c, w in handles:
+                    pv.free_raw(pv.prove_raw(c, w))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+        done.wait()
+        for c, w in handles:
+            w.close()
+            c.close()
+        if pv is not None:
+            pv.close()
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(n_workers)]
+    for t in threads:
+        t.start()
+    ready.wait()
+    t0 = time.perf_counter()
+    done.wait()
+    dt = time.perf_counter() - t0
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return dt
+
+
 def prove_many(jobs, n_workers: int = 4, device: int = 0) -> list:
     """one-shot form of ProverPool.prove_many"""
     with ProverPool(n_workers, device) as pool:

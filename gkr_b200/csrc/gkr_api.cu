@@ -230,6 +230,18 @@ struct gkr_aux_worker {
 static const bool g_aux_gate = getenv("GKR_AUX_NOGATE") == nullptr;     // experiment knob, see release sites
 static int release_aux_jobs(gkr_ctx *ctx, bool gated) {
     if (ctx->aux_pending.empty()) return GKR_OK;
+    if (ctx->aux_inline) {
+        // small proofs (batches of them run one context per host core): no helper thread, a handful of launches inline
+        for (auto &job : ctx->aux_pending) {
+            const int rc = job();
+            if (rc != GKR_OK) {
+                ctx->aux_pending.clear();
+                return rc;
+            }
+        }
+        ctx->aux_pending.clear();
+        return GKR_OK;
+    }
     if (!ctx->aux_worker) ctx->aux_worker = new gkr_aux_worker(ctx->device);
     cudaEvent_t ev = nullptr;
     if (gated) {
@@ -1323,6 +1335,13 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
             if (ctx->aux_worker) ctx->aux_worker->drain();
         }
     } worker_guard{ctx};
+    // the helper thread pays off when a layer's bulk work is tens of launches on large tables; small circuits are
+    // proved in batches with one context per host core, where a second thread per context only oversubscribes them
+    static const int inline_max_k = [] {
+        const char *e = getenv("GKR_AUX_INLINE_MAX_K");
+        return e ? atoi(e) : 12;
+    }();
+    ctx->aux_inline = (int)c->max_k <= inline_max_k;
     P->pub.n_layers = n_layers;
     P->pub.depth = n_layers + 1;
     P->k = c->k;
@@ -1567,7 +1586,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         if (worker_used) {
             GKR_TRY(release_aux_jobs(ctx, false));
             worker_guard.armed = false;
-            GKR_TRY(ctx->aux_worker->drain());
+            if (ctx->aux_worker) GKR_TRY(ctx->aux_worker->drain());
         }
         GKR_CUDA_TRY(cudaStreamSynchronize(ctx->aux));
     }

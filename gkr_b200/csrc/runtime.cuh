@@ -101,6 +101,7 @@ struct gkr_ctx {
     std::vector<std::function<int()>> aux_pending;
     cudaEvent_t gate_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     unsigned gate_idx = 0;
+    bool aux_inline = false;               // this proof is small: run the bulk jobs on the proving thread (set per gkr_prove)
     static constexpr int kSlots = 64;
     gkr::HostSlot *slots_host = nullptr;   // pinned + mapped
     gkr::HostSlot *slots_dev = nullptr;
