@@ -569,7 +569,7 @@ static int eq_table_dev(gkr_ctx *ctx, const HFr *z, uint32_t k, Fr *out) {
     GKR_TRY(ctx->eq_scratch.ensure(sizeof(Fr) * 2 * ((size_t)1 << ((k + 1) / 2 + 1))));
     ctx->begin_launch();
     launch_eq_table(zv, k, out, ctx->eq_scratch.as<Fr>(), ctx->stream);
-    ctx->end_launch(KC_EQ, 32.0 * (double)((uint64_t)1 << k), k <= 8 ? 1 : 3);
+    ctx->end_launch(KC_EQ, 32.0 * (double)((uint64_t)1 << k), k <= 8 ? 1 : 2);
     return ctx->check_launch("eq_table");
 }
 // values -> Moebius coefficients (in place) + support; waits for the result

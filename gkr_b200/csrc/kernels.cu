@@ -309,6 +309,23 @@ __global__ void __launch_bounds__(kThreads) k_eq_expand(const Fr *__restrict__ h
     for (uint64_t idx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; idx < n; idx += (uint64_t)gridDim.x * blockDim.x)
         st_fr(out + idx, fr_mul(ld_fr(hi + (idx >> k_lo)), ld_fr(lo + (idx & mask))));
 }
+// both factor tables of the split in one launch: blocks [0, nb_hi) build hi, the rest lo
+__global__ void __launch_bounds__(kThreads) k_eq_small_pair(FrVec z, uint32_t k_hi, uint32_t k_lo, Fr *__restrict__ hi,
+                                                            Fr *__restrict__ lo, uint32_t nb_hi) {
+    const bool is_lo = blockIdx.x >= nb_hi;
+    const uint32_t nv = is_lo ? k_lo : k_hi, first_var = is_lo ? k_hi : 0;
+    const uint32_t n = 1u << nv;
+    const uint32_t idx = (blockIdx.x - (is_lo ? nb_hi : 0)) * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const Fr one = fr_one();
+    Fr acc = one;
+    for (uint32_t j = 0; j < nv; ++j) {
+        const Fr zj = z.v[first_var + j];
+        const bool bit = (idx >> (nv - 1 - j)) & 1u;
+        acc = fr_mul(acc, bit ? zj : fr_sub(one, zj));
+    }
+    st_fr((is_lo ? lo : hi) + idx, acc);
+}
 void launch_eq_table(const FrVec &z, uint32_t k, Fr *out, Fr *scratch, cudaStream_t s) {
     if (k <= 8) {
         k_eq_small<<<grid_for(1u << k, 64), kThreads, 0, s>>>(z, 0, k, out);
@@ -316,8 +333,8 @@ void launch_eq_table(const FrVec &z, uint32_t k, Fr *out, Fr *scratch, cudaStrea
     }
     const uint32_t k_hi = k / 2, k_lo = k - k_hi;
     Fr *hi = scratch, *lo = scratch + ((size_t)1 << k_hi);
-    k_eq_small<<<grid_for(1u << k_hi, 148), kThreads, 0, s>>>(z, 0, k_hi, hi);
-    k_eq_small<<<grid_for(1u << k_lo, 148), kThreads, 0, s>>>(z, k_hi, k_lo, lo);
+    const uint32_t nb_hi = ((1u << k_hi) + kThreads - 1) / kThreads, nb_lo = ((1u << k_lo) + kThreads - 1) / kThreads;
+    k_eq_small_pair<<<nb_hi + nb_lo, kThreads, 0, s>>>(z, k_hi, k_lo, hi, lo, nb_hi);
     const uint64_t n = (uint64_t)1 << k;
     k_eq_expand<<<stream_grid(n), kThreads, 0, s>>>(hi, lo, out, k_lo, n);
 }
