@@ -465,6 +465,48 @@ def to_dense(layers, input_nodes, witness) -> SubCircuit:
     return SubCircuit(dense, ints_to_fr(input_layer_values(input_nodes, witness)), ks)
 
 
+def to_reference_types(sc: SubCircuit):
+    """The reference's own return types for one sub-circuit (small circuits only: the lists grow with 2^k):
+    `GKRCircuit { layer: [Layer { k, add, mult, wire }], input_k }` (convert.rs:704-781: one chi-form term
+    `[1, e_1..e_v]` per gate with e = 1 for a 0 bit and 2 for a 1 bit of out|left|right, MSB-first; `get_empty` when a
+    layer has no gate of a type; wire = the same bit rows as 0/1) and `Input { w, d }` (convert.rs:812-849: forward
+    evaluation, then the monomial-form MLE of every layer with zero coefficients dropped; d = w[0]).  Term order is
+    `HashMap` order in the reference: compare as sets."""
+    from .field import fr_to_ints
+    from .prover import GKRCircuit, Input, Layer, coef_table_to_terms
+    if max(sc.k) > 14:
+        raise FrontendError("term-list form requested for a layer wider than 2^14")
+    layers = []
+    for L in sc.layers:
+        v = L.k_out + 2 * L.k_in
+        polys, wires = ([], []), ([], [])
+        for g in range(len(L.gtype)):
+            bits = (format(g, "0%db" % L.k_out) if L.k_out else "") + format(int(L.left[g]), "0%db" % L.k_in) + \
+                format(int(L.right[g]), "0%db" % L.k_in)
+            ty = int(L.gtype[g])
+            polys[ty].append([1] + [2 if ch == "1" else 1 for ch in bits])
+            wires[ty].append([int(ch) for ch in bits])
+        add, mult = (p if p else [[0] * (v + 1)] for p in polys)
+        layers.append(Layer(L.k_out, add, mult, (wires[0], wires[1])))
+    values = [fr_to_ints(sc.input_values)]
+    for L in reversed(sc.layers):
+        prev = values[-1]
+        vals = [(prev[int(l)] + prev[int(r)]) % P if int(t) == 0 else prev[int(l)] * prev[int(r)] % P
+                for t, l, r in zip(L.gtype, L.left, L.right)]
+        values.append(vals + [0] * ((1 << L.k_out) - len(vals)))
+    values.reverse()
+    w = []
+    for vals, k in zip(values, sc.k):
+        coef = list(vals)
+        for s_ in range(k):                          # Moebius transform: coefficient of the monomial with bit set S
+            bit = 1 << s_
+            for i in range(1 << k):
+                if i & bit:
+                    coef[i] = (coef[i] - coef[i ^ bit]) % P
+        w.append(coef_table_to_terms(coef, k) if k else [])     # a 1-entry table has an empty MLE (poly.rs:117-119)
+    return GKRCircuit(layers, sc.k[-1]), Input(w, w[0])
+
+
 def convert_r1cs_wtns_gkr(r1cs: R1cs, witness, sym_text: str = ""):
     """convert.rs:673-785 up to the dense boundary: (sub-circuits, public Output)"""
     all_layers, all_inputs = compile_nodes(constraints_to_nodes(r1cs))

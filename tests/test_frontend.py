@@ -205,6 +205,33 @@ def test_mimc7_circuit_like_t_circom():
     assert ok, why
 
 
+def _as_sets(terms):
+    return sorted(tuple(t) for t in terms)
+
+
+def test_reference_typed_output_matches_literal_emission():
+    """frontend.to_reference_types == the literal emission code of convert.rs:704-849 (oracle/l0_reference.py) on
+    compiled sub-circuits, comparing term lists as sets (the reference's order is HashMap order)"""
+    rng = random.Random(31)
+    r, w = random_r1cs(rng, 5, n_free=3, max_terms=2)
+    subs, _ = fe.convert_r1cs_wtns_gkr(r, w)
+    checked = 0
+    for sc in subs:
+        if max(sc.k) > 5:
+            continue
+        checked += 1
+        circ, inp = fe.to_reference_types(sc)
+        layers = [(L.k_out, list(zip(L.gtype.tolist(), L.left.tolist(), L.right.tolist()))) for L in sc.layers]
+        want_c = l0.build_reference_circuit(layers, sc.k[-1])
+        want_i, _ = l0.calculate_input(layers, fr_to_ints(sc.input_values))
+        assert circ.input_k == want_c.input_k and len(circ.layer) == len(want_c.layer)
+        for a, b in zip(circ.layer, want_c.layer):
+            assert a.k == b.k and _as_sets(a.add) == _as_sets(b.add) and _as_sets(a.mult) == _as_sets(b.mult)
+            assert _as_sets(a.wire[0]) == _as_sets(b.wire[0]) and _as_sets(a.wire[1]) == _as_sets(b.wire[1])
+        assert [_as_sets(x) for x in inp.w] == [_as_sets(x) for x in want_i.w] and _as_sets(inp.d) == _as_sets(want_i.d)
+    assert checked >= 3
+
+
 @pytest.mark.gpu
 def test_gpu_prove_compiled_r1cs():
     """aggregator.rs:399-416 without the shell-outs: every sub-circuit of the compiled MiMC7 system proved on the device,
@@ -221,6 +248,21 @@ def test_gpu_prove_compiled_r1cs():
         layers = [(L.k_out, L.k_in, list(zip(L.gtype.tolist(), L.left.tolist(), L.right.tolist()))) for L in sc.layers]
         ok, why = verifier.verify(layers, proof, input_values=fr_to_ints(sc.input_values))
         assert ok, why
+    # the reference's own call on its own types, for a small compiled sub-circuit
+    import gkr_b200
+    rng = random.Random(32)
+    r3, w3 = random_r1cs(rng, 3, n_free=3, max_terms=2)
+    n_typed = 0
+    for sc in fe.convert_r1cs_wtns_gkr(r3, w3)[0]:
+        if max(sc.k) <= 4:
+            n_typed += 1
+            circ, inp = fe.to_reference_types(sc)
+            got = gkr_b200.prove(circ, inp, pv)
+            want = l0.prove(circ, inp)
+            assert got.sumcheck_proofs == want.sumcheck_proofs and got.sumcheck_r == want.sumcheck_r
+            assert got.q == want.q and got.z == want.z and got.r == want.r and got.k == want.k
+            assert _as_sets(got.d) == _as_sets(want.d) and _as_sets(got.input_func) == _as_sets(want.input_func)
+    assert n_typed >= 1
     rng = random.Random(9)
     r2, w2 = random_r1cs(rng, 30)
     bad = list(w2)
