@@ -250,6 +250,13 @@ def run_ours(args):
     pv.stats(reset=True)
     total_ms = timed(step_resident, args.steps, args.warmup)
     st = pv.stats(reset=True)
+    # host transcript time of every rank (contention between the ranks' host threads shows up here first)
+    host_per_rank = None
+    if world > 1:
+        tt = torch.tensor([1e3 * st["transcript_seconds"] / (args.steps + args.warmup)], dtype=torch.float64, device="cuda")
+        gathered = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(gathered, tt)
+        host_per_rank = [round(float(g.item()), 3) for g in gathered]
     launches_timed = st["kernel_launches"] * args.steps // (args.steps + args.warmup)
     e2e_ms = timed(step_e2e, args.steps, max(1, args.warmup // 2))
     st2 = pv.stats(reset=True)
@@ -471,7 +478,8 @@ def run_ours(args):
                                    "gbs": round(x["algo_bytes"] / (x["ms"] * 1e-3) / 1e9, 1) if x["ms"] else None}
                                for n, x in classes.items()},
             "t_circom_like_batch": tcircom,
-            "host": {"transcript_ms_per_step": 1e3 * st["transcript_seconds"] / (args.steps + args.warmup),
+            "host": {"transcript_ms_per_step_per_rank": host_per_rank,
+                     "transcript_ms_per_step": 1e3 * st["transcript_seconds"] / (args.steps + args.warmup),
                      "wait_ms_per_step": 1e3 * st["wait_seconds"] / (args.steps + args.warmup)},
         }
         print(json.dumps(line), flush=True)
