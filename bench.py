@@ -244,8 +244,9 @@ def run_ours(args):
     # start the clock sampler first -- nvidia-smi's start-up (NVML init, ~0.5 s of host and driver time) otherwise
     # lands in the first timed steps and inflates them by several ms
     clocks = Clocks(local) if rank == 0 else None
+    # (with several ranks on one host NVML enumerates every GPU and the cores share their boost budget: spin longer)
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 1.5:
+    while time.perf_counter() - t_spin < (1.5 if world == 1 else 4.0):
         step_resident()
     pv.stats(reset=True)
     total_ms = timed(step_resident, args.steps, args.warmup)
