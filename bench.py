@@ -120,9 +120,10 @@ def cpu_sample_ms(k: int, layers: int, sample_layers: int, seed: int = 1):
     return dt * 1e3 * (layers / sl), orc.num_threads(), f"{sl} of {layers} layers of the same circuit, scaled x{layers / sl:g}"
 
 
-def literal_reference_seconds(ks=(5, 6, 7)):
+def literal_reference_seconds(ks=(5, 6, 7, 8)):
     """seconds for ONE layer of 2^k gates with the LITERAL restatement of the reference's term-list algorithm
-    (oracle/l0_reference.py, pure Python, 1 thread): documents its O(4^k) growth -- it cannot reach k = 16..20."""
+    (oracle/l0_reference.py, pure Python, 1 thread): documents its O(4^k) growth (x3.3-4 per extra variable: k = 20
+    would take on the order of 10^7 s per layer) -- it cannot reach k = 16..20."""
     import random
 
     from oracle import l0_reference as l0
