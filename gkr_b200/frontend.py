@@ -515,6 +515,39 @@ def convert_r1cs_wtns_gkr(r1cs: R1cs, witness, sym_text: str = ""):
     return subs, out
 
 
+def compile_native(r1cs_bytes: bytes, wtns_bytes: bytes):
+    """The same pipeline in the library's native front end (csrc/frontend.cpp, `gkr_frontend_*`): file bytes in,
+    list of SubCircuit out.  A C / Rust host calls these entry points directly and hands the arrays to
+    gkr_circuit_create / gkr_witness_eval without copying."""
+    import ctypes as C
+    from ._lib import LayerDesc, check, lib
+    from .prover import DenseLayer
+    L = lib()
+    h = C.c_void_p()
+    check(L.gkr_frontend_compile(r1cs_bytes, len(r1cs_bytes), wtns_bytes, len(wtns_bytes), C.byref(h)))
+    try:
+        subs = []
+        for i in range(L.gkr_frontend_n_circuits(h)):
+            n_layers, input_k = C.c_uint32(), C.c_uint32()
+            descs, vals = C.POINTER(LayerDesc)(), C.c_void_p()
+            check(L.gkr_frontend_circuit(h, i, C.byref(n_layers), C.byref(descs), C.byref(input_k), C.byref(vals)))
+            layers, ks = [], []
+            for j in range(n_layers.value):
+                d = descs[j]
+                n = d.n_gates
+                layers.append(DenseLayer(d.k_out, d.k_in,
+                                         np.ctypeslib.as_array(C.cast(d.type, C.POINTER(C.c_uint8)), (n,)).copy(),
+                                         np.ctypeslib.as_array(C.cast(d.left, C.POINTER(C.c_uint32)), (n,)).copy(),
+                                         np.ctypeslib.as_array(C.cast(d.right, C.POINTER(C.c_uint32)), (n,)).copy()))
+                ks.append(d.k_out)
+            ks.append(input_k.value)
+            inputs = np.ctypeslib.as_array(C.cast(vals, C.POINTER(C.c_uint32)), ((1 << input_k.value), 8)).copy()
+            subs.append(SubCircuit(layers, inputs, ks))
+        return subs
+    finally:
+        L.gkr_frontend_destroy(h)
+
+
 def prove_r1cs(prover, r1cs: R1cs, witness, sym_text: str = ""):
     """aggregator.rs:399-416 without the circom shell-outs: one device proof per sub-circuit.  The reference asserts
     that the first output of every sub-circuit evaluates to zero (convert.rs:838); here every output must."""

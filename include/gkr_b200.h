@@ -192,6 +192,20 @@ int gkr_mobius(gkr_ctx *ctx, const gkr_fr *values, uint32_t k, gkr_fr *coef_out,
 int gkr_line_restrict(gkr_ctx *ctx, const gkr_fr *values, uint32_t k, const gkr_fr *b, const gkr_fr *c,
                       gkr_fr *coef_ascending /* k+1 */);
 
+/* ---- front end (host only): pre-generated circom artefacts -> sub-circuits at the dense boundary ------------------
+ * Replaces R1csFile::read / WtnsFile::read (rust/src/aggregator.rs:399-404), convert_constraints_to_nodes
+ * (rust/src/convert.rs:360-632), compile (:154-358) and the input-layer evaluation (:793-811): the bytes of a .r1cs
+ * and a .wtns file (iden3 formats, BN254) become one (layers, input values) pair per sub-circuit, to be passed to
+ * gkr_circuit_create / gkr_witness_eval.  Constraints with an empty linear combination are an error (the reference does
+ * not terminate on them, merge_nodes :108-139).  The returned arrays live until gkr_frontend_destroy. */
+typedef struct gkr_frontend gkr_frontend;
+int gkr_frontend_compile(const uint8_t *r1cs, size_t r1cs_len, const uint8_t *wtns, size_t wtns_len, gkr_frontend **out);
+uint32_t gkr_frontend_n_circuits(const gkr_frontend *fe);
+uint32_t gkr_frontend_n_public(const gkr_frontend *fe);       /* n_pub_in + n_pub_out of the r1cs header (make_output, :653-667) */
+int gkr_frontend_circuit(const gkr_frontend *fe, uint32_t i, uint32_t *n_layers, const gkr_layer_desc **layers,
+                         uint32_t *input_k, const gkr_fr **input_values /* 2^input_k canonical values */);
+void gkr_frontend_destroy(gkr_frontend *fe);
+
 /* ---- instrumentation ------------------------------------------------------------------------------ */
 typedef struct {
     uint64_t kernel_launches;  /* kernels launched by this context since creation / last reset */

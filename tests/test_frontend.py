@@ -205,6 +205,40 @@ def test_mimc7_circuit_like_t_circom():
     assert ok, why
 
 
+def _same_subcircuits(a, b):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x.k == y.k and len(x.layers) == len(y.layers)
+        for lx, ly in zip(x.layers, y.layers):
+            assert (lx.k_out, lx.k_in) == (ly.k_out, ly.k_in)
+            assert np.array_equal(lx.gtype, ly.gtype) and np.array_equal(lx.left, ly.left) and np.array_equal(lx.right, ly.right)
+        assert np.array_equal(x.input_values, y.input_values)
+
+
+@pytest.mark.parametrize("n_constraints", [1, 7, 21, 45])
+def test_native_front_end_equals_python(n_constraints):
+    """csrc/frontend.cpp (gkr_frontend_* in the C ABI) against gkr_b200/frontend.py: identical layers and inputs"""
+    rng = random.Random(500 + n_constraints)
+    r, w = random_r1cs(rng, n_constraints)
+    rb, wb = fe.write_r1cs(r), fe.write_wtns(w)
+    _same_subcircuits(fe.compile_native(rb, wb), fe.convert_r1cs_wtns_gkr(fe.read_r1cs(rb), fe.read_wtns(wb))[0])
+
+
+def test_native_front_end_mimc7_and_errors():
+    from gkr_b200._lib import GkrError
+    r, w = mimc7_r1cs(5)
+    rb, wb = fe.write_r1cs(r), fe.write_wtns(w)
+    native = fe.compile_native(rb, wb)
+    assert len(native) == 12
+    _same_subcircuits(native, fe.convert_r1cs_wtns_gkr(r, w)[0])
+    for bad_r, bad_w in ((b"nope" + rb[4:], wb), (rb[:50], wb), (rb, wb[:40]), (rb, fe.write_wtns([P]))):
+        with pytest.raises(GkrError):
+            fe.compile_native(bad_r, bad_w)
+    empty_c = _r1cs([([(1, 1)], [(1, 2)], [])], 3)
+    with pytest.raises(GkrError, match="does not terminate"):
+        fe.compile_native(fe.write_r1cs(empty_c), fe.write_wtns([1, 2, 3]))
+
+
 def _as_sets(terms):
     return sorted(tuple(t) for t in terms)
 
