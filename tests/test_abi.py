@@ -53,3 +53,20 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text.replace(
                     "imports oracle/", "").replace("import oracle/", ""), f
+
+
+def test_public_header_is_plain_c():
+    """the drop-in boundary is a C ABI: include/gkr_b200.h must compile as C99 (and as C++) without extensions"""
+    import os
+    import shutil
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cc = shutil.which("gcc") or "/usr/bin/gcc"
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "hc.c")
+        with open(src, "w") as f:
+            f.write('#include "gkr_b200.h"\nint main(void) { gkr_fr x; (void)x; return GKR_OK; }\n')
+        inc = os.path.join(root, "include")
+        subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", src], check=True)
+        subprocess.run([cc, "-x", "c++", "-std=c++17", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", src], check=True)
