@@ -70,7 +70,7 @@ EXPORTS = [
     "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_verify", "gkr_sumcheck_prod", "gkr_dev_table_synth", "gkr_dev_table_synth_strided", "gkr_comm_unique_id", "gkr_comm_init", "gkr_comm_destroy",
     "gkr_sumcheck_prod_sharded",
     "gkr_dev_table_upload", "gkr_dev_table_download", "gkr_dev_table_free", "gkr_fr_binop", "gkr_eq_table",
-    "gkr_mobius", "gkr_line_restrict", "gkr_ctx_stats", "gkr_ctx_profile", "gkr_bench_field_mul",
+    "gkr_mobius", "gkr_line_restrict", "gkr_ctx_stats", "gkr_ctx_profile", "gkr_bench_field_mul", "gkr_fold_f64_constants", "gkr_selftest",
 ]
 
 _LIB = None
@@ -80,7 +80,7 @@ def build(force: bool = False) -> str:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     if force and os.path.exists(SO_PATH):
         os.remove(SO_PATH)
-    subprocess.check_call(["make", "-C", _SRC, "-s"])
+    subprocess.check_call(["make", "-C", _SRC, "-s", "-j", str(min(8, os.cpu_count() or 1))])
     return SO_PATH
 
 
@@ -145,6 +145,10 @@ def lib():
     L.gkr_ctx_stats.argtypes = [vp, C.POINTER(Stats), i32]
     L.gkr_ctx_profile.argtypes = [vp, i32, C.POINTER(Profile)]
     L.gkr_bench_field_mul.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_double)]
+    if hasattr(L, "gkr_selftest"):
+        L.gkr_selftest.argtypes = [vp, u32, vp, vp]
+    if hasattr(L, "gkr_fold_f64_constants"):       # absent from older builds loaded through GKR_B200_LIB for A/B runs
+        L.gkr_fold_f64_constants.argtypes = [vp, vp]
     _LIB = L
     return L
 

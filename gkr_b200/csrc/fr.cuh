@@ -416,16 +416,20 @@ FR_HD void wide_mac(FrWide &acc, const Fr &a, const Fr &b) {
     wide_add16(acc, od);
 }
 // (acc * R^-1) mod p: the Montgomery-form value of sum_i a_i b_i R^-1, i.e. what sum_i fr_mul(a_i,b_i) gives.
-// acc = A0 + A1 R + A2 R^2  =>  A0 R^-1 + A1 + A2 R.  fr_mul tolerates a first operand up to 2^256.
+// acc = A0 + A1 R + A2 R^2  =>  A0 R^-1 + A1 + A2 R.  A0 and A1 are arbitrary 256-bit words (not < p): they go in as
+// the SECOND operand of fr_mul, which is consumed limb by limb and may be any value below 2^256, while the first
+// operand must stay below p for the row invariant t + a b_i + m p < 2^288 of the carry chains.  (Round 1 passed them
+// first: exact in the portable emulation, but the PTX chains drop a carry once A1 is large -- proofs of tables with
+// more than ~50 accumulated products per thread, i.e. 2^24 entries and up, were wrong.)
 FR_HD Fr wide_reduce(const FrWide &acc) {
     Fr a0, a1, a2 = fr_zero(), one = fr_zero();
     one.l[0] = 1;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a0.l[i] = acc.l[i]; a1.l[i] = acc.l[8 + i]; }
     a2.l[0] = acc.l[16];
-    Fr r = fr_mul(a0, one);
-    r = fr_add(r, fr_mul(fr_mul(a1, fr_r2()), one));
-    r = fr_add(r, fr_mul(a2, fr_r2()));
+    Fr r = fr_mul(one, a0);
+    r = fr_add(r, fr_mul(one, fr_mul(fr_r2(), a1)));
+    r = fr_add(r, fr_mul(fr_r2(), a2));
     return r;
 }
 

@@ -56,6 +56,59 @@ FrConstMul make_const_mul(const HFr &r) {
     return K;
 }
 
+// constants of the FP64-pipe fold (fr_f64.cuh): eleven balanced base-2^24 digits of the centred representative of
+// r * 2^(24 i) mod p, i = 0..10
+FrFoldF64 make_fold_f64(const HFr &r) {
+    static HFr pow24[11];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        HFr x = hfr_one();
+        for (int i = 0; i < 11; ++i) {
+            pow24[i] = x;                        // Montgomery form of 2^(24 i)
+            for (int b = 0; b < 24; ++b) x = hfr_add(x, x);
+        }
+    });
+    // (p - 1) / 2, little-endian 32-bit limbs
+    static const uint32_t half[8] = {0xf8000000u, 0xa1f0fac9u, 0x3cdcb848u, 0x9419f424u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};
+    static const uint32_t pl[8] = {frc::P0, frc::P1, frc::P2, frc::P3, frc::P4, frc::P5, frc::P6, frc::P7};
+    FrFoldF64 K{};
+    for (int i = 0; i < 11; ++i) {
+        uint32_t c[8];
+        hfr_to_canonical(c, hfr_mul(r, pow24[i]));
+        bool neg = false;
+        for (int l = 7; l >= 0; --l)
+            if (c[l] != half[l]) { neg = c[l] > half[l]; break; }
+        if (neg) {                               // magnitude of the centred representative: p - c
+            uint64_t borrow = 0;
+            for (int l = 0; l < 8; ++l) {
+                const uint64_t d = (uint64_t)pl[l] - c[l] - borrow;
+                c[l] = (uint32_t)d;
+                borrow = (d >> 32) & 1;
+            }
+        }
+        uint64_t carry = 0;                      // balanced digits: a digit >= 2^23 becomes digit - 2^24 and carries 1
+        for (int j = 0; j < 11; ++j) {
+            const int bit = 24 * j, w = bit / 32, sh = bit % 32;
+            uint64_t v = c[w] >> sh;
+            if (sh > 8 && w + 1 < 8) v |= (uint64_t)c[w + 1] << (32 - sh);
+            int64_t d = (int64_t)((j < 10 ? (v & 0xFFFFFFu) : v) + carry);
+            carry = 0;
+            if (j < 10 && d >= (1 << 23)) { d -= (1 << 24); carry = 1; }
+            K.c[i][j] = neg ? -(double)d : (double)d;
+        }
+    }
+    return K;
+}
+
+int default_f64_folds() {
+    static const int v = [] {
+        const char *e = getenv("GKR_F64_FOLDS");
+        const int x = e ? atoi(e) : 0;
+        return (x < 0 || x > 6 || x == 1) ? 0 : x;
+    }();
+    return v;
+}
+
 namespace {
 std::mutex g_pool_mu;
 std::multimap<size_t, void *> g_pool;
@@ -373,6 +426,7 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     // profilers that serialise kernels (ncu) cannot run kernels that wait for the host: GKR_NO_PRELAUNCH=1
     if (getenv("GKR_NO_PRELAUNCH")) ctx->prelaunch = false;
     GKR_TRY(ctx->bind());
+    GKR_CUDA_TRY((cudaError_t)kernels_device_init(device));
     int prio_lo = 0, prio_hi = 0;
     GKR_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     GKR_CUDA_TRY(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
@@ -438,6 +492,34 @@ extern "C" int gkr_bench_field_mul(gkr_ctx *ctx, int ilp, int blocks_per_sm, int
     return ctx->check_launch("mul_bench");
 }
 
+extern "C" int gkr_fold_f64_constants(const gkr_fr *r, double *out121) {
+    if (!r || !out121) return GKR_ERR_INVALID;
+    HFr x;
+    if (!hfr_from_canonical(&x, r)) return GKR_ERR_RANGE;
+    const FrFoldF64 K = make_fold_f64(x);
+    for (int i = 0; i < 11; ++i)
+        for (int j = 0; j < 11; ++j) out121[11 * i + j] = K.c[i][j];
+    return GKR_OK;
+}
+
+extern "C" int gkr_selftest(gkr_ctx *ctx, uint32_t iters, const gkr_fr *r, uint32_t *failures2) {
+    if (!ctx || !failures2 || iters == 0 || iters > (1u << 20)) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    HFr x = hfr_from_u64(0x9e3779b97f4a7c15ull);
+    if (r && !hfr_from_canonical(&x, r)) return GKR_ERR_RANGE;
+    GKR_CUDA_TRY(cudaMemsetAsync(ctx->words + 4, 0, 2 * sizeof(unsigned int), ctx->stream));
+    ctx->begin_launch();
+    launch_selftest(iters, make_const_mul(x), make_fold_f64(x), ctx->words + 4, ctx->stream);
+    ctx->end_launch(KC_OTHER, 0.0);
+    GKR_TRY(ctx->check_launch("selftest"));
+    GKR_CUDA_TRY(cudaMemcpyAsync(ctx->pinned_words, ctx->words + 4, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    failures2[0] = ctx->pinned_words[0];
+    failures2[1] = ctx->pinned_words[1];
+    GKR_CUDA_TRY(cudaMemsetAsync(ctx->words + 4, 0, 2 * sizeof(unsigned int), ctx->stream));
+    return GKR_OK;
+}
+
 extern "C" int gkr_ctx_set_option(gkr_ctx *ctx, const char *name, int value) {
     if (!ctx || !name) return GKR_ERR_INVALID;
     if (std::strcmp(name, "paranoid") == 0) {
@@ -450,6 +532,11 @@ extern "C" int gkr_ctx_set_option(gkr_ctx *ctx, const char *name, int value) {
     }
     if (std::strcmp(name, "prelaunch") == 0) {
         ctx->prelaunch = value != 0;
+        return GKR_OK;
+    }
+    if (std::strcmp(name, "f64_folds") == 0) {       // folds per pair moved to the FP64 pipe in the streaming rounds (0, 2..6)
+        if (value < 0 || value > 6 || value == 1) return GKR_ERR_INVALID;
+        ctx->f64_folds = value;
         return GKR_OK;
     }
     set_last_error("unknown option '%s'", name);
@@ -1831,6 +1918,8 @@ static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3]
         const uint32_t s = ctx->next_seq();
         const bool full = (j == 0) || ctx->paranoid;     // the first claim (the sum itself) is not known in advance
         const FrConstMul rc = pending_fold ? make_const_mul(r) : FrConstMul{};
+        const bool f64 = ctx->f64_folds > 0 && pending_fold && prod3_round_wants_f64(true, full, n / 4);
+        const FrFoldF64 rf = f64 ? make_fold_f64(r) : FrFoldF64{};
         Fr *dev_out = sharded_round ? ctx->comm_send : nullptr;
         ctx->begin_launch();
         if (!pending_fold) {
@@ -1842,7 +1931,7 @@ static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3]
             const uint64_t half = n / 2;
             Fr *Ao = dst.as<Fr>(), *Bo = Ao + half, *Co = Bo + half;
             launch_prod3_round(true, full, Ac, Bc, Cc, Ao, Bo, Co, rc, half / 2, ctx->ws, ctx->slot_dev(s), s, ctx->stream,
-                               dev_out);
+                               dev_out, f64 ? &rf : nullptr, ctx->f64_folds);
             ctx->end_launch(half / 2 >= kTailPairs ? KC_PROD3_FUSED : KC_PROD3_TAIL, 96.0 * n + 96.0 * half);
             Ac = Ao; Bc = Bo; Cc = Co;
             n = half;

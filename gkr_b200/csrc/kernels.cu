@@ -2,215 +2,33 @@
 // Tables are arrays of 32-byte Montgomery elements; every table access is a pair of 128-bit loads.
 // Reductions: per-thread accumulators -> warp shuffles -> shared-memory tree -> per-CTA partials ->
 // last CTA (ticket) sums the partials and publishes canonical values to a device-mapped host slot.
-#include <cuda_runtime.h>
+// (The degree-3 product rounds and the multiplier benchmark live in kernels_prod3.cu.)
+#include <atomic>
+#include <mutex>
 
-#include "kernels.cuh"
+#include "kernels_common.cuh"
 
 namespace gkr {
 
-#ifndef GKR_FOLD_PREFETCH
-#define GKR_FOLD_PREFETCH 0       // experiment: L2 prefetch of the next iteration in the fused degree-2 rounds too
-#endif
-#ifndef GKR_LOAD_AHEAD
-#define GKR_LOAD_AHEAD 0          // experiment: issue the W and H loads of a fused degree-2 pair before any arithmetic
-#endif
-#ifndef GKR_PROD3_PAIRS
-#define GKR_PROD3_PAIRS 1         // pairs per loop iteration and thread in the degree-3 kernel (2 => 1 CTA/SM, 255 registers)
-#endif
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-
-// ------------------------------------------------------------------------------------------------
-// 128-bit table access
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ Fr ld_fr(const Fr *p) {
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    uint4 lo = __ldg(q), hi = __ldg(q + 1);
-    Fr r;
-    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
-    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
-    return r;
-}
-// coherent (L2) load for data written earlier in the same kernel by other CTAs
-__device__ __forceinline__ Fr ld_fr_cg(const Fr *p) {
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
-    Fr r;
-    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
-    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
-    return r;
-}
-__device__ __forceinline__ void st_fr(Fr *p, const Fr &v) {
-    uint4 *q = reinterpret_cast<uint4 *>(p);
-    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-}
-
-// pull the cache lines of a future iteration towards L2 (no register cost)
-__device__ __forceinline__ void prefetch_l2(const Fr *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// lo + r * (hi - lo), r given by its constant-multiplier table (kernel parameter => constant bank operands)
-template <class KT>
-__device__ __forceinline__ Fr fold2(const Fr &lo, const Fr &hi, const KT &r) {
-    return fr_add(lo, fr_mul_const(fr_sub(hi, lo), r));
-}
-
-// constant-multiplier table received through a HostCmd (shared memory copy of its 80 raw words)
-struct CmdConst {
-    const uint32_t *raw;
-    __device__ __forceinline__ uint32_t get(int j, int i) const {
-        const int p = 8 * j + i;
-        return raw[(p / 15) * 16 + (p % 15)];
-    }
-};
-__device__ __forceinline__ uint32_t ld_sys(const volatile uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// Warp 0 polls the command block until all five line tags equal `tag` (or an abort tag / timeout shows up),
-// then leaves the 80 raw words in shared memory.  Returns false on abort or timeout.
-__device__ __forceinline__ bool wait_cmd(const HostCmd *cmd, uint32_t tag, uint32_t *raw_smem, int *ok_smem) {
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int ok = 0;
-        for (uint32_t spin = 0; spin < (1u << 24); ++spin) {       // ~30 s, then give up loudly
-            const uint32_t v0 = ld_sys(&cmd->w[lane]);
-            const uint32_t v1 = ld_sys(&cmd->w[32 + lane]);
-            const uint32_t v2 = lane < 16 ? ld_sys(&cmd->w[64 + lane]) : tag;
-            const bool is_tag_lane = (lane & 15) == 15;
-            const bool good = !is_tag_lane || (v0 == tag && v1 == tag && v2 == tag);
-            const bool abort = is_tag_lane && (v0 == kCmdAbort || v1 == kCmdAbort || v2 == kCmdAbort);
-            if (__any_sync(0xffffffffu, abort)) break;
-            if (__all_sync(0xffffffffu, good)) {
-                raw_smem[lane] = v0;
-                raw_smem[32 + lane] = v1;
-                if (lane < 16) raw_smem[64 + lane] = v2;
-                ok = 1;
-                break;
-            }
-            __nanosleep(200);
-        }
-        if (lane == 0) *ok_smem = ok;
-    }
-    __syncthreads();
-    return *ok_smem != 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// reductions
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ Fr warp_sum(Fr v) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        Fr o;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o.l[i] = __shfl_xor_sync(0xffffffffu, v.l[i], off);
-        v = fr_add(v, o);
-    }
-    return v;
-}
-
-// Sum K accumulators over the CTA; result valid in thread 0.
-template <int K>
-__device__ __forceinline__ void block_sum(Fr (&acc)[K], Fr (*smem)[kWarps]) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        Fr w = warp_sum(acc[j]);
-        if (lane == 0) smem[j][warp] = w;
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        const int nw = blockDim.x >> 5;
-        for (int j = 0; j < K; ++j) {
-            Fr v = lane < nw ? smem[j][lane] : fr_zero();
-            acc[j] = warp_sum(v);
-        }
-    }
-    __syncthreads();
-}
-
-// Grid-wide sum of K accumulators; the last CTA to arrive publishes the canonical totals.
-// If dev_out != nullptr (multi-GPU: the totals still have to be combined across ranks) the last CTA
-// stores the Montgomery totals there and nothing is published to the host.
-// second half of grid_sum_publish: thread 0 of every CTA holds the CTA totals in acc
-template <int K>
-__device__ __forceinline__ void grid_publish_cta_totals(Fr (&acc)[K], Fr (*red)[kWarps], Fr *partials, unsigned int *counter,
-                                                        HostSlot *slot, uint32_t seq, uint32_t aux0, Fr *dev_out = nullptr) {
-    __shared__ bool is_last;
-    if (gridDim.x > 1) {
-        if (threadIdx.x == 0) {
-#pragma unroll
-            for (int j = 0; j < K; ++j) st_fr(&partials[(size_t)blockIdx.x * K + j], acc[j]);
-            __threadfence();
-            unsigned int ticket = atomicAdd(counter, 1u);
-            is_last = (ticket == gridDim.x - 1);
-        }
-        __syncthreads();
-        if (!is_last) return;
-        __threadfence();
-#pragma unroll
-        for (int j = 0; j < K; ++j) acc[j] = fr_zero();
-        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-#pragma unroll
-            for (int j = 0; j < K; ++j) acc[j] = fr_add(acc[j], ld_fr_cg(&partials[(size_t)b * K + j]));
-        }
-        block_sum<K>(acc, red);
-        if (threadIdx.x == 0) *counter = 0;
-    }
-    // single-CTA launches (small tables) skip the partials / ticket round trip entirely
-    if (threadIdx.x == 0 && dev_out != nullptr) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) st_fr(&dev_out[j], acc[j]);
-        return;
-    }
-    if (threadIdx.x == 0) {
-        // totals are published in Montgomery form (the host shares the representation); aux[1] = non-zero mask
-        uint32_t nz = 0;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            nz |= fr_is_zero(acc[j]) ? 0u : (1u << j);
-            st_fr(&slot->v[j], acc[j]);
-        }
-        slot->aux[0] = aux0;
-        slot->aux[1] = nz;
-        slot->aux[2] = 0;
-        __threadfence_system();
-        slot->seq = seq;
-    }
-}
-template <int K>
-__device__ __forceinline__ void grid_sum_publish(Fr (&acc)[K], Fr *partials, unsigned int *counter,
-                                                 HostSlot *slot, uint32_t seq, uint32_t aux0, Fr *dev_out = nullptr) {
-    __shared__ Fr red[K][kWarps];
-    block_sum<K>(acc, red);
-    grid_publish_cta_totals<K>(acc, red, partials, counter, slot, seq, aux0, dev_out);
-}
-
-static inline int grid_for(uint64_t work_items, int max_blocks) {
-    uint64_t b = (work_items + kThreads - 1) / kThreads;
-    if (b < 1) b = 1;
-    if (b > (uint64_t)max_blocks) b = (uint64_t)max_blocks;
-    return (int)b;
-}
-
-static int g_sm_count = 0;
+// Per-device facts and one-time function attributes.  A process may drive several devices from several threads
+// (one gkr_ctx per thread, include/gkr_b200.h): nothing here may be cached for "the first device" only.
+namespace {
+constexpr int kMaxDevices = 64;
+std::atomic<int> g_sm_count[kMaxDevices];
+std::once_flag g_dev_once[kMaxDevices];
+int g_dev_init_rc[kMaxDevices];
+}  // namespace
 int device_sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) dev = 0;
+    int n = g_sm_count[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_sm_count[dev].store(n, std::memory_order_relaxed);
     }
-    return g_sm_count;
+    return n;
 }
-// grid for streaming (non-reducing) kernels: a multiple of the SM count, grid-stride loop inside
-static inline int stream_grid(uint64_t work_items) { return grid_for(work_items, device_sm_count() * 8); }
-
 // ------------------------------------------------------------------------------------------------
 // conversions / generators
 // ------------------------------------------------------------------------------------------------
@@ -656,7 +474,7 @@ __device__ __forceinline__ void gkr_poly_body(const Fr *__restrict__ Hin, const 
                                               uint64_t q4, Fr *partials, unsigned int *counter, HostSlot *slot,
                                               uint32_t seq) {
     __shared__ Fr sh[3][4][kPolyChunk];
-    __shared__ Fr red[6][kWarps];
+    __shared__ Fr red[6][kMaxWarps];
     __shared__ Fr wred[kWarps][2];
     const uint32_t t = threadIdx.x, s = t / kPolyChunk, il = t % kPolyChunk;
     Fr accA = fr_zero(), accB = fr_zero();
@@ -731,7 +549,7 @@ __device__ __forceinline__ void gkr_poly2_body(const Fr *__restrict__ Hin, const
                                                Fr *__restrict__ Wout, Fr *__restrict__ Aout, const KT &r,
                                                uint64_t q4, Fr *partials, unsigned int *counter, HostSlot *slot,
                                                uint32_t seq) {
-    __shared__ Fr red[6][kWarps];
+    __shared__ Fr red[6][kMaxWarps];
     __shared__ Fr wred[kWarps][2][3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t odd = lane & 1;
@@ -956,13 +774,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_gkr_poly_tail_cmd(PolyTailArgs a
     }
 }
 void launch_gkr_poly_tail(const PolyTailArgs &a, cudaStream_t s) {
-    static bool once = false;
-    const size_t max_smem = (size_t)(4 * kTailQuads) * 144;
-    if (!once) {
-        cudaFuncSetAttribute(k_gkr_poly_tail_cmd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        cudaFuncSetAttribute(k_gkr_poly_tail_cmd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-        once = true;
-    }
     const uint64_t n_first = a.N >> (a.u0 - 1);
     const unsigned threads = (unsigned)((n_first + 31) / 32 * 32);           // 4 threads per quad = 1 per entry
     const size_t smem = (size_t)n_first * 144;                              // (3 n + 3 n / 2) * 32 B
@@ -980,10 +791,11 @@ void launch_gkr_poly(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout,
         return (uint64_t)1 << (e ? atoi(e) : 13);
     }();
     if (!cmd && quads >= poly2_min) {
-        static const int cap2 = [] {                         // experiment knob: CTAs per SM for the two-thread form
+        static const int per_sm2 = [] {                      // experiment knob: CTAs per SM for the two-thread form
             const char *e = getenv("GKR_POLY2_CTAS_PER_SM");
-            return device_sm_count() * (e ? atoi(e) : 2);     // one resident wave (2 vs 4 per SM: 25.25 vs 25.37 ms per proof)
+            return e ? atoi(e) : 2;                           // one resident wave (2 vs 4 per SM: 25.25 vs 25.37 ms per proof)
         }();
+        const int cap2 = device_sm_count() * per_sm2;
         const int grid2 = grid_for(2 * quads, cap2 < ws.max_blocks ? cap2 : ws.max_blocks);
         if (fold) k_gkr_poly2<true><<<grid2, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
         else k_gkr_poly2<false><<<grid2, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
@@ -1027,13 +839,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_gkr_round_cmd(const Fr *__restr
     gkr_round_body<true, FULL, false>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq);
 }
 
-// lazy accumulation pays once a thread sees several pairs: fewer, fatter CTAs (2 resident per SM)
-static inline bool use_lazy(uint64_t pairs) { return pairs >= ((uint64_t)1 << 20); }
-static inline int round_grid(uint64_t pairs, const ReduceWs &ws) {
-    const int cap = use_lazy(pairs) ? device_sm_count() * (GKR_PROD3_PAIRS == 2 ? 1 : 2) : ws.max_blocks;
-    return grid_for(pairs, cap < ws.max_blocks ? cap : ws.max_blocks);
-}
-
 // the degree-2 GKR round is light on multiplies (memory/latency-bound): the lazy variant's per-thread
 // reduction epilogue only pays for very large tables
 static inline bool use_lazy_gkr(uint64_t pairs) { return pairs >= ((uint64_t)1 << 21); }
@@ -1061,128 +866,6 @@ void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *
     } else {
         if (full) launch_gkr_round_t<false, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, dev_out);
         else launch_gkr_round_t<false, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, dev_out);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// product-of-three sumcheck round, degree 3 (generic prove_sumcheck, rust/src/gkr/sumcheck.rs:158-214).
-// Published: v[0] = g(0), v[1] = g(-1), v[2] = g(inf) = X^3 coefficient, v[3] = g(1) (FULL only; otherwise
-// the host uses g(1) = claim - g(0)).  The host interpolates the four coefficients.
-// ------------------------------------------------------------------------------------------------
-template <bool FOLD, bool FULL, bool LAZY>
-__global__ void __launch_bounds__(kThreads, GKR_PROD3_PAIRS == 2 ? 1 : 2)
-    k_prod3_round(const Fr *__restrict__ Ain, const Fr *__restrict__ Bin, const Fr *__restrict__ Cin, Fr *__restrict__ Aout,
-                  Fr *__restrict__ Bout, Fr *__restrict__ Cout, FrConstMul r, uint64_t q, Fr *partials,
-                  unsigned int *counter, HostSlot *slot, uint32_t seq, Fr *dev_out) {
-    constexpr int K = FULL ? 4 : 3;
-    constexpr int NP = GKR_PROD3_PAIRS;
-    Fr acc[K];
-    FrWide wide[LAZY ? K : 1];
-#pragma unroll
-    for (int j = 0; j < K; ++j) acc[j] = fr_zero();
-    if (LAZY) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) wide_zero(wide[j]);
-    }
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i0 < q; i0 += NP * stride) {
-        if (!FOLD) {
-            const uint64_t nx = i0 + NP * stride;
-            if (nx < q) {
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    prefetch_l2(Ain + nx + t * q);
-                    prefetch_l2(Bin + nx + t * q);
-                    prefetch_l2(Cin + nx + t * q);
-                }
-            }
-        }
-        // stage 1 for every pair of this iteration, then stage 2: independent instruction streams side by side
-        Fr t0[NP], tm[NP], tinf[NP], t1[NP];
-        bool live[NP];
-#pragma unroll
-        for (int u = 0; u < NP; ++u) {
-            const uint64_t i = i0 + u * stride;
-            live[u] = i < q;
-            if (!live[u]) continue;
-            Fr a0, a1, b0, b1;
-            if (FOLD) {
-                a0 = fold2(ld_fr(Ain + i), ld_fr(Ain + i + 2 * q), r);
-                a1 = fold2(ld_fr(Ain + i + q), ld_fr(Ain + i + 3 * q), r);
-                st_fr(Aout + i, a0);
-                st_fr(Aout + i + q, a1);
-                b0 = fold2(ld_fr(Bin + i), ld_fr(Bin + i + 2 * q), r);
-                b1 = fold2(ld_fr(Bin + i + q), ld_fr(Bin + i + 3 * q), r);
-                st_fr(Bout + i, b0);
-                st_fr(Bout + i + q, b1);
-            } else {
-                a0 = ld_fr(Ain + i); a1 = ld_fr(Ain + i + q);
-                b0 = ld_fr(Bin + i); b1 = ld_fr(Bin + i + q);
-            }
-            t0[u] = fr_mul(a0, b0);
-            const Fr da = fr_sub(a1, a0), db = fr_sub(b1, b0);
-            tinf[u] = fr_mul(da, db);
-            if (FULL) {
-                // three products serve all four points: with X = a0 b1 + a1 b0 = t0 + t1 - tinf,
-                // (a0 - da)(b0 - db) = (2a0 - a1)(2b0 - b1) = 4 t0 - 2 X + t1 = 2 t0 - t1 + 2 tinf
-                t1[u] = fr_mul(a1, b1);
-                tm[u] = fr_add(fr_sub(fr_dbl(t0[u]), t1[u]), fr_dbl(tinf[u]));
-            } else {
-                tm[u] = fr_mul(fr_sub(a0, da), fr_sub(b0, db));      // value at X = -1 : lo - d
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < NP; ++u) {
-            const uint64_t i = i0 + u * stride;
-            if (!live[u]) continue;
-            Fr c0, c1;
-            if (FOLD) {
-                c0 = fold2(ld_fr(Cin + i), ld_fr(Cin + i + 2 * q), r);
-                c1 = fold2(ld_fr(Cin + i + q), ld_fr(Cin + i + 3 * q), r);
-                st_fr(Cout + i, c0);
-                st_fr(Cout + i + q, c1);
-            } else {
-                c0 = ld_fr(Cin + i); c1 = ld_fr(Cin + i + q);
-            }
-            const Fr dc = fr_sub(c1, c0);
-            if (LAZY) {
-                wide_mac(wide[0], t0[u], c0);
-                wide_mac(wide[1], tm[u], fr_sub(c0, dc));
-                wide_mac(wide[2], tinf[u], dc);
-                if (FULL) wide_mac(wide[K - 1], t1[u], c1);
-            } else {
-                acc[0] = fr_add(acc[0], fr_mul(t0[u], c0));
-                acc[1] = fr_add(acc[1], fr_mul(tm[u], fr_sub(c0, dc)));
-                acc[2] = fr_add(acc[2], fr_mul(tinf[u], dc));
-                if (FULL) acc[K - 1] = fr_add(acc[K - 1], fr_mul(t1[u], c1));
-            }
-        }
-    }
-    if (LAZY) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) acc[j] = wide_reduce(wide[j]);
-    }
-    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, dev_out);
-}
-template <bool FOLD, bool FULL>
-static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const FrConstMul &r,
-                                 uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, Fr *dev_out,
-                                 cudaStream_t s) {
-    const int grid = round_grid(pairs, ws);
-    if (use_lazy(pairs))
-        k_prod3_round<FOLD, FULL, true><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq, dev_out);
-    else
-        k_prod3_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq, dev_out);
-}
-void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
-                        const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s,
-                        Fr *dev_out) {
-    if (fold) {
-        if (full) launch_prod3_round_t<true, true>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, dev_out, s);
-        else launch_prod3_round_t<true, false>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, dev_out, s);
-    } else {
-        if (full) launch_prod3_round_t<false, true>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, dev_out, s);
-        else launch_prod3_round_t<false, false>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, dev_out, s);
     }
 }
 
@@ -1343,11 +1026,6 @@ void launch_mobius(Fr *table, uint32_t k, cudaStream_t s) {
     if (k == 0) return;
     const uint32_t low = k < (uint32_t)kMobTile ? k : (uint32_t)kMobTile;
     const size_t smem = (size_t)32 << low;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_mobius_low, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMobTile);
-        attr_set = true;
-    }
     k_mobius_low<<<(unsigned)(((uint64_t)1 << k) >> low), kThreads, smem, s>>>(table, low);
     const uint64_t half = ((uint64_t)1 << k) / 2;
     for (uint32_t st = low; st < k; ++st) k_mobius_stage<<<stream_grid(half), kThreads, 0, s>>>(table, st, half);
@@ -1431,58 +1109,17 @@ void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const 
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// integer-pipe ceiling: back-to-back Montgomery products, ILP independent chains per thread
-// ------------------------------------------------------------------------------------------------
-// MODE 0: fr_mul chains; 1: fr_mul_const chains (constant-bank operands); 2: wide_mac into one accumulator
-template <int ILP, int MODE>
-__global__ void __launch_bounds__(kThreads) k_mul_bench(Fr *out, int iters, FrConstMul K) {
-    Fr x[ILP], y = fr_one();
-    y.l[0] ^= threadIdx.x * 2654435761u;
-    y.l[3] ^= blockIdx.x;
-    FrWide w;
-    wide_zero(w);
-#pragma unroll
-    for (int j = 0; j < ILP; ++j) { x[j] = y; x[j].l[1] += j + 1; }
-    for (int it = 0; it < iters; ++it) {
-#pragma unroll
-        for (int j = 0; j < ILP; ++j) {
-            if (MODE == 0) x[j] = fr_mul(x[j], y);
-            else if (MODE == 1) x[j] = fr_mul_const(x[j], K);
-            else { wide_mac(w, x[j], y); x[j].l[0] += w.l[3]; }
-        }
-    }
-    Fr acc = x[0];
-#pragma unroll
-    for (int j = 1; j < ILP; ++j) acc = fr_add(acc, x[j]);
-    if (MODE == 2) acc = fr_add(acc, wide_reduce(w));
-    if (acc.l[7] == 0xffffffffu) st_fr(out + (blockIdx.x * (size_t)blockDim.x + threadIdx.x), acc);   // never true: values < p
-}
-double run_mul_bench(int ilp, int blocks_per_sm, int iters, Fr *scratch, cudaStream_t s, int mode) {
-    const int grid = device_sm_count() * blocks_per_sm;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    FrConstMul K;
-    for (int j = 0; j < 8; ++j)
-        for (int i = 0; i < 8; ++i) K.c[j][i] = 0x9e3779b9u * (8 * j + i + 1);
-    for (int j = 0; j < 8; ++j) K.c[j][7] &= 0x0fffffffu;
-    const int eff_ilp = ilp == 1 ? 1 : ilp == 2 ? 2 : 4;
-    for (int rep = 0; rep < 2; ++rep) {
-        cudaEventRecord(e0, s);
-#define GKR_BENCH_LAUNCH(I, M) k_mul_bench<I, M><<<grid, kThreads, 0, s>>>(scratch, iters, K)
-        if (mode == 0) { if (eff_ilp == 1) GKR_BENCH_LAUNCH(1, 0); else if (eff_ilp == 2) GKR_BENCH_LAUNCH(2, 0); else GKR_BENCH_LAUNCH(4, 0); }
-        else if (mode == 1) { if (eff_ilp == 1) GKR_BENCH_LAUNCH(1, 1); else if (eff_ilp == 2) GKR_BENCH_LAUNCH(2, 1); else GKR_BENCH_LAUNCH(4, 1); }
-        else { if (eff_ilp == 1) GKR_BENCH_LAUNCH(1, 2); else if (eff_ilp == 2) GKR_BENCH_LAUNCH(2, 2); else GKR_BENCH_LAUNCH(4, 2); }
-#undef GKR_BENCH_LAUNCH
-        cudaEventRecord(e1, s);
-        cudaEventSynchronize(e1);
-    }
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    return (double)grid * kThreads * eff_ilp * (double)iters / (ms * 1e-3);
+// cudaFuncSetAttribute is per device: run once for every device a context is created on (gkr_ctx_create)
+int kernels_device_init(int device) {
+    if (device < 0 || device >= kMaxDevices) return (int)cudaErrorInvalidDevice;
+    std::call_once(g_dev_once[device], [device] {
+        const int tail_smem = (4 * kTailQuads) * 144;
+        cudaError_t e = cudaFuncSetAttribute(k_gkr_poly_tail_cmd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gkr_poly_tail_cmd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mobius_low, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMobTile);
+        g_dev_init_rc[device] = (int)e;
+    });
+    return g_dev_init_rc[device];
 }
 
 }  // namespace gkr

@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "fr.cuh"
+#include "fr_f64.cuh"
 
 namespace gkr {
 
@@ -102,9 +103,12 @@ int gkr_poly_tail_max_quads();
 void launch_take_strided(const Fr *in, Fr *out, uint64_t first, uint64_t stride, uint64_t n, cudaStream_t s);
 // product-of-3 round (degree 3).  Publishes v[0] = g(0), v[1] = g(-1), v[2] = g(inf) (= X^3 coefficient) and
 // v[3] = g(1) when full == true.
+// rf != nullptr and nf in 2..6: that many of the six folds of a pair run on the FP64 pipe (streaming fused rounds only,
+// see prod3_round_wants_f64); the published values are bit-identical either way.
 void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
                         const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
-                        cudaStream_t s, Fr *dev_out = nullptr);
+                        cudaStream_t s, Fr *dev_out = nullptr, const FrFoldF64 *rf = nullptr, int nf = 0);
+bool prod3_round_wants_f64(bool fold, bool full, uint64_t pairs);
 // multi-GPU: sum the per-rank partial totals (rank-major, Montgomery) and publish; gathered final entries -> tables
 void launch_sum_ranks_publish(const Fr *gathered, int n_ranks, int count, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
 void launch_interleave_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_tables, uint64_t m, cudaStream_t s);
@@ -136,7 +140,13 @@ void launch_wiring_eval(const uint8_t *type, const uint32_t *left, const uint32_
 // publishes v[0] = sum_i X[i] * Y[i]
 void launch_dot(const Fr *X, const Fr *Y, uint64_t n, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
 
-int device_sm_count();
+// device self-test (see kernels_prod3.cu): failures2[0] counts threads whose lazy accumulation diverged from the
+// Montgomery sums, failures2[1] threads whose FP64-pipe fold differed from the integer fold
+void launch_selftest(uint32_t iters, const FrConstMul &r, const FrFoldF64 &rf, unsigned int *failures2, cudaStream_t s);
+
+int device_sm_count();            // of the calling thread's current device
+// one-time per-device setup (function attributes); the current device must be `device`.  Returns a cudaError_t value.
+int kernels_device_init(int device);
 
 // field multiplications per second with `ilp` independent chains per thread and blocks_per_sm CTAs of 256 threads
 // mode 0: fr_mul, 1: fr_mul_const, 2: wide_mac (lazy 512-bit multiply-accumulate)

@@ -76,6 +76,8 @@ inline Fr to_dev(const HFr &h) {      // identical Montgomery representation: pl
 }
 // constant-multiplier table of r for fr_mul_const: C_j = r * 2^(32 j + 64) mod p as plain integers
 FrConstMul make_const_mul(const HFr &r);
+// constants of the same challenge for the FP64-pipe fold (fr_f64.cuh)
+FrFoldF64 make_fold_f64(const HFr &r);
 inline HFr to_host(const Fr &f) {
     HFr h;
     std::memcpy(h.l, f.l, 32);
@@ -85,6 +87,7 @@ inline HFr to_host(const Fr &f) {
 // process-wide pool of pinned host buffers (proof tables are handed to the caller in pinned memory so
 // the device can write them asynchronously; cudaHostAlloc is far too slow to call per proof)
 int comm_all_gather(gkr_ctx *ctx, const void *send, void *recv, size_t bytes);   // on ctx->stream
+int default_f64_folds();       // GKR_F64_FOLDS, else the built-in default
 void *pinned_get(size_t bytes);
 void pinned_put(void *ptr, size_t bytes);
 
@@ -109,6 +112,7 @@ struct gkr_ctx {
     gkr::HostCmd *cmds_host = nullptr;     // pinned + mapped: challenge tables for pre-launched round kernels
     gkr::HostCmd *cmds_dev = nullptr;
     bool lookahead = true;                 // look-ahead rounds: next message as a polynomial in the pending challenge
+    int f64_folds = gkr::default_f64_folds();   // option "f64_folds": folds per pair on the FP64 pipe in streaming rounds
     bool prelaunch = true;                 // pre-launch the small-table rounds of a phase (option "prelaunch")
     int prelaunched_pending = 0;           // launched kernels still waiting for their challenge (see wait_slot)
     uint32_t seq = 0;

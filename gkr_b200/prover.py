@@ -335,6 +335,13 @@ class Prover:
         _lib.check(self._L.gkr_bench_field_mul(self._ctx, ilp, blocks_per_sm, iters, C.byref(out)))
         return out.value
 
+    def selftest(self, iters: int = 400, r=None):
+        """device self-test (gkr_selftest): returns (lazy-accumulation failures, FP64-fold failures); both must be 0"""
+        out = (C.c_uint32 * 2)()
+        rb = as_fr_array(ints_to_fr([r])) if r is not None else None
+        _lib.check(self._L.gkr_selftest(self._ctx, iters, _vp(rb) if rb is not None else None, out))
+        return out[0], out[1]
+
     def profile(self, enable: int = -1) -> dict:
         """enable = 1 / 0 switches per-kernel CUDA-event timing on / off (and clears the counters);
         -1 only reads.  Returns the counters accumulated so far, per kernel class."""

@@ -230,6 +230,16 @@ int gkr_ctx_profile(gkr_ctx *ctx, int enable, gkr_profile *out);
  * product -- or 32 to time wide_mac, the unreduced 512-bit multiply-accumulate; blocks_per_sm CTAs of 256 threads) */
 int gkr_bench_field_mul(gkr_ctx *ctx, int ilp, int blocks_per_sm, int iters, double *mul_per_second);
 
+/* device self-test of the arithmetic identities the round kernels rely on: failures2[0] = threads whose lazy 512-bit
+ * accumulation diverged from the sum of Montgomery products within `iters` products (pseudo-random and maximal
+ * operands, checked after every product), failures2[1] = threads whose FP64-pipe fold differed from the integer-pipe
+ * fold for the challenge r (NULL: a fixed one).  Both must be 0. */
+int gkr_selftest(gkr_ctx *ctx, uint32_t iters, const gkr_fr *r, uint32_t *failures2);
+
+/* diagnostic: the 11 x 11 constants the FP64-pipe fold uses for the challenge r (row-major: out[11 i + j] = balanced
+ * base-2^24 digit j of the centred representative of r * 2^(24 i) mod p).  Host only; needs no device. */
+int gkr_fold_f64_constants(const gkr_fr *r, double *out121);
+
 #ifdef __cplusplus
 }
 #endif

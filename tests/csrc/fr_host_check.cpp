@@ -49,3 +49,22 @@ extern "C" int frh_mul_const(const unsigned char *consts /*8x32*/, const unsigne
     }
     return 0;
 }
+
+// lo + r*(hi - lo) through the FP64-pipe fold (fr_f64.cuh, host emulation of the same exact double arithmetic);
+// consts = 11 x 11 doubles: balanced base-2^24 digits of the centred representatives of r * 2^(24 i) mod p
+#include "../../gkr_b200/csrc/fr_f64.cuh"
+extern "C" int frh_fold_f64(const double *consts, const unsigned char *lo, const unsigned char *hi, unsigned char *out,
+                            unsigned long n) {
+    FrFoldF64 K{};
+    for (int i = 0; i < 11; ++i)
+        for (int j = 0; j < 11; ++j) K.c[i][j] = consts[11 * i + j];
+    for (unsigned long i = 0; i < n; ++i) {
+        Fr a, b;
+        std::memcpy(a.l, lo + 32 * i, 32);
+        std::memcpy(b.l, hi + 32 * i, 32);
+        if (!fr_is_canonical(a) || !fr_is_canonical(b)) return -1;
+        const Fr r = fold2_f64(a, b, K);
+        std::memcpy(out + 32 * i, r.l, 32);
+    }
+    return 0;
+}

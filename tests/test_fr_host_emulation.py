@@ -17,7 +17,8 @@ def _lib():
     so = os.path.join(HERE, "csrc", "libfr_host_check.so")
     src = os.path.join(HERE, "csrc", "fr_host_check.cpp")
     hdr = os.path.join(HERE, "..", "gkr_b200", "csrc", "fr.cuh")
-    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+    hdr2 = os.path.join(HERE, "..", "gkr_b200", "csrc", "fr_f64.cuh")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)) > os.path.getmtime(so):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
     return C.CDLL(so)
 

@@ -88,6 +88,59 @@ def test_paranoid_mode_and_lazy_path(pv):
     pp.close()
 
 
+def test_device_selftest(pv):
+    """lazy 512-bit accumulation == Montgomery sums after every one of 600 products per thread (random and maximal
+    operands), FP64-pipe fold == integer fold: the identities behind the streaming kernels, checked on the device"""
+    rng = random.Random(5)
+    assert pv.selftest(600) == (0, 0)
+    for r in (0, 1, P - 1, rng.randrange(P), rng.randrange(P)):
+        assert pv.selftest(64, r) == (0, 0)
+
+
+@pytest.mark.parametrize("v", [24])
+def test_streaming_sizes_against_dense_oracle(pv, v):
+    """BASELINE.json config 4 at 2^24: more than 100 products per thread go through one lazy accumulator in the first
+    rounds (round 1 of this build got exactly this wrong: the accumulator's reduction dropped a carry once its upper
+    words filled up, and nothing checked sizes above 2^21).  Oracle equality + the verifier's chain + the final check."""
+    tabs = [pv.dev_table_synth(1, syn.TABLE_STREAM + t, 1 << v) for t in range(3)]
+    got = pv.sumcheck_prod(tabs, v)
+    host = [orc.synth_values(1, syn.TABLE_STREAM + t, 1 << v) for t in range(3)]
+    want = orc.sumcheck_prod(host, v)
+    assert got == want
+    msgs, chal, fin = got
+    claim = (verifier.horner(msgs[0], 0) + verifier.horner(msgs[0], 1)) % P
+    for m, r in zip(msgs, chal):
+        assert (verifier.horner(m, 0) + verifier.horner(m, 1)) % P == claim
+        assert l0.multi_hash(m, 0) == r
+        claim = verifier.horner(m, r)
+    assert claim == fin[0] * fin[1] % P * fin[2] % P
+
+
+@pytest.mark.parametrize("nf", [3, 4, 6])
+def test_fp64_pipe_folds_are_bit_identical(pv, nf):
+    """option f64_folds: nf of the six folds of a pair run on the FP64 pipe (fr_f64.cuh) in the streaming rounds.
+    2^23 entries: rounds 2 and 3 use those kernels.  Every output must equal the integer-pipe run, which the tests
+    above tie to the oracle; the claim chain is re-checked on the host as well."""
+    from gkr_b200 import Prover
+    v, seed = 23, 5
+    tabs = [pv.dev_table_synth(seed, syn.TABLE_STREAM + t, 1 << v) for t in range(3)]
+    pv.set_option("f64_folds", 0)
+    want = pv.sumcheck_prod(tabs, v)
+    pf = Prover(0)
+    pf.set_option("f64_folds", nf)
+    tabs_f = [pf.dev_table_synth(seed, syn.TABLE_STREAM + t, 1 << v) for t in range(3)]
+    got = pf.sumcheck_prod(tabs_f, v)
+    pf.close()
+    assert got == want
+    msgs, chal, fin = got
+    claim = (verifier.horner(msgs[0], 0) + verifier.horner(msgs[0], 1)) % P
+    for m, r in zip(msgs, chal):
+        assert (verifier.horner(m, 0) + verifier.horner(m, 1)) % P == claim
+        assert l0.multi_hash(m, 0) == r
+        claim = verifier.horner(m, r)
+    assert claim == fin[0] * fin[1] % P * fin[2] % P
+
+
 def test_rejects_unsupported(pv):
     from gkr_b200._lib import GkrError
     t = ints_to_fr([1, 2])
