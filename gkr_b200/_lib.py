@@ -65,7 +65,7 @@ class Profile(C.Structure):
 # every symbol include/gkr_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "gkr_ctx_create", "gkr_ctx_destroy", "gkr_ctx_stream", "gkr_ctx_sync", "gkr_ctx_set_option", "gkr_last_error", "gkr_version", "gkr_mimc7_multi_hash", "gkr_mimc7_hash", "gkr_mimc7_round_constant",
-    "gkr_frontend_compile", "gkr_frontend_n_circuits", "gkr_frontend_n_public", "gkr_frontend_circuit", "gkr_frontend_destroy",
+    "gkr_frontend_compile", "gkr_frontend_compile_sym", "gkr_frontend_n_outputs", "gkr_frontend_output", "gkr_frontend_n_circuits", "gkr_frontend_n_public", "gkr_frontend_circuit", "gkr_frontend_destroy",
     "gkr_circuit_create", "gkr_circuit_destroy", "gkr_witness_create", "gkr_witness_eval", "gkr_witness_layer",
     "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_verify", "gkr_sumcheck_prod", "gkr_dev_table_synth", "gkr_dev_table_synth_strided", "gkr_comm_unique_id", "gkr_comm_init", "gkr_comm_destroy",
     "gkr_sumcheck_prod_sharded",
@@ -107,6 +107,11 @@ def lib():
     L.gkr_mimc7_hash.argtypes = [vp, vp, vp]
     L.gkr_mimc7_round_constant.argtypes = [u32, vp]
     L.gkr_frontend_compile.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]
+    if hasattr(L, "gkr_frontend_compile_sym"):
+        L.gkr_frontend_compile_sym.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(vp)]
+        L.gkr_frontend_n_outputs.argtypes = [vp]
+        L.gkr_frontend_n_outputs.restype = u32
+        L.gkr_frontend_output.argtypes = [vp, u32, C.POINTER(u32), vp, C.POINTER(C.c_char_p)]
     L.gkr_frontend_n_circuits.argtypes = [vp]
     L.gkr_frontend_n_circuits.restype = u32
     L.gkr_frontend_n_public.argtypes = [vp]

@@ -36,14 +36,16 @@ class ProverPool:
         layers, input_values = job
         pv = self._prover()
         c = pv.circuit(layers)
-        w = pv.witness_eval(c, input_values)
+        w = None
         try:
+            w = pv.witness_eval(c, input_values)
             if raw:                                  # proof produced in the library's own memory and released
                 pv.free_raw(pv.prove_raw(c, w))
                 return None
             return pv.prove(c, w)
         finally:
-            w.close()
+            if w is not None:
+                w.close()
             c.close()
 
     def prove_many(self, jobs, raw: bool = False) -> list:

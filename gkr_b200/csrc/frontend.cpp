@@ -63,8 +63,9 @@ const U256 kMinusOne = neg_mod_p(kOne);
 struct Reader {
     const uint8_t *p;
     size_t n, off = 0;
-    void need(size_t k) const {
-        if (off + k > n) throw FrontendError("truncated file");
+    void need(uint64_t k) const {
+        // off <= n is an invariant; written so that a 64-bit size taken from the file cannot wrap the comparison
+        if (off > n || k > (uint64_t)(n - off)) throw FrontendError("truncated file");
     }
     uint32_t u32() {
         need(4);
@@ -98,9 +99,9 @@ Sections read_sections(const uint8_t *data, size_t len, const char *magic, uint3
     for (uint32_t i = 0; i < n_sections; ++i) {
         const uint32_t ty = r.u32();
         const uint64_t size = r.u64();
-        r.need(size);
+        r.need(size);                                                      // rejects sizes beyond the end of the file
         out.emplace(ty, std::make_pair(data + r.off, (size_t)size));       // first section of a type wins
-        r.off += size;
+        r.off += (size_t)size;
     }
     return out;
 }
@@ -123,10 +124,14 @@ R1cs parse_r1cs(const uint8_t *data, size_t len) {
     h.u64();
     const uint32_t n_constraints = h.u32();
     Reader b{secs.at(2).first, secs.at(2).second};
+    // counts come from the file: bound them by what the section can hold before sizing anything from them
+    // (a constraint is at least three empty term lists = 12 bytes, a term 36 bytes)
+    if ((uint64_t)n_constraints * 12 > b.n) throw FrontendError("constraint count exceeds the constraint section");
     r.constraints.resize(n_constraints);
     for (auto &c : r.constraints)
         for (auto &lc : c) {
             const uint32_t n = b.u32();
+            if ((uint64_t)n * 36 > b.n - b.off) throw FrontendError("term count exceeds the constraint section");
             lc.reserve(n);
             for (uint32_t i = 0; i < n; ++i) {
                 const uint32_t wire = b.u32();
@@ -145,6 +150,7 @@ std::vector<U256> parse_wtns(const uint8_t *data, size_t len) {
     if (h.fe() != kP) throw FrontendError("wtns prime is not the BN254 scalar field");
     const uint32_t n = h.u32();
     Reader d{secs.at(2).first, secs.at(2).second};
+    if ((uint64_t)n * 32 > d.n) throw FrontendError("witness count exceeds the data section");
     std::vector<U256> w(n);
     for (auto &v : w) {
         v = d.fe();
@@ -371,10 +377,44 @@ std::vector<SubCircuit> compile(Pool &pool, std::vector<std::vector<int>> groups
 struct gkr_frontend {
     std::vector<SubCircuit> circuits;
     uint32_t n_pub = 0;
+    // Output of the reference (convert.rs:634-667): wire i+1 -> (witness value, name from the .sym file), i < n_pub
+    std::vector<std::string> out_names;
+    std::vector<gkr_fr> out_values;
 };
 
-extern "C" int gkr_frontend_compile(const uint8_t *r1cs, size_t r1cs_len, const uint8_t *wtns, size_t wtns_len,
-                                    gkr_frontend **out) {
+namespace {
+// parse_sym (convert.rs:851-871): the name after `main.` in the 4th comma-separated column of the first num_public
+// lines.  The reference indexes l[3] and name_main[1] unchecked (it panics on a malformed line); here that is an error.
+std::vector<std::string> parse_sym(const char *text, size_t len, uint32_t num_public) {
+    std::vector<std::string> res;
+    if (num_public == 0) return res;
+    size_t pos = 0;
+    while (pos < len && res.size() < num_public) {
+        size_t eol = pos;
+        while (eol < len && text[eol] != '\n') ++eol;
+        size_t end = eol;
+        if (end > pos && text[end - 1] == '\r') --end;          // str::lines() strips \r\n as well
+        const std::string line(text + pos, end - pos);
+        pos = eol + 1;
+        size_t col = 0, start = 0;
+        for (int c = 0; c < 3; ++c) {
+            col = line.find(',', start);
+            if (col == std::string::npos) throw FrontendError("sym line has fewer than four columns");
+            start = col + 1;
+        }
+        const size_t stop = line.find(',', start);
+        const std::string field = line.substr(start, stop == std::string::npos ? std::string::npos : stop - start);
+        const size_t dot = field.find('.');
+        if (dot == std::string::npos) throw FrontendError("sym name has no component after `main.`");
+        const size_t dot2 = field.find('.', dot + 1);
+        res.push_back(field.substr(dot + 1, dot2 == std::string::npos ? std::string::npos : dot2 - dot - 1));
+    }
+    return res;
+}
+}  // namespace
+
+static int frontend_compile(const uint8_t *r1cs, size_t r1cs_len, const uint8_t *wtns, size_t wtns_len, const char *sym,
+                            size_t sym_len, gkr_frontend **out) {
     if (!r1cs || !wtns || !out) return GKR_ERR_INVALID;
     *out = nullptr;
     try {
@@ -384,6 +424,13 @@ extern "C" int gkr_frontend_compile(const uint8_t *r1cs, size_t r1cs_len, const 
         Pool pool;
         fe->circuits = compile(pool, constraints_to_nodes(pool, r), w);
         fe->n_pub = r.n_pub_in + r.n_pub_out;
+        if (sym) {
+            fe->out_names = parse_sym(sym, sym_len, fe->n_pub);
+            // make_output (convert.rs:653-667) reads witness[i + 1] for every name
+            if (fe->out_names.size() + 1 > w.size()) throw FrontendError("witness is shorter than the public signals");
+            fe->out_values.resize(fe->out_names.size());
+            for (size_t i = 0; i < fe->out_names.size(); ++i) std::memcpy(&fe->out_values[i], w[i + 1].data(), 32);
+        }
         *out = fe.release();
         return GKR_OK;
     } catch (const FrontendError &e) {
@@ -392,7 +439,30 @@ extern "C" int gkr_frontend_compile(const uint8_t *r1cs, size_t r1cs_len, const 
     } catch (const std::bad_alloc &) {
         gkr::set_last_error("front end: out of memory");
         return GKR_ERR_OOM;
+    } catch (const std::exception &e) {               // nothing may unwind through the C boundary
+        gkr::set_last_error("front end: %s", e.what());
+        return GKR_ERR_INVALID;
+    } catch (...) {
+        gkr::set_last_error("front end: unknown failure");
+        return GKR_ERR_INTERNAL;
     }
+}
+extern "C" int gkr_frontend_compile(const uint8_t *r1cs, size_t r1cs_len, const uint8_t *wtns, size_t wtns_len,
+                                    gkr_frontend **out) {
+    return frontend_compile(r1cs, r1cs_len, wtns, wtns_len, nullptr, 0, out);
+}
+extern "C" int gkr_frontend_compile_sym(const uint8_t *r1cs, size_t r1cs_len, const uint8_t *wtns, size_t wtns_len,
+                                        const char *sym, size_t sym_len, gkr_frontend **out) {
+    if (!sym) return GKR_ERR_INVALID;
+    return frontend_compile(r1cs, r1cs_len, wtns, wtns_len, sym, sym_len, out);
+}
+extern "C" uint32_t gkr_frontend_n_outputs(const gkr_frontend *fe) { return fe ? (uint32_t)fe->out_names.size() : 0; }
+extern "C" int gkr_frontend_output(const gkr_frontend *fe, uint32_t i, uint32_t *wire, gkr_fr *value, const char **name) {
+    if (!fe || i >= fe->out_names.size() || !wire || !value || !name) return GKR_ERR_INVALID;
+    *wire = i + 1;
+    *value = fe->out_values[i];
+    *name = fe->out_names[i].c_str();
+    return GKR_OK;
 }
 extern "C" uint32_t gkr_frontend_n_circuits(const gkr_frontend *fe) { return fe ? (uint32_t)fe->circuits.size() : 0; }
 extern "C" uint32_t gkr_frontend_n_public(const gkr_frontend *fe) { return fe ? fe->n_pub : 0; }

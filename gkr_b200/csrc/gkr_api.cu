@@ -405,6 +405,7 @@ int gkr_ctx::wait_slot(uint32_t s, const HostSlot **out) {
     return GKR_OK;
 }
 
+extern "C" void gkr_ctx_destroy(gkr_ctx *ctx);
 extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     if (!out) return GKR_ERR_INVALID;
     *out = nullptr;
@@ -420,11 +421,17 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
         set_last_error("device %d out of range (%d devices)", device, n_dev);
         return GKR_ERR_INVALID;
     }
-    std::unique_ptr<gkr_ctx> ctx(new (std::nothrow) gkr_ctx());
+    // gkr_ctx_destroy null-checks every member: a failure half-way releases what exists already
+    std::unique_ptr<gkr_ctx, void (*)(gkr_ctx *)> ctx(new (std::nothrow) gkr_ctx(), gkr_ctx_destroy);
     if (!ctx) return GKR_ERR_OOM;
     ctx->device = device;
-    // profilers that serialise kernels (ncu) cannot run kernels that wait for the host: GKR_NO_PRELAUNCH=1
-    if (getenv("GKR_NO_PRELAUNCH")) ctx->prelaunch = false;
+    // Kernels that wait for the host (pre-launched rounds) cannot work under tools that serialise or replay kernels
+    // (ncu, compute-sanitizer, nsys with CUDA injection): those announce themselves through injection variables.
+    // A probe after the streams exist catches whatever does not; and a phase whose pre-launched kernel still gives up
+    // is re-run without pre-launching (kRetryNoPrelaunch).  GKR_NO_PRELAUNCH=1 forces the same by hand.
+    for (const char *name : {"GKR_NO_PRELAUNCH", "CUDA_INJECTION64_PATH", "CUDA_INJECTION32_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR",
+                             "NV_NSIGHT_INJECTION_PORT_BASE", "NVTX_INJECTION64_PATH"})
+        if (const char *e = getenv(name); e && *e) ctx->prelaunch = false;
     GKR_TRY(ctx->bind());
     GKR_CUDA_TRY((cudaError_t)kernels_device_init(device));
     int prio_lo = 0, prio_hi = 0;
@@ -447,6 +454,19 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     GKR_CUDA_TRY(cudaEventCreate(&ctx->ev0));
     GKR_CUDA_TRY(cudaEventCreate(&ctx->ev1));
     GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->prelaunch) {
+        // one-off probe (tens of microseconds when kernels run concurrently with the host, its 20 ms budget otherwise)
+        ctx->cmds_host[0].w[0] = 0;
+        const uint32_t s = ctx->next_seq();
+        launch_probe_host_wait(const_cast<const uint32_t *>(&ctx->cmds_dev[0].w[0]), 20ull * 1000 * 1000, ctx->slot_dev(s), s, ctx->stream);
+        GKR_TRY(ctx->check_launch("probe"));
+        ctx->cmds_host[0].w[0] = 1;
+        const HostSlot *slot;
+        GKR_TRY(ctx->wait_slot(s, &slot));
+        if (slot->aux[0] == 0) ctx->prelaunch = false;
+        ctx->cmds_host[0].w[0] = 0;
+        ctx->stats.kernel_launches += 1;
+    }
     *out = ctx.release();
     return GKR_OK;
 }
@@ -532,6 +552,10 @@ extern "C" int gkr_ctx_set_option(gkr_ctx *ctx, const char *name, int value) {
     }
     if (std::strcmp(name, "prelaunch") == 0) {
         ctx->prelaunch = value != 0;
+        return GKR_OK;
+    }
+    if (std::strcmp(name, "test_drop_cmd") == 0) {    // test hook: challenges are never handed to kernels that were launched
+        ctx->test_drop_cmd = value != 0;             // ahead of them (what a kernel-serialising tool does to the library)
         return GKR_OK;
     }
     if (std::strcmp(name, "f64_folds") == 0) {       // folds per pair moved to the FP64 pipe in the streaming rounds (0, 2..6)
@@ -952,6 +976,9 @@ struct RoundState {
     HFr claim, r;
     bool have_claim;
 };
+// internal return code of a phase whose pre-launched kernel gave up waiting for its challenge (it never saw the
+// host's write: kernels are being serialised by a tool).  The caller switches pre-launching off and runs the phase again.
+constexpr int kRetryNoPrelaunch = 1;
 // host half of one round: published sums -> message (static length rule) -> challenge -> next claim
 static int consume_values(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, uint32_t j, bool full, HFr x0, HFr x2, HFr x1,
                           RoundState &st, HFr *last_hash) {
@@ -1165,13 +1192,13 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
         GKR_TRY(ctx->wait_slot(p.seq, &slot));
         if (slot->aux[2] == 0xDEADu) {
             set_last_error("pre-launched round kernel %u gave up waiting for its challenge", j);
-            return GKR_ERR_INTERNAL;
+            return kRetryNoPrelaunch;
         }
         GKR_TRY(consume_round(ctx, t, io, j, full, slot, st, last_hash));
         // hand the challenge to the next (already running, waiting) kernel
         if (j + 1 < k && plan[j + 1].launched && !plan[j + 1].commanded) {
             const FrConstMul rc = make_const_mul(st.r);
-            write_cmd(ctx->cmds_host + (plan[j + 1].seq % gkr_ctx::kSlots), &rc, plan[j + 1].seq);
+            if (!ctx->test_drop_cmd) write_cmd(ctx->cmds_host + (plan[j + 1].seq % gkr_ctx::kSlots), &rc, plan[j + 1].seq);
             plan[j + 1].commanded = true;
             ctx->prelaunched_pending--;
         }
@@ -1255,7 +1282,7 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         const uint64_t quads = T[j].n / 4;
         if (p.launched) {
             const FrConstMul rc = make_const_mul(st.r);
-            write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), &rc, p.seq);
+            if (!ctx->test_drop_cmd) write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), &rc, p.seq);
             p.commanded = true;
             ctx->prelaunched_pending--;
             return GKR_OK;
@@ -1280,10 +1307,9 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         // pre-launched: many CTAs polling host memory at once were measured to delay the command by 25 us.
         if (can_prelaunch && j + 1 <= k - 1 && !P[j + 1].launched && T[j + 1].n / 4 <= (uint64_t)gkr_poly_tail_max_quads()) {
             const uint32_t u = j + 1, n_levels = k - u;
-            uint32_t seq0 = 0;
+            const uint32_t seq0 = ctx->next_seq_run(n_levels);          // consecutive: the kernel uses seq0 + level
             for (uint32_t v = u; v + 1 <= k; ++v) {
-                P[v].seq = ctx->next_seq();
-                if (v == u) seq0 = P[v].seq;
+                P[v].seq = seq0 + (v - u);
                 write_cmd(ctx->cmds_host + (P[v].seq % gkr_ctx::kSlots), nullptr, 0u);
                 P[v].launched = true;
                 ctx->prelaunched_pending++;
@@ -1345,7 +1371,7 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         TraceScope ts_consume(TS_CONSUME);
         if (slot->aux[2] == 0xDEADu) {
             set_last_error("pre-launched look-ahead kernel %u gave up waiting for its challenge", j - 1);
-            return GKR_ERR_INTERNAL;
+            return kRetryNoPrelaunch;
         }
         if (g_trace && T[j - 1].n / 4 <= (uint64_t)gkr_poly_tail_max_quads() && j - 1 > s) {
             auto u64 = [&](int i) { return (uint64_t)slot->aux[i] | ((uint64_t)slot->aux[i + 1] << 32); };
@@ -1585,9 +1611,25 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         io.first_round_seq = seq_first;
         HFr claim = hfr_zero();
         if (!lookahead) GKR_TRY(release_aux_jobs(ctx, false));
-        GKR_TRY(L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, nullptr, &claim)
-                : lookahead ? run_phase_poly(ctx, t, io, &last_hash, nullptr, &claim)
-                            : run_phase(ctx, t, io, &last_hash, nullptr, &claim));
+        auto run_phase_any = [&](const HFr *claim_in) -> int {
+            for (int attempt = 0;; ++attempt) {
+                const int rc = L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, claim_in, &claim)
+                             : lookahead ? run_phase_poly(ctx, t, io, &last_hash, claim_in, &claim)
+                                         : run_phase(ctx, t, io, &last_hash, claim_in, &claim);
+                if (rc != kRetryNoPrelaunch) return rc;
+                if (attempt > 0 || !ctx->prelaunch) return GKR_ERR_INTERNAL;
+                // the inputs of the phase (H, W, A of size N) are never written: run it again from the start, with
+                // every round launched on demand; the messages and challenges are recomputed identically
+                fprintf(stderr, "[gkr_b200] a pre-launched kernel never saw its challenge (kernels serialised by a tool?): "
+                                "pre-launching disabled for this context\n");
+                ctx->prelaunch = false;
+                GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                io.first_round_seq = 0;
+            }
+        };
+        {
+            GKR_TRY(run_phase_any(nullptr));
+        }
         // W(u): fold the last size-2 W table with r_k
         const double t_setup1 = g_trace ? now_seconds() : 0.0;
         ctx->begin_launch();
@@ -1613,9 +1655,10 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         if (g_trace) { g_trace_t[TS_SETUP_LAUNCH] += now_seconds() - t_setup1; g_trace_n[TS_SETUP_LAUNCH]++; }
         io.challenges = rs.data() + k;
         io.msgs = &P->msgs[3 * (ro + k)]; io.msg_len = &P->msg_len[ro + k]; io.chal_out = &P->chal[ro + k];
-        GKR_TRY(L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, &claim, &claim)
-                : lookahead ? run_phase_poly(ctx, t, io, &last_hash, &claim, &claim)
-                            : run_phase(ctx, t, io, &last_hash, &claim, &claim));
+        {
+            const HFr claim_in = claim;           // a retry must start from the same claim
+            GKR_TRY(run_phase_any(&claim_in));
+        }
 
         // ---- q_i = W restricted to the line b* -> c* (poly.rs:469-500): needs only b*, c* => runs on the
         //      low-priority stream while the next layer's rounds proceed; collected after the last layer ----
@@ -1721,6 +1764,22 @@ extern "C" int gkr_verify(gkr_ctx *ctx, const gkr_circuit *c, const gkr_proof *p
     for (uint32_t i = 0; i <= n_layers; ++i)
         if (pf->k[i] != c->k[i]) REJECT("rejected: k[%u] mismatch", i);
     if (pf->d_len != ((uint64_t)1 << c->k[0]) || pf->d_len == 0) REJECT("rejected: d has the wrong size");
+    // the proof may come from anywhere: its offset arrays must be the ones the circuit's k implies before they index anything
+    if (!pf->k || !pf->round_off || !pf->msg_len || !pf->msgs || !pf->chal || !pf->q_off || !pf->q_len || !pf->q || !pf->z_off ||
+        !pf->z || !pf->r || !pf->d_coef)
+        REJECT("rejected: proof with null arrays");
+    {
+        uint64_t ro = 0, qo = 0, zo = 0;
+        for (uint32_t i = 0; i <= n_layers; ++i) {
+            if (pf->z_off[i] != zo) REJECT("rejected: z offsets do not match the circuit");
+            zo += c->k[i];
+            if (i == n_layers) break;
+            if (pf->round_off[i] != ro || pf->q_off[i] != qo) REJECT("rejected: round / q offsets do not match the circuit");
+            ro += 2ull * c->k[i + 1];
+            qo += c->k[i + 1] + 1;
+        }
+        if (pf->round_off[n_layers] != ro || pf->n_rounds != ro) REJECT("rejected: round count does not match the circuit");
+    }
     auto load = [&](const gkr_fr &x, HFr *out) { return hfr_from_canonical(out, &x); };
 
     const uint64_t Nmax = (uint64_t)1 << c->max_k;

@@ -1109,6 +1109,27 @@ void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const 
 }
 
 
+// Can a running kernel see a host write made AFTER its launch call returned?  Not under tools that serialise or
+// replay kernels (ncu, compute-sanitizer): there every pre-launched kernel would spin until it gives up.  The probe
+// waits up to budget_ns for the flag and reports what it saw in aux[0].
+__global__ void k_probe_host_wait(const volatile uint32_t *flag, unsigned long long budget_ns, HostSlot *slot, uint32_t seq) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    uint32_t seen = 0;
+    do {
+        seen = ld_sys(flag);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (!seen && t1 - t0 < budget_ns);
+    slot->aux[0] = seen;
+    slot->aux[1] = 0;
+    slot->aux[2] = 0;
+    __threadfence_system();
+    slot->seq = seq;
+}
+void launch_probe_host_wait(const uint32_t *flag_dev, unsigned long long budget_ns, HostSlot *slot, uint32_t seq, cudaStream_t s) {
+    k_probe_host_wait<<<1, 1, 0, s>>>(flag_dev, budget_ns, slot, seq);
+}
+
 // cudaFuncSetAttribute is per device: run once for every device a context is created on (gkr_ctx_create)
 int kernels_device_init(int device) {
     if (device < 0 || device >= kMaxDevices) return (int)cudaErrorInvalidDevice;

@@ -144,6 +144,9 @@ void launch_dot(const Fr *X, const Fr *Y, uint64_t n, const ReduceWs &ws, HostSl
 // Montgomery sums, failures2[1] threads whose FP64-pipe fold differed from the integer fold
 void launch_selftest(uint32_t iters, const FrConstMul &r, const FrFoldF64 &rf, unsigned int *failures2, cudaStream_t s);
 
+// aux[0] of the slot = 1 if the kernel saw *flag_dev become non-zero within budget_ns of starting
+void launch_probe_host_wait(const uint32_t *flag_dev, unsigned long long budget_ns, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
+
 int device_sm_count();            // of the calling thread's current device
 // one-time per-device setup (function attributes); the current device must be `device`.  Returns a cudaError_t value.
 int kernels_device_init(int device);

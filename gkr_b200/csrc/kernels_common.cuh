@@ -82,7 +82,7 @@ __device__ __forceinline__ bool wait_cmd(const HostCmd *cmd, uint32_t tag, uint3
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         int ok = 0;
-        for (uint32_t spin = 0; spin < (1u << 24); ++spin) {       // ~30 s, then give up loudly
+        for (uint32_t spin = 0; spin < (1u << 21); ++spin) {       // ~4 s, then give up: the host retries without pre-launching
             const uint32_t v0 = ld_sys(&cmd->w[lane]);
             const uint32_t v1 = ld_sys(&cmd->w[32 + lane]);
             const uint32_t v2 = lane < 16 ? ld_sys(&cmd->w[64 + lane]) : tag;

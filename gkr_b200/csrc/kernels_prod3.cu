@@ -152,15 +152,15 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1)
     grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, dev_out);
 }
 
-// Variant selection for the streaming (lazy) rounds.  Defaults are the measured best (profiles/r02_prod3_variants.md);
-// GKR_P3_THREADS / GKR_P3_SACC override them for experiments.
+// Variant selection for the streaming (lazy) rounds.  Default = the measured best (profiles/r02_prod3_variants.md: 2^28
+// sumcheck 36.8 ms with two 256-thread CTAs per SM and register accumulators, 34.0 ms with one 512-thread CTA per SM and
+// shared-memory accumulators; 384 threads 34.6 ms, 448 threads 38.8 ms).  GKR_P3_THREADS=256 selects the old form.
 struct P3Variant { int threads; bool sacc; };
 static P3Variant p3_variant() {
     static const P3Variant v = [] {
-        const char *t = getenv("GKR_P3_THREADS"), *a = getenv("GKR_P3_SACC");
-        P3Variant x{256, false};
-        if (t && atoi(t) == 384) x.threads = 384;
-        if (a) x.sacc = atoi(a) != 0;
+        const char *t = getenv("GKR_P3_THREADS");
+        P3Variant x{512, true};
+        if (t && atoi(t) == 256) x = P3Variant{256, false};
         return x;
     }();
     return v;
@@ -196,15 +196,12 @@ static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout
 #define GKR_P3(NF, T, SA) launch_p3_lazy<FOLD, FULL, NF, T, SA>(A, B, C, Aout, Bout, Cout, r, rf ? *rf : no_rf, pairs, ws, slot, seq, dev_out, s)
 #define GKR_P3_TS(NF)                                            \
     do {                                                         \
-        if (v.threads == 384) { if (v.sacc) GKR_P3(NF, 384, true); else GKR_P3(NF, 384, false); } \
-        else { if (v.sacc) GKR_P3(NF, 256, true); else GKR_P3(NF, 256, false); }                  \
+        if (v.threads == 512) GKR_P3(NF, 512, true); else GKR_P3(NF, 256, false);                  \
     } while (0)
     if constexpr (FOLD && !FULL) {           // FP64-pipe folds: streaming fused rounds only
         if (rf) {
             switch (nf) {
                 case 3: GKR_P3_TS(3); return;
-                case 4: GKR_P3_TS(4); return;
-                case 6: GKR_P3_TS(6); return;
                 default: break;
             }
         }

@@ -114,6 +114,7 @@ struct gkr_ctx {
     bool lookahead = true;                 // look-ahead rounds: next message as a polynomial in the pending challenge
     int f64_folds = gkr::default_f64_folds();   // option "f64_folds": folds per pair on the FP64 pipe in streaming rounds
     bool prelaunch = true;                 // pre-launch the small-table rounds of a phase (option "prelaunch")
+    bool test_drop_cmd = false;            // test hook, see gkr_ctx_set_option
     int prelaunched_pending = 0;           // launched kernels still waiting for their challenge (see wait_slot)
     uint32_t seq = 0;
     gkr::ReduceWs ws{};
@@ -169,7 +170,16 @@ struct gkr_ctx {
             prof.algo_bytes[kc] += algo_bytes;
         }
     }
-    uint32_t next_seq() { return ++seq; }
+    // Sequence numbers tag result slots and command blocks.  0 is the "empty" state of both and 0xFFFFFFFF the abort
+    // tag, so neither is ever handed out; next_seq_run(n) returns the first of n CONSECUTIVE numbers (the persistent tail
+    // kernel derives the numbers of its levels from the first one) and skips ahead if the run would straddle the wrap.
+    uint32_t next_seq() { return next_seq_run(1); }
+    uint32_t next_seq_run(uint32_t n) {
+        if (seq > 0xFFFFFFFFu - 1u - n) seq = 0;          // wrap before the run, never inside it
+        const uint32_t first = seq + 1;
+        seq += n;
+        return first;
+    }
     gkr::HostSlot *slot_dev(uint32_t s) const { return slots_dev + (s % kSlots); }
     // spin until the slot for sequence number s has been published
     int wait_slot(uint32_t s, const gkr::HostSlot **out);

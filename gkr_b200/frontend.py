@@ -515,16 +515,21 @@ def convert_r1cs_wtns_gkr(r1cs: R1cs, witness, sym_text: str = ""):
     return subs, out
 
 
-def compile_native(r1cs_bytes: bytes, wtns_bytes: bytes):
+def compile_native(r1cs_bytes: bytes, wtns_bytes: bytes, sym_text: str | None = None):
     """The same pipeline in the library's native front end (csrc/frontend.cpp, `gkr_frontend_*`): file bytes in,
     list of SubCircuit out.  A C / Rust host calls these entry points directly and hands the arrays to
-    gkr_circuit_create / gkr_witness_eval without copying."""
+    gkr_circuit_create / gkr_witness_eval without copying.  With sym_text also returns the reference's Output
+    (parse_sym + make_output, convert.rs:851-871, 653-667) built natively: (subs, Output)."""
     import ctypes as C
     from ._lib import LayerDesc, check, lib
     from .prover import DenseLayer
     L = lib()
     h = C.c_void_p()
-    check(L.gkr_frontend_compile(r1cs_bytes, len(r1cs_bytes), wtns_bytes, len(wtns_bytes), C.byref(h)))
+    if sym_text is None:
+        check(L.gkr_frontend_compile(r1cs_bytes, len(r1cs_bytes), wtns_bytes, len(wtns_bytes), C.byref(h)))
+    else:
+        sb = sym_text.encode()
+        check(L.gkr_frontend_compile_sym(r1cs_bytes, len(r1cs_bytes), wtns_bytes, len(wtns_bytes), sb, len(sb), C.byref(h)))
     try:
         subs = []
         for i in range(L.gkr_frontend_n_circuits(h)):
@@ -543,7 +548,16 @@ def compile_native(r1cs_bytes: bytes, wtns_bytes: bytes):
             ks.append(input_k.value)
             inputs = np.ctypeslib.as_array(C.cast(vals, C.POINTER(C.c_uint32)), ((1 << input_k.value), 8)).copy()
             subs.append(SubCircuit(layers, inputs, ks))
-        return subs
+        if sym_text is None:
+            return subs
+        out = Output({}, {})
+        for i in range(L.gkr_frontend_n_outputs(h)):
+            wire, name = C.c_uint32(), C.c_char_p()
+            val = np.zeros(8, np.uint32)
+            check(L.gkr_frontend_output(h, i, C.byref(wire), val.ctypes.data_as(C.c_void_p), C.byref(name)))
+            out.wire_map[wire.value] = int.from_bytes(val.tobytes(), "little")
+            out.name_map[wire.value] = name.value.decode()
+        return subs, out
     finally:
         L.gkr_frontend_destroy(h)
 

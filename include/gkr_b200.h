@@ -204,6 +204,13 @@ uint32_t gkr_frontend_n_circuits(const gkr_frontend *fe);
 uint32_t gkr_frontend_n_public(const gkr_frontend *fe);       /* n_pub_in + n_pub_out of the r1cs header (make_output, :653-667) */
 int gkr_frontend_circuit(const gkr_frontend *fe, uint32_t i, uint32_t *n_layers, const gkr_layer_desc **layers,
                          uint32_t *input_k, const gkr_fr **input_values /* 2^input_k canonical values */);
+/* the same with the .sym text (`#s,#w,#c,main.name` per line): also builds the reference's `Output` (convert.rs:634-667,
+ * parse_sym :851-871): output i < n_outputs is wire i + 1, its witness value and the name after `main.`.  The name pointer
+ * lives until gkr_frontend_destroy.  A malformed .sym line is GKR_ERR_INVALID (the reference panics). */
+int gkr_frontend_compile_sym(const uint8_t *r1cs, size_t r1cs_len, const uint8_t *wtns, size_t wtns_len, const char *sym,
+                             size_t sym_len, gkr_frontend **out);
+uint32_t gkr_frontend_n_outputs(const gkr_frontend *fe);
+int gkr_frontend_output(const gkr_frontend *fe, uint32_t i, uint32_t *wire, gkr_fr *value, const char **name);
 void gkr_frontend_destroy(gkr_frontend *fe);
 
 /* ---- instrumentation ------------------------------------------------------------------------------ */

@@ -239,6 +239,46 @@ def test_native_front_end_mimc7_and_errors():
         fe.compile_native(fe.write_r1cs(empty_c), fe.write_wtns([1, 2, 3]))
 
 
+def test_native_sym_and_output():
+    """parse_sym / make_output in csrc/frontend.cpp (convert.rs:851-871, 653-667) against the Python mirror"""
+    from gkr_b200._lib import GkrError
+    r, w = mimc7_r1cs(7)
+    r.header.n_pub_out, r.header.n_pub_in = 1, 2
+    rb, wb = fe.write_r1cs(r), fe.write_wtns(w)
+    sym = "1,1,0,main.out\r\n2,2,0,main.in1\n3,3,0,main.in2.limb[0]\n4,4,0,main.hidden\n"
+    subs, out = fe.compile_native(rb, wb, sym)
+    want_subs, want_out = fe.convert_r1cs_wtns_gkr(fe.read_r1cs(rb), fe.read_wtns(wb), sym)
+    _same_subcircuits(subs, want_subs)
+    assert out.name_map == want_out.name_map == {1: "out", 2: "in1", 3: "in2"}
+    assert out.wire_map == {k: int(v) for k, v in want_out.wire_map.items()}
+    assert out.get_name(2) == "in1" and out.get_name(9) is None
+    # fewer lines than public signals: the reference stops at the end of the file
+    assert fe.compile_native(rb, wb, "1,1,0,main.out\n")[1].name_map == {1: "out"}
+    for bad in ("1,1,0\n", "1,1,0,main\n"):                 # the reference panics (l[3] / name_main[1] out of bounds)
+        with pytest.raises(GkrError):
+            fe.compile_native(rb, wb, bad)
+    r.header.n_pub_out = r.header.n_pub_in = 0
+    assert fe.compile_native(fe.write_r1cs(r), wb, sym)[1].name_map == {}
+
+
+def test_native_front_end_rejects_hostile_sizes():
+    """section sizes and counts taken from the file must not wrap a comparison or size an allocation"""
+    import struct
+    from gkr_b200._lib import GkrError
+    r, w = mimc7_r1cs(3)
+    rb, wb = fe.write_r1cs(r), fe.write_wtns(w)
+    huge = bytearray(rb)
+    huge[16:24] = struct.pack("<Q", 0xFFFFFFFFFFFFFFF0)           # size of the first section
+    with pytest.raises(GkrError, match="truncated"):
+        fe.compile_native(bytes(huge), wb)
+    wbad = bytearray(wb)
+    # header section: type(4) size(8) | field size(4) prime(32) count(4)
+    off = 12 + 12 + 4 + 32
+    wbad[off:off + 4] = struct.pack("<I", 0xFFFFFFFF)
+    with pytest.raises(GkrError, match="exceeds"):
+        fe.compile_native(rb, bytes(wbad))
+
+
 def _as_sets(terms):
     return sorted(tuple(t) for t in terms)
 

@@ -219,6 +219,27 @@ def test_lookahead_off_matches(pv):
     pn.close()
 
 
+@pytest.mark.parametrize("lookahead", [1, 0])
+def test_prelaunched_kernel_that_never_sees_its_challenge_is_retried(lookahead):
+    """what ncu / compute-sanitizer do to the library: kernels launched ahead of their challenge never see the host's
+    write.  The kernel gives up after its bounded spin (~4 s), the phase is re-run with on-demand launches, the context
+    stops pre-launching -- and the proof is the same (round 1 returned GKR_ERR_INTERNAL after 21 s here)."""
+    from gkr_b200 import Prover
+    pt = Prover(0)
+    pt.set_option("lookahead", lookahead)
+    pt.set_option("prelaunch", 1)
+    pt.set_option("test_drop_cmd", 1)
+    rng = random.Random(77)
+    ks = [9, 10, 9]
+    layers = random_circuit(rng, ks, "mixed")
+    inputs = [rng.randrange(P) for _ in range(1 << ks[-1])]
+    got = _gpu_prove(pt, layers, inputs)
+    assert_same_dense(run_l1(layers, inputs)[0], got)
+    got2 = _gpu_prove(pt, layers, inputs)            # the context no longer pre-launches: no second wait
+    assert_same_dense(got, got2)
+    pt.close()
+
+
 def _skewed_circuit(rng, ks, hubs):
     """layers whose gates read a few hub wires very often (rows with thousands of CSR edges) and leave most rows
     without any edge: the multi-pass and empty-row paths of the fused wiring kernel"""

@@ -43,9 +43,9 @@ def child(v):
 def main():
     v = int(sys.argv[1]) if len(sys.argv) > 1 else 26
     points = []
-    for threads in (256, 384):
+    for threads in (256, 384, 448, 512):
         for sacc in (0, 1):
-            for nf in (0, 3, 4, 6):
+            for nf in (0,):
                 points.append({"GKR_P3_THREADS": str(threads), "GKR_P3_SACC": str(sacc), "GKR_F64_FOLDS": str(nf)})
     base = None
     for env in points:
