@@ -802,8 +802,8 @@ extern "C" int gkr_circuit_create(gkr_ctx *ctx, uint32_t n_layers, const gkr_lay
     if (!c) return GKR_ERR_OOM;
     c->device = ctx->device;
     c->owner = ctx;
-    c->n_ranks = ctx->nccl_comm ? ctx->n_ranks : 1;
-    c->rank = ctx->nccl_comm ? ctx->rank : 0;
+    c->n_ranks = ctx->dist_ranks();
+    c->rank = ctx->comm_active ? ctx->rank : 0;
     uint32_t lb = 0;
     while ((1 << lb) < c->n_ranks) ++lb;
     c->layers.resize(n_layers);
@@ -955,6 +955,7 @@ struct PhaseIO {
     const Fr *W_last;          // out: device pointer to the size-2 W table of the last round
     uint32_t shard_bits = 0;   // > 0: H, W, A hold this rank's shard (2^(k - shard_bits) rows each)
     uint32_t first_round_seq = 0;   // != 0: round 1 was already launched (fused with the wiring sums) under this sequence number
+    XchgArg first_round_xa{};       // ... and, on a sharded layer, with this exchange
 };
 
 // host -> waiting kernel: payload first, then the five line tags (x86 keeps the store order)
@@ -1018,6 +1019,146 @@ static int consume_round(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, uin
                           full ? to_host(slot->v[2]) : hfr_zero(), st, last_hash);
 }
 
+// ------------------------------------------------------------------------------------------------
+// multi-GPU exchange helpers (shared host block when the communicator has one, NCCL all-gather otherwise)
+// ------------------------------------------------------------------------------------------------
+// what a reducing launch whose totals must be summed over the ranks gets
+static XchgArg xchg_begin(gkr_ctx *ctx, const char *site = "") {
+    XchgArg xa;
+    if (ctx->xchg) {
+        xa.seq = ctx->xchg->next();
+        xa.out = &ctx->xchg->dev->row[xa.seq % kXchgRing][ctx->rank];
+        static const bool trace = getenv("GKR_XCHG_TRACE") != nullptr;
+        if (trace) fprintf(stderr, "[xchg] rank %d seq %u %s\n", ctx->rank, xa.seq, site);
+    } else {
+        xa.dev_out = ctx->comm_send;
+    }
+    return xa;
+}
+// after that launch.  Shared block: nothing to enqueue (the kernel writes its entry of the row).  Fallback: all-gather
+// the K totals and let a one-warp kernel add them and publish slot s.
+static int xchg_finish_round(gkr_ctx *ctx, int K, uint32_t s) {
+    if (ctx->xchg) return GKR_OK;
+    GKR_TRY(comm_all_gather(ctx, ctx->comm_send, ctx->comm_recv, (size_t)K * sizeof(Fr)));
+    ctx->begin_launch();
+    launch_sum_ranks_publish(ctx->comm_recv, ctx->n_ranks, K, ctx->slot_dev(s), s, ctx->stream);
+    ctx->end_launch(KC_OTHER, 32.0 * K * ctx->n_ranks);
+    return ctx->check_launch("sum_ranks_publish");
+}
+// in-process groups: meet the other ranks (all allocations of this call done) before the first exchanging kernel
+static void group_barrier(gkr_ctx *ctx) {
+    if (ctx->comm_active && ctx->xchg && ctx->xchg->group) ctx->xchg->group->arrive_and_wait();
+}
+// Result of an exchanged launch: with the shared block, wait until every rank's entry of row xa.seq carries the flag and
+// add the K totals in rank order into `sum` (which then stands in for the host slot); otherwise wait for slot s.
+static int xchg_wait(gkr_ctx *ctx, const XchgArg &xa, int K, uint32_t s, HostSlot *sum, const HostSlot **out) {
+    if (!xa.out) return ctx->wait_slot(s, out);
+    TraceScope trace_scope(g_wait_site);
+    const double t0 = now_seconds();
+    XchgEntry *row = ctx->xchg->host->row[xa.seq % kXchgRing];
+    HFr tot[6];
+    for (int j = 0; j < K; ++j) tot[j] = hfr_zero();
+    uint32_t aux0 = 0;
+    for (int r = 0; r < ctx->n_ranks; ++r) {
+        volatile XchgEntry *e = &row[r];
+        uint64_t spins = 0;
+        double next_check = now_seconds() + 2.0;
+        while (e->flag != xa.seq) {
+            _mm_pause();
+            if ((++spins & 0xFFF) != 0) continue;
+            const double now = now_seconds();
+            if (now < next_check) continue;
+            next_check = now + 2.0;
+            if (r == ctx->rank) {                // our own kernel: a launch failure would otherwise look like a slow peer
+                cudaError_t err = cudaStreamQuery(ctx->stream);
+                if (err != cudaSuccess && err != cudaErrorNotReady) {
+                    set_last_error("stream error while waiting for an exchanged round result: %s", cudaGetErrorString(err));
+                    return GKR_ERR_CUDA;
+                }
+            }
+            if (now - t0 > 60.0) {
+                set_last_error("multi-GPU exchange %u: the partial sums of rank %d never arrived (is every rank running the same call?)",
+                               (unsigned)xa.seq, r);
+                return GKR_ERR_COMM;
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        for (int j = 0; j < K; ++j) {
+            Fr v;
+            std::memcpy(&v, const_cast<const Fr *>(&e->v[j]), sizeof v);
+            const HFr h = to_host(v);
+            if (hf::geq_p(h.l)) {
+                set_last_error("multi-GPU exchange: rank %d published an unreduced value", r);
+                return GKR_ERR_INTERNAL;
+            }
+            tot[j] = hfr_add(tot[j], h);
+        }
+        if (r == ctx->rank) aux0 = e->aux[0];
+    }
+    std::memset(sum, 0, sizeof *sum);
+    uint32_t nz = 0;
+    for (int j = 0; j < K; ++j) {
+        sum->v[j] = to_dev(tot[j]);
+        nz |= hfr_is_zero(tot[j]) ? 0u : (1u << j);
+    }
+    sum->aux[0] = aux0;
+    sum->aux[1] = nz;
+    *out = sum;
+    ctx->stats.wait_seconds += now_seconds() - t0;
+    return GKR_OK;
+}
+// The shards are small: fold them with the pending challenge (if any), gather every rank's shard and continue on the
+// replicated tables of m * P entries (no further exchange in the many small late rounds).  cur: this rank's three
+// tables of n entries; out: the three gathered tables (in ctx->shard_mini); returns m * P through n_out.
+static int gather_shards(gkr_ctx *ctx, const Fr *const cur[3], bool pending_fold, const HFr &r, uint64_t n, const Fr *out[3],
+                         uint64_t *n_out) {
+    const int P = ctx->n_ranks;
+    const uint64_t m = pending_fold ? n / 2 : n;
+    if (ctx->xchg && 3 * m > sizeof(ctx->xchg->host->stage[0]) / sizeof(Fr)) {
+        set_last_error("gather_shards: %llu entries per table exceed the staging area", (unsigned long long)m);
+        return GKR_ERR_INTERNAL;
+    }
+    Fr *send = ctx->xchg ? ctx->xchg->dev->stage[ctx->rank] : ctx->comm_send + 8;
+    for (int i = 0; i < 3; ++i) {
+        if (pending_fold) {
+            ctx->begin_launch();
+            launch_fold(cur[i], send + i * m, make_const_mul(r), m, ctx->stream);
+            ctx->end_launch(KC_OTHER, 96.0 * m);
+            GKR_TRY(ctx->check_launch("fold"));
+        } else {
+            GKR_CUDA_TRY(cudaMemcpyAsync(send + i * m, cur[i], m * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+    }
+    GKR_TRY(ctx->shard_mini.ensure(sizeof(Fr) * 3 * m * (size_t)P));
+    Fr *mini = ctx->shard_mini.as<Fr>();
+    if (ctx->xchg) {
+        // flag behind the folds in stream order; then a host-side barrier on every rank's flag; then read all areas
+        const XchgArg xa = xchg_begin(ctx, "gather");
+        ctx->begin_launch();
+        launch_xchg_flag(xa, ctx->stream);
+        ctx->end_launch(KC_OTHER, 0.0);
+        GKR_TRY(ctx->check_launch("xchg_flag"));
+        HostSlot dummy;
+        const HostSlot *unused;
+        GKR_TRY(xchg_wait(ctx, xa, 0, 0, &dummy, &unused));
+        StagedPtrs sp{};
+        for (int rk = 0; rk < P; ++rk) sp.p[rk] = ctx->xchg->dev->stage[rk];
+        ctx->begin_launch();
+        launch_interleave_staged(sp, mini, P, 3, m, ctx->stream);
+        ctx->end_launch(KC_OTHER, 192.0 * m * P);
+        GKR_TRY(ctx->check_launch("interleave_staged"));
+    } else {
+        GKR_TRY(comm_all_gather(ctx, send, ctx->comm_recv, 3 * m * sizeof(Fr)));
+        ctx->begin_launch();
+        launch_interleave_gathered(ctx->comm_recv, mini, P, 3, m, ctx->stream);
+        ctx->end_launch(KC_OTHER, 192.0 * m * P);
+        GKR_TRY(ctx->check_launch("interleave_gathered"));
+    }
+    out[0] = mini; out[1] = mini + m * P; out[2] = mini + 2 * m * P;
+    *n_out = m * (uint64_t)P;
+    return GKR_OK;
+}
+
 // Multi-GPU phase: H, W, A are this rank's shards (rows idx = i * P + rank).  The first k - log2(P) rounds
 // reduce locally, all-gather the partial sums (NCCL) and add them on every rank; then every rank folds its
 // last two rows, the single entries are gathered and the remaining log2(P) rounds run on the P-entry tables.
@@ -1037,28 +1178,9 @@ static int run_phase_sharded(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io,
     bool gathered = false;
     for (uint32_t j = 0; j < k; ++j) {
         if (!gathered && n <= std::max<uint64_t>(kGatherEntries, 2) && (pending_fold || n <= kGatherEntries / 2)) {
-            const uint64_t m = pending_fold ? n / 2 : n;
-            Fr *send = ctx->comm_send + 8;
-            const Fr *cur[3] = {Hc, Wc, Ac};
-            for (int i = 0; i < 3; ++i) {
-                if (pending_fold) {
-                    ctx->begin_launch();
-                    launch_fold(cur[i], send + i * m, make_const_mul(st.r), m, ctx->stream);
-                    ctx->end_launch(KC_OTHER, 96.0 * m);
-                    GKR_TRY(ctx->check_launch("fold"));
-                } else {
-                    GKR_CUDA_TRY(cudaMemcpyAsync(send + i * m, cur[i], m * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-                }
-            }
-            GKR_TRY(comm_all_gather(ctx, send, ctx->comm_recv, 3 * m * sizeof(Fr)));
-            GKR_TRY(ctx->shard_mini.ensure(sizeof(Fr) * 3 * m * (size_t)P));
-            Fr *mini = ctx->shard_mini.as<Fr>();
-            ctx->begin_launch();
-            launch_interleave_gathered(ctx->comm_recv, mini, P, 3, m, ctx->stream);
-            ctx->end_launch(KC_OTHER, 192.0 * m * P);
-            GKR_TRY(ctx->check_launch("interleave_gathered"));
-            Hc = mini; Wc = mini + m * P; Ac = mini + 2 * m * P;
-            n = m * (uint64_t)P;
+            const Fr *cur[3] = {Hc, Wc, Ac}, *got[3];
+            GKR_TRY(gather_shards(ctx, cur, pending_fold, st.r, n, got, &n));
+            Hc = got[0]; Wc = got[1]; Ac = got[2];
             pending_fold = false;
             gathered = true;
         }
@@ -1066,34 +1188,28 @@ static int run_phase_sharded(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io,
         const uint32_t s = ctx->next_seq();
         const bool full = !st.have_claim || ctx->paranoid;
         const FrConstMul rc = pending_fold ? make_const_mul(st.r) : FrConstMul{};
-        Fr *dev_out = sharded_round ? ctx->comm_send : nullptr;
+        const XchgArg xa = sharded_round ? xchg_begin(ctx) : XchgArg{};
         ctx->begin_launch();
         if (!pending_fold) {
             launch_gkr_round(false, full, Hc, Wc, Ac, nullptr, nullptr, nullptr, rc, n / 2, ctx->ws, ctx->slot_dev(s), s,
-                             ctx->stream, nullptr, dev_out);
+                             ctx->stream, nullptr, xa);
             ctx->end_launch(n / 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full ? 96.0 : 80.0) * n);
         } else {
             DevBuf &dst = (flip ^= 1) ? ctx->foldA : ctx->foldB;
             const uint64_t half = n / 2;
             Fr *Ho = dst.as<Fr>(), *Wo = Ho + half, *Ao = Wo + half;
             launch_gkr_round(true, full, Hc, Wc, Ac, Ho, Wo, Ao, rc, half / 2, ctx->ws, ctx->slot_dev(s), s, ctx->stream,
-                             nullptr, dev_out);
+                             nullptr, xa);
             ctx->end_launch(half / 2 >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 144.0 * n);
             Hc = Ho; Wc = Wo; Ac = Ao;
             n = half;
         }
         GKR_TRY(ctx->check_launch("gkr_round"));
-        if (sharded_round) {
-            const int K = full ? 3 : 2;
-            GKR_TRY(comm_all_gather(ctx, ctx->comm_send, ctx->comm_recv, (size_t)K * sizeof(Fr)));
-            ctx->begin_launch();
-            launch_sum_ranks_publish(ctx->comm_recv, P, K, ctx->slot_dev(s), s, ctx->stream);
-            ctx->end_launch(KC_OTHER, 32.0 * K * P);
-            GKR_TRY(ctx->check_launch("sum_ranks_publish"));
-        }
+        if (sharded_round) GKR_TRY(xchg_finish_round(ctx, full ? 3 : 2, s));
         pending_fold = true;
         const HostSlot *slot;
-        GKR_TRY(ctx->wait_slot(s, &slot));
+        HostSlot xsum;
+        GKR_TRY(xchg_wait(ctx, xa, full ? 3 : 2, s, &xsum, &slot));
         GKR_TRY(consume_round(ctx, t, io, j, full, slot, st, last_hash));
     }
     io.W_last = Wc;
@@ -1222,31 +1338,56 @@ static uint64_t lookahead_entries() {
 // it evaluates message j+1 at once -- a round then costs max(hash, device) instead of hash + device.
 static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *last_hash, const HFr *claim_in,
                           HFr *claim_out) {
-    const uint32_t k = io.k;
-    const uint64_t N = (uint64_t)1 << k;
-    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 2, 4)));
-    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(N / 4, 4)));
+    // Table-sharded layers (io.shard_bits > 0): H, W, A hold this rank's rows and every reducing kernel that runs on
+    // shards combines its totals across the ranks before it publishes (XchgArg).  Level g is where the shards have
+    // become small: T_g is gathered (fold with r_{g-1}, every rank's shard, global index order) and everything from
+    // there on runs replicated without exchange -- including the persistent tail kernel.
+    const uint32_t k = io.k, lb = io.shard_bits;
+    const bool sharded = lb > 0;
+    const uint64_t N = (uint64_t)1 << k, Nloc = N >> lb;
+    uint32_t g = 0;                                  // 0: not sharded
+    if (sharded) {
+        g = 1;
+        while ((Nloc >> (g - 1)) > kGatherEntries / 2) ++g;
+    }
+    const uint64_t gathered_n = sharded ? (N >> (g - 1)) : 0;
+    GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(std::max<uint64_t>(Nloc / 2, 4), gathered_n)));
+    GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(std::max<uint64_t>(Nloc / 4, 4), gathered_n)));
     GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
-    // level j = 1..k: T_j has N / 2^(j-1) entries; T_1 = the inputs, T_j (j >= 2) ping-pongs between foldA / foldB
+    // level j = 1..k: T_1 = the inputs, T_j (j >= 2) ping-pongs between foldA / foldB; local levels (j < g) have
+    // Nloc / 2^(j-1) entries, replicated ones N / 2^(j-1); T_g itself is set by the gather
     struct Level {
         const Fr *H, *W, *A;
         uint64_t n;
     };
     std::vector<Level> T(k + 1);
-    T[1] = Level{io.H, io.W, io.A, N};
+    T[1] = Level{io.H, io.W, io.A, Nloc};
     for (uint32_t j = 2; j <= k; ++j) {
-        DevBuf &dst = (j & 1) ? ctx->foldB : ctx->foldA;      // T_2 (N/2 entries) lives in foldA
-        const uint64_t n = N >> (j - 1);
+        DevBuf &dst = (j & 1) ? ctx->foldB : ctx->foldA;      // T_2 lives in foldA
+        const uint64_t n = (sharded && j < g ? Nloc : N) >> (j - 1);
         Fr *h = dst.as<Fr>();
         T[j] = Level{h, h + n, h + 2 * n, n};
     }
+    RoundState st{claim_in ? *claim_in : hfr_zero(), hfr_zero(), claim_in != nullptr};
+    // the gather that produces T_g: from the inputs (g == 1) or by folding T_{g-1} with the pending challenge
+    auto gather_level = [&]() -> int {
+        const Level &src = g == 1 ? T[1] : T[g - 1];
+        const Fr *cur[3] = {src.H, src.W, src.A}, *got[3];
+        uint64_t n_out = 0;
+        GKR_TRY(gather_shards(ctx, cur, g > 1, st.r, src.n, got, &n_out));
+        T[g] = Level{got[0], got[1], got[2], n_out};
+        return GKR_OK;
+    };
+    if (sharded && g == 1) GKR_TRY(gather_level());           // tiny shards: replicated from the start
+    auto local_level = [&](uint32_t j) { return sharded && j < g; };
     // s = first level small enough for look-ahead rounds (and with at least 4 entries); k + 1 if there is none
     uint32_t s = k + 1;
     for (uint32_t j = 1; j + 1 <= k; ++j)
-        if (T[j].n <= lookahead_entries()) { s = j; break; }
+        if (T[j].n <= lookahead_entries() && T[j].n >= 4) { s = j; break; }
     struct Poly {                 // P_j, j = s..k-1
         uint32_t seq = 0;
         bool launched = false, commanded = false;
+        XchgArg xa{};             // local levels of a sharded layer: the exchange its six sums go through
     };
     std::vector<Poly> P(k + 1);
     struct AbortGuard {
@@ -1264,7 +1405,6 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         }
     } guard{ctx, P};
     const bool can_prelaunch = ctx->prelaunch && !ctx->profiling;
-    RoundState st{claim_in ? *claim_in : hfr_zero(), hfr_zero(), claim_in != nullptr};
 
     auto tail_args = [&](uint32_t u0, uint32_t n_levels, uint32_t seq0) {
         PolyTailArgs a{};
@@ -1277,9 +1417,7 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
     };
     auto start_poly = [&](uint32_t j) -> int {      // j == s: reads T_s; j > s: folds T_{j-1} with r_{j-1} = st.r into T_j
         Poly &p = P[j];
-        const bool fold = j > s;
-        const Level &in = fold ? T[j - 1] : T[j];
-        const uint64_t quads = T[j].n / 4;
+        bool fold = j > s;
         if (p.launched) {
             const FrConstMul rc = make_const_mul(st.r);
             if (!ctx->test_drop_cmd) write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), &rc, p.seq);
@@ -1287,25 +1425,35 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
             ctx->prelaunched_pending--;
             return GKR_OK;
         }
+        if (sharded && j == g && fold) {              // the fold happens inside the gather; P_g then reads T_g
+            GKR_TRY(gather_level());
+            fold = false;
+        }
+        const Level &in = fold ? T[j - 1] : T[j];
+        const uint64_t quads = T[j].n / 4;
         p.seq = ctx->next_seq();
         const FrConstMul rc = fold ? make_const_mul(st.r) : FrConstMul{};
+        const XchgArg xa = local_level(j) ? xchg_begin(ctx, "poly") : XchgArg{};
+        p.xa = xa;
         ctx->begin_launch();
-        if (fold && quads <= (uint64_t)gkr_poly_tail_max_quads()) {
+        if (fold && quads <= (uint64_t)gkr_poly_tail_max_quads() && !local_level(j)) {
             // the tail kernel always reads its challenge from a command block: fill it first, then launch
             write_cmd(ctx->cmds_host + (p.seq % gkr_ctx::kSlots), &rc, p.seq);
             launch_gkr_poly_tail(tail_args(j, 1, p.seq), ctx->stream);
         } else {
             launch_gkr_poly(fold, in.H, in.W, in.A, const_cast<Fr *>(T[j].H), const_cast<Fr *>(T[j].W), const_cast<Fr *>(T[j].A), rc,
-                            quads, ctx->ws, ctx->slot_dev(p.seq), p.seq, ctx->stream);
+                            quads, ctx->ws, ctx->slot_dev(p.seq), p.seq, ctx->stream, nullptr, xa);
         }
         ctx->end_launch(quads * 2 >= kTailPairs ? (fold ? KC_ROUND_FUSED : KC_ROUND) : KC_ROUND_TAIL,
                         fold ? 144.0 * in.n : 80.0 * in.n);
         GKR_TRY(ctx->check_launch("gkr_poly"));
+        if (local_level(j)) GKR_TRY(xchg_finish_round(ctx, 6, p.seq));
         p.launched = p.commanded = true;
         // once the next level fits the single-CTA tail kernel, every remaining level is enqueued now as ONE kernel
         // that waits for its challenges on the device (consecutive sequence numbers).  Multi-CTA levels are not
         // pre-launched: many CTAs polling host memory at once were measured to delay the command by 25 us.
-        if (can_prelaunch && j + 1 <= k - 1 && !P[j + 1].launched && T[j + 1].n / 4 <= (uint64_t)gkr_poly_tail_max_quads()) {
+        if (can_prelaunch && j + 1 <= k - 1 && !P[j + 1].launched && T[j + 1].n / 4 <= (uint64_t)gkr_poly_tail_max_quads() &&
+            !(sharded && j + 1 <= g)) {
             const uint32_t u = j + 1, n_levels = k - u;
             const uint32_t seq0 = ctx->next_seq_run(n_levels);          // consecutive: the kernel uses seq0 + level
             for (uint32_t v = u; v + 1 <= k; ++v) {
@@ -1328,25 +1476,34 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         const uint32_t sq = fused_first ? io.first_round_seq : ctx->next_seq();
         const bool full = !st.have_claim;
         const double t_launch0 = g_trace ? now_seconds() : 0.0;
+        bool fold = j > 1;
+        if (sharded && j == g && fold) {              // T_g comes out of the gather; the round then reads it
+            GKR_TRY(gather_level());
+            fold = false;
+        }
+        const XchgArg xa = fused_first ? io.first_round_xa : local_level(j) ? xchg_begin(ctx, "direct") : XchgArg{};
         ctx->begin_launch();
         if (fused_first) {
             // launched by the caller together with the wiring sums (launch_wiring_round1)
-        } else if (j == 1) {
-            launch_gkr_round(false, full, T[1].H, T[1].W, T[1].A, nullptr, nullptr, nullptr, FrConstMul{}, N / 2, ctx->ws,
-                             ctx->slot_dev(sq), sq, ctx->stream);
-            ctx->end_launch(N / 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full ? 96.0 : 80.0) * N);
+        } else if (!fold) {
+            launch_gkr_round(false, full, T[j].H, T[j].W, T[j].A, nullptr, nullptr, nullptr, FrConstMul{}, T[j].n / 2, ctx->ws,
+                             ctx->slot_dev(sq), sq, ctx->stream, nullptr, xa);
+            ctx->end_launch(T[j].n / 2 >= kTailPairs ? KC_ROUND : KC_ROUND_TAIL, (full ? 96.0 : 80.0) * T[j].n);
         } else {
             launch_gkr_round(true, full, T[j - 1].H, T[j - 1].W, T[j - 1].A, const_cast<Fr *>(T[j].H), const_cast<Fr *>(T[j].W),
-                             const_cast<Fr *>(T[j].A), make_const_mul(st.r), T[j].n / 2, ctx->ws, ctx->slot_dev(sq), sq, ctx->stream);
+                             const_cast<Fr *>(T[j].A), make_const_mul(st.r), T[j].n / 2, ctx->ws, ctx->slot_dev(sq), sq, ctx->stream,
+                             nullptr, xa);
             ctx->end_launch(T[j].n / 2 >= kTailPairs ? KC_ROUND_FUSED : KC_ROUND_TAIL, 144.0 * T[j - 1].n);
         }
         GKR_TRY(ctx->check_launch("gkr_round"));
+        if (!fused_first && local_level(j)) GKR_TRY(xchg_finish_round(ctx, full ? 3 : 2, sq));
         if (g_trace && !fused_first) { g_trace_t[TS_DIRECT_LAUNCH] += now_seconds() - t_launch0; g_trace_n[TS_DIRECT_LAUNCH]++; }
         if (j == s) GKR_TRY(start_poly(s));           // right behind the kernel that produced T_s: prepares message s+1
         if (j == last_direct) GKR_TRY(release_aux_jobs(ctx, true));   // bulk work of the previous layer goes behind these
         const HostSlot *slot;
+        HostSlot xsum;
         g_wait_site = TS_WAIT_DIRECT;
-        GKR_TRY(ctx->wait_slot(sq, &slot));
+        GKR_TRY(xchg_wait(ctx, xa, full ? 3 : 2, sq, &xsum, &slot));
         g_wait_site = TS_WAIT_OTHER;
         TraceScope ts_consume(TS_CONSUME);
         GKR_TRY(consume_round(ctx, t, io, j - 1, full, slot, st, last_hash));
@@ -1359,9 +1516,10 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
             GKR_TRY(start_poly(j));
         }
         const HostSlot *slot;
+        HostSlot xsum;
         g_wait_site = TS_WAIT_AHEAD;
         const double t_w0 = g_trace ? now_seconds() : 0.0;
-        GKR_TRY(ctx->wait_slot(P[j - 1].seq, &slot));
+        GKR_TRY(xchg_wait(ctx, P[j - 1].xa, 6, P[j - 1].seq, &xsum, &slot));
         g_wait_site = TS_WAIT_OTHER;
         if (g_trace) {
             int lg = 0;
@@ -1369,7 +1527,7 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
             g_wait_by_log2[lg] += now_seconds() - t_w0;
         }
         TraceScope ts_consume(TS_CONSUME);
-        if (slot->aux[2] == 0xDEADu) {
+        if (!local_level(j - 1) && slot->aux[2] == 0xDEADu) {
             set_last_error("pre-launched look-ahead kernel %u gave up waiting for its challenge", j - 1);
             return kRetryNoPrelaunch;
         }
@@ -1420,7 +1578,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         set_last_error("gkr_prove: witness/circuit/context mismatch");
         return GKR_ERR_INVALID;
     }
-    if (c->n_ranks != (ctx->nccl_comm ? ctx->n_ranks : 1) || c->rank != (ctx->nccl_comm ? ctx->rank : 0)) {
+    if (c->n_ranks != ctx->dist_ranks() || c->rank != (ctx->comm_active ? ctx->rank : 0)) {
         set_last_error("gkr_prove: the circuit was created for %d rank(s) / rank %d; create it after gkr_comm_init on "
                        "this context", c->n_ranks, c->rank);
         return GKR_ERR_INVALID;
@@ -1534,6 +1692,20 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         ctx->stats.d2h_bytes += n * sizeof(Fr);
     }
 
+    if (c->n_ranks > 1) {
+        // table-sharded layers: size every workspace a phase can need now, so that nothing allocates (and implicitly
+        // synchronises the device) once kernels that wait for the other ranks are in flight
+        const uint64_t nloc_max = std::max<uint64_t>(Nmax >> shard_bits, 4);
+        const uint64_t gathered_max = (kGatherEntries / 2) * (uint64_t)c->n_ranks;
+        GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(std::max<uint64_t>(Nmax / 2, 64), gathered_max)));
+        GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(std::max<uint64_t>(Nmax / 2, 64), gathered_max)));
+        GKR_TRY(ctx->shard_mini.ensure(sizeof(Fr) * 3 * std::max<uint64_t>(gathered_max, kGatherEntries * (uint64_t)c->n_ranks)));
+        GKR_TRY(ctx->shard_w.ensure(sizeof(Fr) * nloc_max));
+        GKR_TRY(ctx->eq_scratch.ensure(sizeof(Fr) * 2 * ((size_t)1 << ((c->max_k + 1) / 2 + 1))));
+        GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        group_barrier(ctx);
+    }
+
     // z_0 = 0 (prover.rs:16-21)
     std::vector<HFr> z(c->k[0], hfr_zero());
     std::vector<HFr> rs;
@@ -1567,16 +1739,27 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
             Wrounds = ctx->shard_w.as<Fr>();
         }
         GKR_TRY(eq_table_dev(ctx, z.data(), L.k_out, ctx->eqz.as<Fr>()));
-        const bool lookahead = ctx->lookahead && !ctx->paranoid && !L.sharded;
-        // single pass: wiring sums + first round of the phase (needs whole 32-row blocks in both halves)
-        const bool fuse_wiring = lookahead && N >= 64;
+        // sharded layers run the same look-ahead phases on their shards (GKR_SHARDED_LOOKAHEAD=0: the plain round chain)
+        static const bool sharded_lookahead = [] {
+            const char *e = getenv("GKR_SHARDED_LOOKAHEAD");
+            return !(e && atoi(e) == 0);
+        }();
+        const bool lookahead = ctx->lookahead && !ctx->paranoid && (!L.sharded || sharded_lookahead);
+        // single pass: wiring sums + first round of the phase (needs whole 32-row blocks in both halves of this rank's rows)
+        const bool fuse_wiring = lookahead && Nrows >= 64;
         uint32_t seq_first = 0;
+        XchgArg first_xa{};
+        if (getenv("GKR_XCHG_TRACE"))
+            fprintf(stderr, "[xchg] rank %d layer %u k=%u sharded=%d Nrows=%llu lookahead=%d fuse=%d\n", ctx->rank, li, k, (int)L.sharded,
+                    (unsigned long long)Nrows, (int)lookahead, (int)fuse_wiring);
         ctx->begin_launch();
         if (fuse_wiring) {
             seq_first = ctx->next_seq();
-            launch_wiring_round1(false, true, L.rowptr1, L.gate1, L.other1, ctx->eqz.as<Fr>(), W, nullptr, Wrounds, H, A, N, ctx->ws,
-                                 ctx->slot_dev(seq_first), seq_first, ctx->stream);
-            ctx->end_launch(KC_WIRING, 76.0 * L.n_edges1 + 96.0 * N);
+            first_xa = L.sharded ? xchg_begin(ctx, "wiring1") : XchgArg{};
+            launch_wiring_round1(false, true, L.rowptr1, L.gate1, L.other1, ctx->eqz.as<Fr>(), W, nullptr, Wrounds, H, A, Nrows, ctx->ws,
+                                 ctx->slot_dev(seq_first), seq_first, ctx->stream, first_xa);
+            ctx->end_launch(KC_WIRING, 76.0 * L.n_edges1 + 96.0 * Nrows);
+            if (L.sharded) GKR_TRY(xchg_finish_round(ctx, 3, seq_first));
         } else {
             launch_wiring_phase1(L.rowptr1, L.gate1, L.other1, L.n_edges1, ctx->eqz.as<Fr>(), W, ctx->wP.as<Fr>(),
                                  ctx->wQ.as<Fr>(), H, A, Nrows, ctx->stream);
@@ -1609,15 +1792,17 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         io.challenges = rs.data();
         io.msgs = &P->msgs[3 * ro]; io.msg_len = &P->msg_len[ro]; io.chal_out = &P->chal[ro];
         io.first_round_seq = seq_first;
+        io.first_round_xa = first_xa;
         HFr claim = hfr_zero();
         if (!lookahead) GKR_TRY(release_aux_jobs(ctx, false));
         auto run_phase_any = [&](const HFr *claim_in) -> int {
             for (int attempt = 0;; ++attempt) {
-                const int rc = L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, claim_in, &claim)
-                             : lookahead ? run_phase_poly(ctx, t, io, &last_hash, claim_in, &claim)
+                const int rc = lookahead ? run_phase_poly(ctx, t, io, &last_hash, claim_in, &claim)
+                             : L.sharded ? run_phase_sharded(ctx, t, io, &last_hash, claim_in, &claim)
                                          : run_phase(ctx, t, io, &last_hash, claim_in, &claim);
                 if (rc != kRetryNoPrelaunch) return rc;
-                if (attempt > 0 || !ctx->prelaunch) return GKR_ERR_INTERNAL;
+                // (not for sharded layers: the ranks' exchange counters must stay in lockstep)
+                if (attempt > 0 || !ctx->prelaunch || L.sharded) return GKR_ERR_INTERNAL;
                 // the inputs of the phase (H, W, A of size N) are never written: run it again from the start, with
                 // every round launched on demand; the messages and challenges are recomputed identically
                 fprintf(stderr, "[gkr_b200] a pre-launched kernel never saw its challenge (kernels serialised by a tool?): "
@@ -1642,9 +1827,11 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         ctx->begin_launch();
         if (fuse_wiring) {
             seq_first = ctx->next_seq();
-            launch_wiring_round1(true, false, L.rowptr2, L.gate2, L.other2, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu, Wrounds, H, A, N,
-                                 ctx->ws, ctx->slot_dev(seq_first), seq_first, ctx->stream);
-            ctx->end_launch(KC_WIRING, 76.0 * L.n_edges2 + 96.0 * N);
+            first_xa = L.sharded ? xchg_begin(ctx, "wiring2") : XchgArg{};
+            launch_wiring_round1(true, false, L.rowptr2, L.gate2, L.other2, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu, Wrounds, H, A, Nrows,
+                                 ctx->ws, ctx->slot_dev(seq_first), seq_first, ctx->stream, first_xa);
+            ctx->end_launch(KC_WIRING, 76.0 * L.n_edges2 + 96.0 * Nrows);
+            if (L.sharded) GKR_TRY(xchg_finish_round(ctx, 2, seq_first));
         } else {
             launch_wiring_phase2(L.rowptr2, L.gate2, L.other2, L.n_edges2, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu,
                                  ctx->wP.as<Fr>(), H, A, Nrows, ctx->stream);
@@ -1652,6 +1839,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         }
         GKR_TRY(ctx->check_launch("wiring_phase2"));
         io.first_round_seq = seq_first;
+        io.first_round_xa = first_xa;
         if (g_trace) { g_trace_t[TS_SETUP_LAUNCH] += now_seconds() - t_setup1; g_trace_n[TS_SETUP_LAUNCH]++; }
         io.challenges = rs.data() + k;
         io.msgs = &P->msgs[3 * (ro + k)]; io.msg_len = &P->msg_len[ro + k]; io.chal_out = &P->chal[ro + k];
@@ -1927,7 +2115,7 @@ extern "C" void gkr_dev_table_free(gkr_ctx *ctx, void *dev) {
 // when n_ranks == 1), 2^(n_vars - log2 n_ranks) entries each.
 static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3], const gkr_transcript *t, gkr_fr *msgs,
                              uint8_t *msg_len, gkr_fr *chal, gkr_fr *final_vals) {
-    const int P = ctx->nccl_comm ? ctx->n_ranks : 1;
+    const int P = ctx->dist_ranks();
     uint32_t lb = 0;
     while ((1 << lb) < P) ++lb;
     const uint32_t local_vars = n_vars - lb;
@@ -1936,6 +2124,11 @@ static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3]
     GKR_TRY(ctx->foldA.ensure(sizeof(Fr) * 3 * fold_cap));
     GKR_TRY(ctx->foldB.ensure(sizeof(Fr) * 3 * fold_cap));
     GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
+    if (P > 1) {
+        GKR_TRY(ctx->shard_mini.ensure(sizeof(Fr) * 3 * kGatherEntries * (uint64_t)P));
+        GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        group_barrier(ctx);
+    }
     const HFr inv2 = hfr_inv(hfr_from_u64(2));
     const Fr *Ac = T[0], *Bc = T[1], *Cc = T[2];
     uint64_t n = Nloc;                 // entries per current table on this rank
@@ -1946,30 +2139,9 @@ static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3]
     bool gathered = (P == 1);
     for (uint32_t j = 0; j < n_vars; ++j) {
         if (!gathered && n <= std::max<uint64_t>(kGatherEntries, 2) && (pending_fold || n <= kGatherEntries / 2)) {
-            // the shards are small: fold them with the pending challenge, all-gather every rank's folded shard
-            // and continue on the full-size (replicated) tables without any further exchange
-            const uint64_t m = pending_fold ? n / 2 : n;
-            Fr *send = ctx->comm_send + 8;
-            const Fr *cur[3] = {Ac, Bc, Cc};
-            for (int i = 0; i < 3; ++i) {
-                if (pending_fold) {
-                    ctx->begin_launch();
-                    launch_fold(cur[i], send + i * m, make_const_mul(r), m, ctx->stream);
-                    ctx->end_launch(KC_OTHER, 96.0 * m);
-                    GKR_TRY(ctx->check_launch("fold"));
-                } else {
-                    GKR_CUDA_TRY(cudaMemcpyAsync(send + i * m, cur[i], m * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-                }
-            }
-            GKR_TRY(comm_all_gather(ctx, send, ctx->comm_recv, 3 * m * sizeof(Fr)));
-            GKR_TRY(ctx->shard_mini.ensure(sizeof(Fr) * 3 * m * (size_t)P));
-            Fr *mini = ctx->shard_mini.as<Fr>();
-            ctx->begin_launch();
-            launch_interleave_gathered(ctx->comm_recv, mini, P, 3, m, ctx->stream);
-            ctx->end_launch(KC_OTHER, 192.0 * m * P);
-            GKR_TRY(ctx->check_launch("interleave_gathered"));
-            Ac = mini; Bc = mini + m * P; Cc = mini + 2 * m * P;
-            n = m * (uint64_t)P;
+            const Fr *cur[3] = {Ac, Bc, Cc}, *got[3];
+            GKR_TRY(gather_shards(ctx, cur, pending_fold, r, n, got, &n));
+            Ac = got[0]; Bc = got[1]; Cc = got[2];
             pending_fold = false;
             gathered = true;
         }
@@ -1979,34 +2151,28 @@ static int sumcheck_prod_run(gkr_ctx *ctx, uint32_t n_vars, const Fr *const T[3]
         const FrConstMul rc = pending_fold ? make_const_mul(r) : FrConstMul{};
         const bool f64 = ctx->f64_folds > 0 && pending_fold && prod3_round_wants_f64(true, full, n / 4);
         const FrFoldF64 rf = f64 ? make_fold_f64(r) : FrFoldF64{};
-        Fr *dev_out = sharded_round ? ctx->comm_send : nullptr;
+        const XchgArg xa = sharded_round ? xchg_begin(ctx) : XchgArg{};
         ctx->begin_launch();
         if (!pending_fold) {
             launch_prod3_round(false, full, Ac, Bc, Cc, nullptr, nullptr, nullptr, rc, n / 2, ctx->ws, ctx->slot_dev(s), s,
-                               ctx->stream, dev_out);
+                               ctx->stream, xa);
             ctx->end_launch(n / 2 >= kTailPairs ? KC_PROD3 : KC_PROD3_TAIL, 96.0 * n);
         } else {
             DevBuf &dst = (flip ^= 1) ? ctx->foldA : ctx->foldB;
             const uint64_t half = n / 2;
             Fr *Ao = dst.as<Fr>(), *Bo = Ao + half, *Co = Bo + half;
             launch_prod3_round(true, full, Ac, Bc, Cc, Ao, Bo, Co, rc, half / 2, ctx->ws, ctx->slot_dev(s), s, ctx->stream,
-                               dev_out, f64 ? &rf : nullptr, ctx->f64_folds);
+                               xa, f64 ? &rf : nullptr, ctx->f64_folds);
             ctx->end_launch(half / 2 >= kTailPairs ? KC_PROD3_FUSED : KC_PROD3_TAIL, 96.0 * n + 96.0 * half);
             Ac = Ao; Bc = Bo; Cc = Co;
             n = half;
         }
         GKR_TRY(ctx->check_launch("prod3_round"));
-        if (sharded_round) {
-            const int K = full ? 4 : 3;
-            GKR_TRY(comm_all_gather(ctx, ctx->comm_send, ctx->comm_recv, (size_t)K * sizeof(Fr)));
-            ctx->begin_launch();
-            launch_sum_ranks_publish(ctx->comm_recv, P, K, ctx->slot_dev(s), s, ctx->stream);
-            ctx->end_launch(KC_OTHER, 32.0 * K * P);
-            GKR_TRY(ctx->check_launch("sum_ranks_publish"));
-        }
+        if (sharded_round) GKR_TRY(xchg_finish_round(ctx, full ? 4 : 3, s));
         pending_fold = true;
         const HostSlot *slot;
-        GKR_TRY(ctx->wait_slot(s, &slot));
+        HostSlot xsum;
+        GKR_TRY(xchg_wait(ctx, xa, full ? 4 : 3, s, &xsum, &slot));
         HFr g0 = to_host(slot->v[0]), gm = to_host(slot->v[1]), ginf = to_host(slot->v[2]);
         HFr g1 = full ? to_host(slot->v[3]) : hfr_zero();
         if (hf::geq_p(g0.l) || hf::geq_p(gm.l) || hf::geq_p(ginf.l) || hf::geq_p(g1.l)) {
@@ -2122,10 +2288,10 @@ extern "C" int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_var
         }
     }
     // the single-GPU entry point ignores a communicator that may be attached to the context
-    void *saved = ctx->nccl_comm;
-    ctx->nccl_comm = nullptr;
+    const bool saved = ctx->comm_active;
+    ctx->comm_active = false;
     const int rc = sumcheck_prod_run(ctx, n_vars, T, t, msgs, msg_len, chal, final_vals);
-    ctx->nccl_comm = saved;
+    ctx->comm_active = saved;
     return rc;
 }
 
@@ -2133,8 +2299,8 @@ extern "C" int gkr_sumcheck_prod_sharded(gkr_ctx *ctx, uint32_t n_tables, uint32
                                          const gkr_transcript *t, gkr_fr *msgs, uint8_t *msg_len, gkr_fr *chal,
                                          gkr_fr *final_vals) {
     if (!ctx || !local_tables || !msgs || !msg_len || !chal) return GKR_ERR_INVALID;
-    if (!ctx->nccl_comm) {
-        set_last_error("gkr_sumcheck_prod_sharded: call gkr_comm_init first");
+    if (!ctx->comm_active) {
+        set_last_error("gkr_sumcheck_prod_sharded: call gkr_comm_init (or create the contexts with gkr_comm_create) first");
         return GKR_ERR_COMM;
     }
     uint32_t lb = 0;

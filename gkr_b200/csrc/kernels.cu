@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
     k_wiring_round1(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ csr_gate, const uint32_t *__restrict__ csr_other,
                     const Fr *__restrict__ X, const Fr *__restrict__ Y, const Fr *__restrict__ wu_ptr, const Fr *__restrict__ Wtab,
                     Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n, Fr *partials, unsigned int *counter, HostSlot *slot,
-                    uint32_t seq) {
+                    uint32_t seq, XchgArg xa) {
     constexpr int K = FULL ? 3 : 2;
     __shared__ Fr stage[kWarps][2][kWiringChunk];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -336,11 +336,11 @@ __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
         acc[1] = fr_add(acc[1], fr_mul(fr_sub(h[1], h[0]), fr_sub(wh, wl)));
         if (FULL) acc[K - 1] = fr_add(acc[K - 1], fr_add(fr_mul(h[1], wh), a[1]));
     }
-    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u);
+    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, xa);
 }
 void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
                           const Fr *X, const Fr *Y, const Fr *wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
-                          HostSlot *slot, uint32_t seq, cudaStream_t s) {
+                          HostSlot *slot, uint32_t seq, cudaStream_t s, XchgArg xa) {
     const uint64_t n_blocks = n / 64;
     int grid = (int)((n_blocks + kWarps - 1) / kWarps);
     const int resident = device_sm_count() * GKR_WIRING_MINB;      // one wave: block pairs are uneven, a second wave only adds a tail
@@ -348,7 +348,7 @@ void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const 
     if (grid > ws.max_blocks) grid = ws.max_blocks;
     if (grid < 1) grid = 1;
 #define GKR_WR1(P2, F) \
-    k_wiring_round1<P2, F><<<grid, kThreads, 0, s>>>(rowptr, csr_gate, csr_other, X, Y, wu, Wtab, H, A, n, ws.partials, ws.counter, slot, seq)
+    k_wiring_round1<P2, F><<<grid, kThreads, 0, s>>>(rowptr, csr_gate, csr_other, X, Y, wu, Wtab, H, A, n, ws.partials, ws.counter, slot, seq, xa)
     if (phase2) { if (full) GKR_WR1(true, true); else GKR_WR1(true, false); }
     else { if (full) GKR_WR1(false, true); else GKR_WR1(false, false); }
 #undef GKR_WR1
@@ -369,7 +369,7 @@ __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const
                                                const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                                Fr *__restrict__ Wout, Fr *__restrict__ Aout, const KT &r,
                                                uint64_t q, Fr *partials, unsigned int *counter,
-                                               HostSlot *slot, uint32_t seq, Fr *dev_out = nullptr) {
+                                               HostSlot *slot, uint32_t seq, XchgArg xa = XchgArg{}) {
     constexpr int K = FULL ? 3 : 2;
     Fr acc[K];
     FrWide wide[LAZY ? K : 1];
@@ -447,7 +447,7 @@ __device__ __forceinline__ void gkr_round_body(const Fr *__restrict__ Hin, const
 #pragma unroll
         for (int j = 0; j < K; ++j) acc[j] = fr_add(acc[j], wide_reduce(wide[j]));
     }
-    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, dev_out);
+    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, xa);
 }
 // ------------------------------------------------------------------------------------------------
 // Look-ahead round: the message of the NEXT round as a polynomial in the challenge that is not known yet.
@@ -472,7 +472,7 @@ __device__ __forceinline__ void gkr_poly_body(const Fr *__restrict__ Hin, const 
                                               const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                               Fr *__restrict__ Wout, Fr *__restrict__ Aout, const KT &r,
                                               uint64_t q4, Fr *partials, unsigned int *counter, HostSlot *slot,
-                                              uint32_t seq) {
+                                              uint32_t seq, XchgArg xa = XchgArg{}) {
     __shared__ Fr sh[3][4][kPolyChunk];
     __shared__ Fr red[6][kMaxWarps];
     __shared__ Fr wred[kWarps][2];
@@ -535,7 +535,7 @@ __device__ __forceinline__ void gkr_poly_body(const Fr *__restrict__ Hin, const 
         acc[2] = fr_add(wred[4][0], wred[5][0]);
         acc[5] = fr_add(wred[6][0], wred[7][0]);
     }
-    grid_publish_cta_totals<6>(acc, red, partials, counter, slot, seq, 0u);
+    grid_publish_cta_totals<6>(acc, red, partials, counter, slot, seq, 0u, xa);
 }
 static_assert(kThreads == 4 * kPolyChunk, "gkr_poly_body maps four threads to each quad of a chunk");
 // Large tables: two threads per quad and no shared memory or CTA barriers (the four-thread form above is bound by
@@ -548,7 +548,7 @@ __device__ __forceinline__ void gkr_poly2_body(const Fr *__restrict__ Hin, const
                                                const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                                Fr *__restrict__ Wout, Fr *__restrict__ Aout, const KT &r,
                                                uint64_t q4, Fr *partials, unsigned int *counter, HostSlot *slot,
-                                               uint32_t seq) {
+                                               uint32_t seq, XchgArg xa = XchgArg{}) {
     __shared__ Fr red[6][kMaxWarps];
     __shared__ Fr wred[kWarps][2][3];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -621,23 +621,23 @@ __device__ __forceinline__ void gkr_poly2_body(const Fr *__restrict__ Hin, const
             tot[5] = fr_add(tot[5], wred[wv][1][2]);     // E2
         }
     }
-    grid_publish_cta_totals<6>(tot, red, partials, counter, slot, seq, 0u);
+    grid_publish_cta_totals<6>(tot, red, partials, counter, slot, seq, 0u, xa);
 }
 template <bool FOLD>
 __global__ void __launch_bounds__(kThreads, 2) k_gkr_poly2(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
                                                            const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                                            Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
                                                            uint64_t q4, Fr *partials, unsigned int *counter,
-                                                           HostSlot *slot, uint32_t seq) {
-    gkr_poly2_body<FOLD>(Hin, Win, Ain, Hout, Wout, Aout, r, q4, partials, counter, slot, seq);
+                                                           HostSlot *slot, uint32_t seq, XchgArg xa) {
+    gkr_poly2_body<FOLD>(Hin, Win, Ain, Hout, Wout, Aout, r, q4, partials, counter, slot, seq, xa);
 }
 template <bool FOLD>
 __global__ void __launch_bounds__(kThreads, 2) k_gkr_poly(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
                                                           const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                                           Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
                                                           uint64_t q4, Fr *partials, unsigned int *counter,
-                                                          HostSlot *slot, uint32_t seq) {
-    gkr_poly_body<FOLD>(Hin, Win, Ain, Hout, Wout, Aout, r, q4, partials, counter, slot, seq);
+                                                          HostSlot *slot, uint32_t seq, XchgArg xa) {
+    gkr_poly_body<FOLD>(Hin, Win, Ain, Hout, Wout, Aout, r, q4, partials, counter, slot, seq, xa);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_gkr_poly_cmd(const Fr *__restrict__ Hin, const Fr *__restrict__ Win,
                                                               const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
@@ -785,7 +785,7 @@ void launch_gkr_poly_tail(const PolyTailArgs &a, cudaStream_t s) {
 int gkr_poly_tail_max_quads() { return kTailQuads; }
 
 void launch_gkr_poly(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
-                     uint64_t quads, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s, const HostCmd *cmd) {
+                     uint64_t quads, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s, const HostCmd *cmd, XchgArg xa) {
     static const uint64_t poly2_min = [] {               // tables from this many quads up use the two-thread form
         const char *e = getenv("GKR_POLY2_MIN_LOG2");
         return (uint64_t)1 << (e ? atoi(e) : 13);
@@ -797,14 +797,14 @@ void launch_gkr_poly(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout,
         }();
         const int cap2 = device_sm_count() * per_sm2;
         const int grid2 = grid_for(2 * quads, cap2 < ws.max_blocks ? cap2 : ws.max_blocks);
-        if (fold) k_gkr_poly2<true><<<grid2, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
-        else k_gkr_poly2<false><<<grid2, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
+        if (fold) k_gkr_poly2<true><<<grid2, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq, xa);
+        else k_gkr_poly2<false><<<grid2, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq, xa);
         return;
     }
     const int grid = grid_for(4 * quads, ws.max_blocks);      // 64 quads per CTA pass
     if (cmd) k_gkr_poly_cmd<<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, cmd, quads, ws.partials, ws.counter, slot, seq);
-    else if (fold) k_gkr_poly<true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
-    else k_gkr_poly<false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq);
+    else if (fold) k_gkr_poly<true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq, xa);
+    else k_gkr_poly<false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, quads, ws.partials, ws.counter, slot, seq, xa);
 }
 
 #ifndef GKR_ROUND_MINB
@@ -815,8 +815,8 @@ __global__ void __launch_bounds__(kThreads, LAZY ? 2 : GKR_ROUND_MINB) k_gkr_rou
                                                            const Fr *__restrict__ Ain, Fr *__restrict__ Hout,
                                                            Fr *__restrict__ Wout, Fr *__restrict__ Aout, FrConstMul r,
                                                            uint64_t q, Fr *partials, unsigned int *counter,
-                                                           HostSlot *slot, uint32_t seq, Fr *dev_out) {
-    gkr_round_body<FOLD, FULL, LAZY>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq, dev_out);
+                                                           HostSlot *slot, uint32_t seq, XchgArg xa) {
+    gkr_round_body<FOLD, FULL, LAZY>(Hin, Win, Ain, Hout, Wout, Aout, r, q, partials, counter, slot, seq, xa);
 }
 // pre-launched variant: waits for the challenge's constant table in a mapped command block
 template <bool FULL>
@@ -844,16 +844,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_gkr_round_cmd(const Fr *__restr
 static inline bool use_lazy_gkr(uint64_t pairs) { return pairs >= ((uint64_t)1 << 21); }
 template <bool FOLD, bool FULL>
 static void launch_gkr_round_t(const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
-                               uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s, Fr *dev_out) {
+                               uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s, XchgArg xa) {
     const int grid = use_lazy_gkr(pairs) ? round_grid(pairs, ws) : grid_for(pairs, ws.max_blocks);
     if (use_lazy_gkr(pairs))
-        k_gkr_round<FOLD, FULL, true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq, dev_out);
+        k_gkr_round<FOLD, FULL, true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq, xa);
     else
-        k_gkr_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq, dev_out);
+        k_gkr_round<FOLD, FULL, false><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, r, pairs, ws.partials, ws.counter, slot, seq, xa);
 }
 void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
                       const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s,
-                      const HostCmd *cmd, Fr *dev_out) {
+                      const HostCmd *cmd, XchgArg xa) {
     if (cmd) {
         const int grid = grid_for(pairs, ws.max_blocks);
         if (full) k_gkr_round_cmd<true><<<grid, kThreads, 0, s>>>(H, W, A, Hout, Wout, Aout, cmd, pairs, ws.partials, ws.counter, slot, seq);
@@ -861,11 +861,11 @@ void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *
         return;
     }
     if (fold) {
-        if (full) launch_gkr_round_t<true, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, dev_out);
-        else launch_gkr_round_t<true, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, dev_out);
+        if (full) launch_gkr_round_t<true, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, xa);
+        else launch_gkr_round_t<true, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, xa);
     } else {
-        if (full) launch_gkr_round_t<false, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, dev_out);
-        else launch_gkr_round_t<false, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, dev_out);
+        if (full) launch_gkr_round_t<false, true>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, xa);
+        else launch_gkr_round_t<false, false>(H, W, A, Hout, Wout, Aout, r, pairs, ws, slot, seq, s, xa);
     }
 }
 
@@ -900,6 +900,33 @@ __global__ void __launch_bounds__(kThreads) k_interleave_gathered(const Fr *__re
 }
 void launch_interleave_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_tables, uint64_t m, cudaStream_t s) {
     k_interleave_gathered<<<stream_grid((uint64_t)n_ranks * n_tables * m), kThreads, 0, s>>>(gathered, out, n_ranks, n_tables, m);
+}
+// shared-host exchange: the folded shards were written to this rank's staging area (mapped host memory) by the kernels
+// queued before; raise the flag of the exchange row so that the peers' hosts know the area is complete
+__global__ void k_xchg_flag(XchgArg xa) {
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        xa.out->flag = xa.seq;
+    }
+}
+void launch_xchg_flag(XchgArg xa, cudaStream_t s) { k_xchg_flag<<<1, 32, 0, s>>>(xa); }
+// ... and, once every rank's flag is up: staged[rank][table][i] -> n_tables contiguous tables of m * n_ranks entries in
+// global index order idx = i * n_ranks + rank (reads of mapped host memory: ~100 KB per rank, once per phase)
+__global__ void __launch_bounds__(kThreads) k_interleave_staged(StagedPtrs staged, Fr *__restrict__ out, int n_ranks, int n_tables,
+                                                                uint64_t m) {
+    const uint64_t total = (uint64_t)n_ranks * n_tables * m;
+    for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < total; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t t = x / (m * n_ranks), idx = x % (m * n_ranks);
+        const uint64_t i = idx / n_ranks, rk = idx % n_ranks;
+        const uint4 *q = reinterpret_cast<const uint4 *>(staged.p[rk] + t * m + i);
+        const uint4 lo = __ldcv(q), hi = __ldcv(q + 1);
+        uint4 *o = reinterpret_cast<uint4 *>(out + x);
+        o[0] = lo;
+        o[1] = hi;
+    }
+}
+void launch_interleave_staged(const StagedPtrs &staged, Fr *out, int n_ranks, int n_tables, uint64_t m, cudaStream_t s) {
+    k_interleave_staged<<<stream_grid((uint64_t)n_ranks * n_tables * m), kThreads, 0, s>>>(staged, out, n_ranks, n_tables, m);
 }
 // ------------------------------------------------------------------------------------------------
 // verifier side: add_i(z,b,c) and mult_i(z,b,c) = sum over gates of eq(z,g) eq(b,l_g) eq(c,r_g), split by type

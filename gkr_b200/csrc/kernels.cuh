@@ -38,6 +38,32 @@ struct ReduceWs {
     int max_blocks;
 };
 
+// ---- multi-GPU exchange of the per-round partial sums -------------------------------------------------
+// All ranks share one block of pinned, device-mapped HOST memory (one allocation inside a process, POSIX shared memory
+// registered with CUDA between processes): a ring of kXchgRing rows with one 256-byte entry per rank, plus one staging
+// area per rank for the one-off gather of the folded shards.  The last CTA of a reducing kernel writes its totals into
+// ITS entry of row (seq % kXchgRing) and then the flag = seq (system-scope fence in between) -- instead of publishing to
+// its own host slot -- and every rank's host polls the n_ranks entries of the row and adds them in rank order (exact
+// modular sums: bit-identical everywhere).  No kernel ever waits for another GPU, so nothing depends on kernels of
+// different ranks being co-scheduled (ranks may even share a device), there is no NCCL call and no extra launch per
+// round.  A rank can be at most a few exchanges ahead of its peers (the next message needs their contribution), far
+// less than the ring length.
+constexpr int kMaxRanks = 8;
+constexpr int kXchgRing = 32;
+struct alignas(256) XchgEntry {
+    Fr v[6];
+    uint32_t aux[15];
+    volatile uint32_t flag;
+};
+static_assert(sizeof(XchgEntry) == 256, "XchgEntry layout");
+// what a reducing kernel does with its totals: publish to the host slot (default), write them to this rank's entry of
+// the shared exchange row (out + seq), or -- fallback exchange -- store them for an NCCL all-gather (dev_out)
+struct XchgArg {
+    XchgEntry *out = nullptr;        // device address of entry [seq % kXchgRing][rank] in the shared block
+    uint32_t seq = 0;
+    Fr *dev_out = nullptr;
+};
+
 // ---- conversions / generators ------------------------------------------------------------------
 void launch_to_mont(const Fr *in, Fr *out, uint64_t n, unsigned int *err_flag, cudaStream_t s);
 void launch_from_mont(const Fr *in, Fr *out, uint64_t n, cudaStream_t s);
@@ -65,7 +91,7 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 // sums like launch_gkr_round(fold = false, full, ...) would.  phase2: Y = equ and wu = W(u); else Y = W, wu unused.
 void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
                           const Fr *X, const Fr *Y, const Fr *wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
-                          HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
+                          HostSlot *slot_dev, uint32_t seq, cudaStream_t s, XchgArg xa = XchgArg{});
 
 // ---- sumcheck rounds --------------------------------------------------------------------------
 // GKR round (degree 2) on (H, W, A).  Publishes v[0] = g(0), v[1] = X^2 coefficient, and v[2] = g(1)
@@ -77,13 +103,13 @@ void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const 
 // (bounded spin) in the mapped command block, so that launch latency overlaps the host transcript.
 void launch_gkr_round(bool fold, bool full, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout,
                       const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
-                      cudaStream_t s, const HostCmd *cmd = nullptr, Fr *dev_out = nullptr);
+                      cudaStream_t s, const HostCmd *cmd = nullptr, XchgArg xa = XchgArg{});
 // Look-ahead round (see kernels.cu): folds 8*quads-entry tables with r into 4*quads-entry ones (fold == true) and
 // publishes the six sums Q0, Q1, Q2, E0, E1, E2 from which the host evaluates the NEXT round's message at the next
 // challenge.  cmd != nullptr: pre-launched, waits for r in the command block.
 void launch_gkr_poly(bool fold, const Fr *H, const Fr *W, const Fr *A, Fr *Hout, Fr *Wout, Fr *Aout, const FrConstMul &r,
                      uint64_t quads, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq, cudaStream_t s,
-                     const HostCmd *cmd = nullptr);
+                     const HostCmd *cmd = nullptr, XchgArg xa = XchgArg{});
 // single-CTA tail of a look-ahead phase: levels u0 .. u0 + n_levels - 1 (T_u has N >> (u-1) entries per table, at most
 // 4 * gkr_poly_tail_max_quads() for u0); level u folds T_{u-1} (the first from H0/W0/A0, later ones from shared memory)
 // with the challenge in command block seq0 + (u - u0), writes T_u to buf_even / buf_odd (by parity of u; tables at
@@ -107,11 +133,16 @@ void launch_take_strided(const Fr *in, Fr *out, uint64_t first, uint64_t stride,
 // see prod3_round_wants_f64); the published values are bit-identical either way.
 void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
                         const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot_dev, uint32_t seq,
-                        cudaStream_t s, Fr *dev_out = nullptr, const FrFoldF64 *rf = nullptr, int nf = 0);
+                        cudaStream_t s, XchgArg xa = XchgArg{}, const FrFoldF64 *rf = nullptr, int nf = 0);
 bool prod3_round_wants_f64(bool fold, bool full, uint64_t pairs);
 // multi-GPU: sum the per-rank partial totals (rank-major, Montgomery) and publish; gathered final entries -> tables
 void launch_sum_ranks_publish(const Fr *gathered, int n_ranks, int count, HostSlot *slot_dev, uint32_t seq, cudaStream_t s);
 void launch_interleave_gathered(const Fr *gathered, Fr *out, int n_ranks, int n_tables, uint64_t m, cudaStream_t s);
+// shared-host form: raise this rank's flag of an exchange row once everything queued before on the stream is done
+void launch_xchg_flag(XchgArg xa, cudaStream_t s);
+// staged[rank]: device address of rank's staging area in the shared block, holding n_tables x m entries (table-major)
+struct StagedPtrs { const Fr *p[kMaxRanks]; };
+void launch_interleave_staged(const StagedPtrs &staged, Fr *out, int n_ranks, int n_tables, uint64_t m, cudaStream_t s);
 // plain fold out[i] = in[i] + r (in[i+half] - in[i])
 void launch_fold(const Fr *in, Fr *out, const FrConstMul &r, uint64_t half, cudaStream_t s);
 // publish up to 6 device values (Montgomery -> canonical) to a slot

@@ -141,12 +141,12 @@ __device__ __forceinline__ void block_sum(Fr (&acc)[K], Fr (*smem)[kMaxWarps]) {
 }
 
 // Grid-wide sum of K accumulators; the last CTA to arrive publishes the canonical totals.
-// If dev_out != nullptr (multi-GPU: the totals still have to be combined across ranks) the last CTA
-// stores the Montgomery totals there and nothing is published to the host.
+// Multi-GPU (xa): the totals go to this rank's entry of the shared exchange row (xa.out; every rank's host adds the
+// entries up), or -- fallback exchange -- to xa.dev_out for an NCCL all-gather; the host slot is not written then.
 // second half of grid_sum_publish: thread 0 of every CTA holds the CTA totals in acc
 template <int K>
 __device__ __forceinline__ void grid_publish_cta_totals(Fr (&acc)[K], Fr (*red)[kMaxWarps], Fr *partials, unsigned int *counter,
-                                                        HostSlot *slot, uint32_t seq, uint32_t aux0, Fr *dev_out = nullptr) {
+                                                        HostSlot *slot, uint32_t seq, uint32_t aux0, XchgArg xa = XchgArg{}) {
     __shared__ bool is_last;
     if (gridDim.x > 1) {
         if (threadIdx.x == 0) {
@@ -169,9 +169,19 @@ __device__ __forceinline__ void grid_publish_cta_totals(Fr (&acc)[K], Fr (*red)[
         if (threadIdx.x == 0) *counter = 0;
     }
     // single-CTA launches (small tables) skip the partials / ticket round trip entirely
-    if (threadIdx.x == 0 && dev_out != nullptr) {
+    if (threadIdx.x == 0 && xa.dev_out != nullptr) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) st_fr(&dev_out[j], acc[j]);
+        for (int j = 0; j < K; ++j) st_fr(&xa.dev_out[j], acc[j]);
+    }
+    if (xa.dev_out != nullptr) return;
+    if (xa.out != nullptr) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) st_fr(&xa.out->v[j], acc[j]);
+            xa.out->aux[0] = aux0;
+            __threadfence_system();
+            xa.out->flag = xa.seq;
+        }
         return;
     }
     if (threadIdx.x == 0) {
@@ -191,10 +201,10 @@ __device__ __forceinline__ void grid_publish_cta_totals(Fr (&acc)[K], Fr (*red)[
 }
 template <int K>
 __device__ __forceinline__ void grid_sum_publish(Fr (&acc)[K], Fr *partials, unsigned int *counter,
-                                                 HostSlot *slot, uint32_t seq, uint32_t aux0, Fr *dev_out = nullptr) {
+                                                 HostSlot *slot, uint32_t seq, uint32_t aux0, XchgArg xa = XchgArg{}) {
     __shared__ Fr red[K][kMaxWarps];
     block_sum<K>(acc, red);
-    grid_publish_cta_totals<K>(acc, red, partials, counter, slot, seq, aux0, dev_out);
+    grid_publish_cta_totals<K>(acc, red, partials, counter, slot, seq, aux0, xa);
 }
 
 static inline int grid_for(uint64_t work_items, int max_blocks) {

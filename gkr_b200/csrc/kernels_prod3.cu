@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1)
     k_prod3_round(const Fr *__restrict__ Ain, const Fr *__restrict__ Bin, const Fr *__restrict__ Cin, Fr *__restrict__ Aout,
                   Fr *__restrict__ Bout, Fr *__restrict__ Cout, const __grid_constant__ FrConstMul r,
                   const __grid_constant__ FrFoldF64 rf, uint64_t q, Fr *partials, unsigned int *counter, HostSlot *slot,
-                  uint32_t seq, Fr *dev_out) {
+                  uint32_t seq, XchgArg xa) {
     constexpr int K = FULL ? 4 : 3;
     extern __shared__ uint32_t wsm[];                     // SACC: [K][17][THREADS]
     Fr acc[K];
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1)
 #pragma unroll
         for (int j = 0; j < K; ++j) acc[j] = wide_reduce(wide[j]);
     }
-    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, dev_out);
+    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, xa);
 }
 
 // Variant selection for the streaming (lazy) rounds.  Default = the measured best (profiles/r02_prod3_variants.md: 2^28
@@ -167,7 +167,7 @@ static P3Variant p3_variant() {
 }
 template <bool FOLD, bool FULL, int NF, int THREADS, bool SACC>
 static void launch_p3_lazy(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const FrConstMul &r,
-                           const FrFoldF64 &rf, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, Fr *dev_out,
+                           const FrFoldF64 &rf, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, XchgArg xa,
                            cudaStream_t s) {
     constexpr int K = FULL ? 4 : 3;
     const size_t smem = SACC ? (size_t)K * 17 * THREADS * sizeof(uint32_t) : 0;
@@ -180,20 +180,20 @@ static void launch_p3_lazy(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *
     const int cap = device_sm_count() * per_sm;
     const uint64_t want = (pairs + THREADS - 1) / THREADS;
     const int grid = (int)(want < (uint64_t)cap ? want : (uint64_t)cap);
-    kern<<<grid, THREADS, smem, s>>>(A, B, C, Aout, Bout, Cout, r, rf, pairs, ws.partials, ws.counter, slot, seq, dev_out);
+    kern<<<grid, THREADS, smem, s>>>(A, B, C, Aout, Bout, Cout, r, rf, pairs, ws.partials, ws.counter, slot, seq, xa);
 }
 template <bool FOLD, bool FULL>
 static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const FrConstMul &r,
                                  const FrFoldF64 *rf, int nf, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq,
-                                 Fr *dev_out, cudaStream_t s) {
+                                 XchgArg xa, cudaStream_t s) {
     static const FrFoldF64 no_rf{};
     if (!use_lazy(pairs)) {
         k_prod3_round<FOLD, FULL, false, 0, 256, false><<<round_grid(pairs, ws), kThreads, 0, s>>>(
-            A, B, C, Aout, Bout, Cout, r, no_rf, pairs, ws.partials, ws.counter, slot, seq, dev_out);
+            A, B, C, Aout, Bout, Cout, r, no_rf, pairs, ws.partials, ws.counter, slot, seq, xa);
         return;
     }
     const P3Variant v = p3_variant();
-#define GKR_P3(NF, T, SA) launch_p3_lazy<FOLD, FULL, NF, T, SA>(A, B, C, Aout, Bout, Cout, r, rf ? *rf : no_rf, pairs, ws, slot, seq, dev_out, s)
+#define GKR_P3(NF, T, SA) launch_p3_lazy<FOLD, FULL, NF, T, SA>(A, B, C, Aout, Bout, Cout, r, rf ? *rf : no_rf, pairs, ws, slot, seq, xa, s)
 #define GKR_P3_TS(NF)                                            \
     do {                                                         \
         if (v.threads == 512) GKR_P3(NF, 512, true); else GKR_P3(NF, 256, false);                  \
@@ -213,13 +213,13 @@ static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout
 bool prod3_round_wants_f64(bool fold, bool full, uint64_t pairs) { return fold && !full && use_lazy(pairs); }
 void launch_prod3_round(bool fold, bool full, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout,
                         const FrConstMul &r, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, cudaStream_t s,
-                        Fr *dev_out, const FrFoldF64 *rf, int nf) {
+                        XchgArg xa, const FrFoldF64 *rf, int nf) {
     if (fold) {
-        if (full) launch_prod3_round_t<true, true>(A, B, C, Aout, Bout, Cout, r, rf, nf, pairs, ws, slot, seq, dev_out, s);
-        else launch_prod3_round_t<true, false>(A, B, C, Aout, Bout, Cout, r, rf, nf, pairs, ws, slot, seq, dev_out, s);
+        if (full) launch_prod3_round_t<true, true>(A, B, C, Aout, Bout, Cout, r, rf, nf, pairs, ws, slot, seq, xa, s);
+        else launch_prod3_round_t<true, false>(A, B, C, Aout, Bout, Cout, r, rf, nf, pairs, ws, slot, seq, xa, s);
     } else {
-        if (full) launch_prod3_round_t<false, true>(A, B, C, Aout, Bout, Cout, r, rf, nf, pairs, ws, slot, seq, dev_out, s);
-        else launch_prod3_round_t<false, false>(A, B, C, Aout, Bout, Cout, r, rf, nf, pairs, ws, slot, seq, dev_out, s);
+        if (full) launch_prod3_round_t<false, true>(A, B, C, Aout, Bout, Cout, r, rf, nf, pairs, ws, slot, seq, xa, s);
+        else launch_prod3_round_t<false, false>(A, B, C, Aout, Bout, Cout, r, rf, nf, pairs, ws, slot, seq, xa, s);
     }
 }
 

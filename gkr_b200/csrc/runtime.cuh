@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <functional>
@@ -87,6 +89,46 @@ inline HFr to_host(const Fr &f) {
 // process-wide pool of pinned host buffers (proof tables are handed to the caller in pinned memory so
 // the device can write them asynchronously; cudaHostAlloc is far too slow to call per proof)
 int comm_all_gather(gkr_ctx *ctx, const void *send, void *recv, size_t bytes);   // on ctx->stream
+
+// ranks created together inside one process (gkr_comm_create) may share a device.  There an implicitly synchronising
+// call of one rank (cudaMalloc, cudaHostAlloc ...) waits for the other rank's kernel, which may itself be waiting for this
+// rank's contribution to an exchange.  Collective entry points therefore do their allocations first and then meet at
+// this barrier before the first exchanging kernel is launched.
+struct LocalGroup {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 0, waiting = 0, refs = 0;
+    uint64_t generation = 0;
+    void *block = nullptr;          // the group's exchange block (portable pinned host memory)
+    void arrive_and_wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const uint64_t gen = generation;
+        if (++waiting == n) {
+            waiting = 0;
+            ++generation;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return generation != gen; });
+        }
+    }
+};
+
+// The block of pinned host memory all ranks share (kernels.cuh: XchgEntry): exchange rows, then one staging area per rank
+struct XchgBlock {
+    XchgEntry row[kXchgRing][kMaxRanks];
+    Fr stage[kMaxRanks][3 * (kGatherEntries / 2)];      // a rank's folded shard at the gather: 3 tables x <= 2^10 entries
+};
+// one rank's view of it
+struct XchgState {
+    XchgBlock *host = nullptr;      // host address
+    XchgBlock *dev = nullptr;       // the same block as addressed by this rank's device
+    bool owner = false;             // this rank allocated / created it
+    bool is_shm = false;            // POSIX shared memory registered with CUDA (one process per GPU)
+    char shm_name[64] = {};
+    uint32_t seq = 0;               // exchange counter; all ranks advance it in lockstep
+    uint32_t next() { if (++seq == 0) ++seq; return seq; }
+    LocalGroup *group = nullptr;    // in-process groups only
+};
 int default_f64_folds();       // GKR_F64_FOLDS, else the built-in default
 void *pinned_get(size_t bytes);
 void pinned_put(void *ptr, size_t bytes);
@@ -120,10 +162,16 @@ struct gkr_ctx {
     gkr::ReduceWs ws{};
     unsigned int *words = nullptr;         // [8] device words: [0] range-error flag, [4..6] support/flags scratch
 
-    // multi-GPU (comm.cpp): NCCL communicator, this rank, staging for the per-round partial sums
+    // multi-GPU (comm.cpp).  A communicator is attached either by gkr_comm_init (one process per GPU: NCCL bootstrap,
+    // mailboxes shared through CUDA IPC) or by gkr_comm_create (all ranks in this process, one host thread each).
+    // With mailboxes (xchg != nullptr) the per-round exchange happens inside the reducing kernels; otherwise it falls
+    // back to ncclAllGather + a summing kernel.
     void *nccl_comm = nullptr;
+    bool comm_active = false;
     int n_ranks = 1, rank = 0;
     Fr *comm_send = nullptr, *comm_recv = nullptr;
+    gkr::XchgState *xchg = nullptr;
+    int dist_ranks() const { return comm_active ? n_ranks : 1; }
 
     // recycled device allocations for witness tables (cudaMalloc/cudaFree per proof serialise in the driver)
     std::multimap<size_t, void *> dev_pool;          // free blocks by true size

@@ -111,14 +111,26 @@ class Prover:
     """One gkr_ctx: a device + stream.  Not thread-safe; use one Prover per thread (the reference
     proves sub-circuits concurrently from rayon workers, rust/src/aggregator.rs:353,414)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _ctx=None):
         self._L = _lib.lib()
-        ctx = C.c_void_p()
-        _lib.check(self._L.gkr_ctx_create(device, C.byref(ctx)))
-        self._ctx = ctx
+        if _ctx is None:
+            _ctx = C.c_void_p()
+            _lib.check(self._L.gkr_ctx_create(device, C.byref(_ctx)))
+        self._ctx = _ctx
         self.device = device
         self._witnesses = weakref.WeakSet()
         self._circuits = weakref.WeakSet()
+
+    @classmethod
+    def group(cls, device_ids) -> list:
+        """gkr_comm_create: one Prover per rank, all inside this process (rank r on device_ids[r]; ranks may share a
+        device).  Drive each from its own thread; the sharded entry points are collective over the group."""
+        L = _lib.lib()
+        n = len(device_ids)
+        ids = (C.c_int * n)(*device_ids)
+        ctxs = (C.c_void_p * n)()
+        _lib.check(L.gkr_comm_create(n, ids, ctxs))
+        return [cls(device_ids[r], _ctx=C.c_void_p(ctxs[r])) for r in range(n)]
 
     def close(self):
         """destroys the context after closing the circuits and witnesses created from it"""

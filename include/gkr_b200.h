@@ -167,6 +167,11 @@ int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_vars, const vo
 int gkr_comm_unique_id(uint8_t out[GKR_COMM_ID_BYTES]);
 int gkr_comm_init(gkr_ctx *ctx, int n_ranks, int rank, const uint8_t id[GKR_COMM_ID_BYTES]);
 void gkr_comm_destroy(gkr_ctx *ctx);
+/* The same communicator with every rank inside ONE process: creates n_ranks contexts (rank r on device_ids[r]; ranks may
+ * share a device) whose mailboxes address each other directly.  Each context is then driven by its own host thread;
+ * the sharded entry points are collective over the group.  No NCCL involved.  Destroy every context with
+ * gkr_ctx_destroy (in any order, after all ranks have finished). */
+int gkr_comm_create(int n_ranks, const int *device_ids, gkr_ctx **ctxs_out);
 /* Table-sharded product sumcheck over n_vars GLOBAL variables.  The tables are split on the variables
  * bound LAST, i.e. the low log2(n_ranks) index bits: rank p holds entries idx = i * n_ranks + p as
  * local_tables[t][i], i < 2^(n_vars - log2 n_ranks), Montgomery-form device buffers (gkr_dev_table_*).
