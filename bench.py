@@ -8,7 +8,11 @@ BASELINE.json config 3: 2^20 gates/layer x 16 layers, BN254 Fr, MiMC7 transcript
   value : ms per proof with circuit + witness already resident in HBM (device time, CUDA events on the
           prover's stream, max over ranks).  N > 1: every rank proves one independent proof of the same
           shape (batch distribution, no data-path collective) -> weak scaling, value = ms per proof
-          amortised over the job (max-rank time / N).
+          amortised over the job (max-rank time / N); `latency_ms_per_proof` and `proofs_per_s` say the same two ways.
+  parity: every timed path is checked inside this script -- gkr_verify on the proofs of all seeds, on the 2^24-gate layer
+          and on a sample of the batch; the verifier's chain / transcript / final-evaluation checks on the 2^24 and
+          2^28 sumchecks; at N > 1 the sharded sumcheck and the table-sharded proof bit-exact against rank 0's
+          single-GPU results.
   e2e   : the same metric through the public host API with HOST buffers: pinned input layer -> H2D ->
           on-device circuit evaluation -> proof -> Proof arrays back on the host.
 Extra objects: roofline (dominant kernel class, per-launch CUDA events inside the library),
@@ -104,11 +108,20 @@ class Clocks:
 # --------------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline: the dense oracle port on a bounded sample
 # --------------------------------------------------------------------------------------------------
+def _all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every core of the box"""
+    from oracle import oracle as orc
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    orc.set_num_threads(n)
+    return n
+
+
 def cpu_sample_ms(k: int, layers: int, sample_layers: int, seed: int = 1):
     """ms for a full `layers`-layer proof, extrapolated from proving the first `sample_layers` layers
     (all layers have the same shape and cost) with the dense CPU oracle on all host threads."""
     from gkr_b200 import synthetic as syn
     from oracle import oracle as orc
+    _all_host_threads()
     sl = min(sample_layers, layers)
     circ = syn.layered_circuit(seed, k, sl)
     inputs = syn.input_values(seed, k)
@@ -146,6 +159,7 @@ def run_reference(args):
         return
     k, layers = args.k, args.layers
     sample_layers = 1 if k >= 20 else 2
+    _all_host_threads()
     for _ in range(args.warmup):
         cpu_sample_ms(k, layers, sample_layers)
     vals = []
@@ -268,16 +282,39 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = ms_per_step / world                      # amortised ms per proof over the whole job
     e2e_value = e2e_ms / args.steps / world
+    parity = {}
+
+    # ---- seeds 1..3 for the timing of this config; every seed's proof goes through gkr_verify (the
+    # complete verifier: claim chain, transcript hashes, add_i/mult_i on the device, q, z, the input layer) ----------
+    seeds = None
+    if world == 1 and args.seeds > 1:
+        seeds = {str(seed): {"ms": round(ms_per_step, 4)}}
+        for sd in range(2, args.seeds + 1):
+            cl = syn.layered_circuit(sd, k, layers)
+            iv = syn.input_values(sd, k)
+            cc = pv.circuit(cl)
+            ww = pv.witness_eval(cc, iv)
+
+            def step_sd(cc=cc, ww=ww):
+                pv.free_raw(pv.prove_raw(cc, ww))
+            n_sd = max(2, args.steps // 2)
+            seeds[str(sd)] = {"ms": round(timed(step_sd, n_sd, 1) / n_sd, 4)}
+            seeds[str(sd)]["verified"] = bool(pv.verify(cc, pv.prove(cc, ww), iv)[0])
+            ww.close()
+            cc.close()
+        seeds[str(seed)]["verified"] = bool(pv.verify(circuit, pv.prove(circuit, witness), pinned_np)[0])
+        parity["c3_all_seeds_verified"] = all(v["verified"] for v in seeds.values())
+    elif rank == 0:
+        parity["c3_proof_verified"] = bool(pv.verify(circuit, pv.prove(circuit, witness), pinned_np)[0])
 
     # ---- per-kernel-class device timing (library-side CUDA events around every launch) --------------
     pv.profile(1)
     step_resident()
     prof = pv.profile(0)
     classes = {n: d for n, d in prof.items() if d["launches"]}
-    # dominant streaming kernel class (launches of >= 2^16 pairs; the ~500 latency-bound tail launches are listed
-    # separately under kernel_classes.gkr_round_tail)
-    # (critical-path classes only: `line` and `mobius` run on the low-priority stream, overlapped with the rounds)
-    dom = max(("gkr_round_fused", "gkr_round", "wiring", "eq"), key=lambda n: prof[n]["ms"])
+    # the class that takes the most device time, over ALL classes (the ~500 latency-bound launches on small tables are
+    # the class gkr_round_tail; `line` and `mobius` run on the low-priority stream, overlapped with the rounds)
+    dom = max(classes, key=lambda n: prof[n]["ms"])
     d = prof[dom]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -287,13 +324,19 @@ def run_ours(args):
         except Exception:
             traffic = None
     achieved = d["algo_bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    proof_bytes = sum(x["algo_bytes"] for x in prof.values())
+    dev_ms_all = sum(x["ms"] for x in prof.values())
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "launches": d["launches"], "avg_launch_us": 1e3 * d["ms"] / max(1, d["launches"]),
                 "algo_bytes_per_launch": d["algo_bytes"] / max(1, d["launches"]),
+                "share_of_device_time": d["ms"] / max(1e-9, dev_ms_all),
+                "whole_proof": {"algo_bytes": proof_bytes, "gbs_over_wall_time": proof_bytes / (ms_per_step * 1e-3) / 1e9,
+                                "frac_of_hbm_peak_over_wall_time": proof_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                                "gbs_over_device_busy_time": proof_bytes / (dev_ms_all * 1e-3) / 1e9 if dev_ms_all else None,
+                                "note": "wall time of a proof is bounded by its 640 serial host hashes, see `host`"},
                 "note": "tables of this workload (3 x 32 MiB per phase) mostly fit the 126 MB L2; the HBM-bound "
-                        "measurement is the `sumcheck` object (tables larger than L2)",
-                "share_of_device_time": d["ms"] / max(1e-9, sum(x["ms"] for x in prof.values()))}
+                        "measurements are the `sumcheck` objects (tables larger than L2)"}
 
     # ---- standalone product sumcheck (BASELINE.json config 4; tables larger than L2) --------------------------
     # N = 1: whole tables on one GPU.  N > 1: tables sharded on the low log2(N) index bits, per-round NCCL
@@ -321,51 +364,91 @@ def run_ours(args):
                     "first_round_gbs": sp["prod3_round"]["algo_bytes"] / (sp["prod3_round"]["ms"] * 1e-3) / 1e9
                     if sp["prod3_round"]["ms"] else 0.0}
         algo = 32.0 * 3 * (4 * N - 6)
+        from gkr_b200 import verify as gv
+        from gkr_b200.field import fr_to_ints
+
+        def unpack(raw):
+            msgs, mlen, chal, fin = raw
+            return [fr_to_ints(msgs[j, :mlen[j]]) for j in range(v)], fr_to_ints(chal), fr_to_ints(fin)
         try:
             if world == 1:
                 tabs = make_tables(N, 0, 1)
                 sc_ms = timed(lambda: pv.sumcheck_prod_raw(tabs, v), args.steps, args.warmup) / args.steps
                 rk = sc_profile(lambda: pv.sumcheck_prod_raw(tabs, v))
+                # the verifier's checks on the timed computation: chain, transcript, final product, and the final
+                # evaluations T_i(r) recomputed on the device with an eq table and a dot product
+                m_, c_, f_ = unpack(pv.sumcheck_prod_raw(tabs, v))
+                chk = gv.check_sumcheck_prod(m_, c_, f_, evals=[pv.dev_table_eval(t, c_) for t in tabs])
+                parity["sumcheck_2p%d" % v] = chk
                 extra = {}
             else:
                 gd.init_comm(pv)
                 tabs = make_tables(N // world, rank, world)
                 sc_ms = timed(lambda: pv.sumcheck_prod_sharded_raw(tabs, v), args.steps, args.warmup) / args.steps
                 rk = sc_profile(lambda: pv.sumcheck_prod_sharded_raw(tabs, v))
+                sharded_raw = pv.sumcheck_prod_sharded_raw(tabs, v)
                 for t in tabs:
                     t.close()
                 tabs = []
                 single_ms = None
                 if rank == 0:
-                    full = make_tables(N, 0, 1)
+                    # the unsharded run on rank 0, on a context of its own: timing reference AND bit-exact parity reference
+                    p1 = gkr_b200.Prover(local)
+                    ext1 = torch.cuda.ExternalStream(p1.stream, device=torch.device("cuda", local))
+                    full = [p1.dev_table_synth(sc_seed, syn.TABLE_STREAM + t, N) for t in range(3)]
                     for _ in range(2):
-                        pv.sumcheck_prod_raw(full, v)
+                        p1.sumcheck_prod_raw(full, v)
                     t0 = torch.cuda.Event(enable_timing=True)
                     t1 = torch.cuda.Event(enable_timing=True)
-                    t0.record(ext)
+                    t0.record(ext1)
                     for _ in range(args.steps):
-                        pv.sumcheck_prod_raw(full, v)
-                    t1.record(ext)
+                        single_raw = p1.sumcheck_prod_raw(full, v)
+                    t1.record(ext1)
                     t1.synchronize()
                     single_ms = t0.elapsed_time(t1) / args.steps
+                    same = all(np.array_equal(a, b) for a, b in zip(single_raw, sharded_raw))
+                    m_, c_, f_ = unpack(sharded_raw)
+                    chk = gv.check_sumcheck_prod(m_, c_, f_, evals=[p1.dev_table_eval(t, c_) for t in full])
+                    chk["sharded_equals_single_gpu"] = bool(same)
+                    chk["ok"] = bool(chk["ok"] and same)
+                    parity["sumcheck_2p%d_sharded_x%d" % (v, world)] = chk
                     for t in full:
                         t.close()
+                    p1.close()
                 barrier()
                 # one proof of the headline circuit with every layer table-sharded over all ranks (strong scaling;
-                # latency-bound: 640 serial rounds each pay an NCCL all-gather)
+                # latency-bound: 640 serial rounds, the large ones sharded, the exchange hidden behind the host hash)
                 try:
                     sh_layers = syn.layered_circuit(1, k, layers)
+                    sh_inputs = syn.input_values(1, k)
                     sh_circ = pv.circuit(sh_layers)                     # created after init_comm => per-rank CSRs
-                    sh_wit = pv.witness_eval(sh_circ, syn.input_values(1, k))
+                    sh_wit = pv.witness_eval(sh_circ, sh_inputs)
 
                     def step_sharded():
                         ptr = pv.prove_raw(sh_circ, sh_wit)
                         pv.free_raw(ptr)
-                    gkr_sharded_ms = timed(step_sharded, max(2, args.steps // 2), 1) / max(2, args.steps // 2)
+                    gkr_sharded_ms = timed(step_sharded, max(2, args.steps // 2), 2) / max(2, args.steps // 2)
+                    sh_proof = pv.prove(sh_circ, sh_wit)
                     sh_wit.close()
+                    if rank == 0:
+                        # bit-exact against the same proof from one GPU (rank 0's seed is 1 too), which gkr_verify accepts
+                        p1 = gkr_b200.Prover(local)
+                        c1 = p1.circuit(sh_layers)
+                        w1 = p1.witness_eval(c1, sh_inputs)
+                        one = p1.prove(c1, w1)
+                        fields = ("sumcheck_proofs", "sumcheck_r", "q", "z", "r", "d_coef", "input_coef")
+                        parity["gkr_table_sharded_x%d" % world] = {
+                            "equals_single_gpu_proof": all(getattr(one, f) == getattr(sh_proof, f) for f in fields),
+                            "verified": bool(p1.verify(c1, sh_proof, sh_inputs)[0])}
+                        parity["gkr_table_sharded_x%d" % world]["ok"] = all(parity["gkr_table_sharded_x%d" % world].values())
+                        w1.close()
+                        c1.close()
+                        p1.close()
+                    barrier()
                 except GkrError as e:
                     gkr_sharded_ms = f"error: {e}"
-                extra = {"sharding": f"low log2({world}) index bits, per-round ncclAllGather of 96-128 B partial sums",
+                extra = {"sharding": f"low log2({world}) index bits; per-round partial sums through a shared pinned host block, "
+                                     "summed by every rank's host (no NCCL call, no extra launch per round)",
                          "gkr_table_sharded_ms_per_proof": gkr_sharded_ms,
                          "single_gpu_ms_same_run": single_ms,
                          "speedup_vs_single_gpu": (single_ms / sc_ms) if single_ms else None}
@@ -376,6 +459,22 @@ def run_ours(args):
                         **extra}
             for t in tabs:
                 t.close()
+            # the second size BASELINE.json names (2^24), single GPU only: same measurement, same checks
+            if world == 1 and args.sumcheck_vars_small and args.sumcheck_vars_small != v:
+                v2 = args.sumcheck_vars_small
+                N2 = 1 << v2
+                tabs2 = make_tables(N2, 0, 1)
+                ms2 = timed(lambda: pv.sumcheck_prod_raw(tabs2, v2), args.steps, args.warmup) / args.steps
+                msgs, mlen, chal, fin = pv.sumcheck_prod_raw(tabs2, v2)
+                m_ = [fr_to_ints(msgs[j, :mlen[j]]) for j in range(v2)]
+                c_, f_ = fr_to_ints(chal), fr_to_ints(fin)
+                parity["sumcheck_2p%d" % v2] = gv.check_sumcheck_prod(m_, c_, f_, evals=[pv.dev_table_eval(t, c_) for t in tabs2])
+                algo2 = 32.0 * 3 * (4 * N2 - 6)
+                sumcheck["second_size"] = {"n_vars": v2, "ms": ms2, "melem_s": N2 / (ms2 * 1e-3) / 1e6,
+                                           "gbs_whole_sumcheck": algo2 / (ms2 * 1e-3) / 1e9,
+                                           "frac_whole_sumcheck": algo2 / (ms2 * 1e-3) / 1e9 / hbm_peak}
+                for t in tabs2:
+                    t.close()
         except GkrError as e:
             sumcheck = {"n_vars": v, "error": str(e)}
 
@@ -387,11 +486,14 @@ def run_ours(args):
             big_layers = syn.layered_circuit(seed, lk, 1)
             big_c = pv.circuit(big_layers)
             big_w = pv.witness_eval(big_c, syn.input_values(seed, lk))
+            big_inputs = syn.input_values(seed, lk)
             for _ in range(2):
                 pv.free_raw(pv.prove_raw(big_c, big_w))
             pv.profile(1)
             pv.free_raw(pv.prove_raw(big_c, big_w))
             bp = pv.profile(0)
+            # the streaming (lazy-accumulation) kernels of this size are exercised nowhere else: verify what they produced
+            parity["gkr_layer_2p%d_verified" % lk] = bool(pv.verify(big_c, pv.prove(big_c, big_w), big_inputs)[0])
             big_w.close()
             big_c.close()
 
@@ -433,6 +535,20 @@ def run_ours(args):
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             one = timed_prove_stage(jobs[:12], min(12, workers), local)
             dt = float(dt.item())
+            # a sample of the batch through the complete verifier (every rank checks some of its own proofs)
+            ok_n = 0
+            sample = jobs[:: max(1, len(jobs) // 24)][:24]
+            for lay, inp in sample:
+                cj = pv.circuit(lay)
+                wj = pv.witness_eval(cj, inp)
+                ok_n += 1 if pv.verify(cj, pv.prove(cj, wj), inp)[0] else 0
+                wj.close()
+                cj.close()
+            okt = torch.tensor([ok_n, len(sample)], dtype=torch.int64, device="cuda")
+            if world > 1:
+                dist.all_reduce(okt, op=dist.ReduceOp.SUM)
+            parity["batch_sample_verified"] = {"verified": int(okt[0].item()), "of": int(okt[1].item()),
+                                               "ok": int(okt[0].item()) == int(okt[1].item())}
             tcircom = {"inputs": args.tcircom_inputs, "constraints_per_input": 364, "sub_circuits_per_input": 12,
                        "proofs": 12 * args.tcircom_inputs, "host_threads_per_gpu": workers, "ms_total": 1e3 * dt,
                        "ms_per_input": 1e3 * dt / args.tcircom_inputs, "proofs_per_s": 12 * args.tcircom_inputs / dt,
@@ -454,9 +570,12 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            ms, cores, sample = cpu_sample_ms(k, layers, 1 if k >= 20 else 2)
-            cpu = {"value": ms, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                   "note": "dense CPU oracle (oracle/gkr_dense.c); the Rust reference cannot be built here",
+            ms1, cores, sample1 = cpu_sample_ms(k, layers, 1 if k >= 20 else 2)
+            # one complete proof on all host threads (~10-20 s at the headline size): the number itself, not an extrapolation
+            ms, cores, sample = cpu_sample_ms(k, layers, layers)
+            cpu = {"value": ms, "unit": UNIT, "cores": cores, "kind": "port", "sample": "the whole proof, once (" + sample + ")",
+                   "extrapolated_from_one_layer_ms": ms1,
+                   "note": "dense CPU oracle (oracle/gkr_dense.c, OpenMP on every host thread); the Rust reference cannot be built here",
                    "literal_reference_algorithm_seconds_per_layer": literal_reference_seconds()}
         except Exception as e:  # the oracle is a checker, never a dependency of the measured path
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
@@ -474,6 +593,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": st2["d2h_bytes"] // n_e2e,
                     "note": "pinned input layer -> H2D -> device circuit evaluation -> gkr_prove -> Proof on host"},
             "gpu_launches": int(launches_timed),
+            "latency_ms_per_proof": ms_per_step, "proofs_per_s": 1e3 * world / ms_per_step,
+            "parity": dict(parity, all_ok=all((v.get("ok", True) if isinstance(v, dict) else bool(v)) for v in parity.values())),
+            "seeds": seeds,
             "roofline": roofline, "cpu_baseline": cpu, "sumcheck": sumcheck, "clocks": clock_info,
             "integer_roofline": int_roof, "gkr_rounds_large_tables": gkr_large,
             "kernel_classes": {n: {"launches": x["launches"], "ms": round(x["ms"], 4),
@@ -498,6 +620,8 @@ def main():
     ap.add_argument("--k", type=int, default=20, help="log2 gates per layer (BASELINE config 3: 20)")
     ap.add_argument("--layers", type=int, default=16)
     ap.add_argument("--sumcheck-vars", type=int, default=28, help="standalone 3-table sumcheck size (0 = skip)")
+    ap.add_argument("--sumcheck-vars-small", type=int, default=24, help="second standalone sumcheck size, N = 1 only (0 = skip)")
+    ap.add_argument("--seeds", type=int, default=3, help="time and verify the headline circuit for seeds 1..SEEDS (N = 1)")
     ap.add_argument("--large-layer-k", type=int, default=24, help="also profile the GKR round kernels on one 2^k-gate layer (0 = skip)")
     ap.add_argument("--tcircom-inputs", type=int, default=64, help="batch of t.circom-like input proofs (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true")

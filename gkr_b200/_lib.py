@@ -69,7 +69,7 @@ EXPORTS = [
     "gkr_circuit_create", "gkr_circuit_destroy", "gkr_witness_create", "gkr_witness_eval", "gkr_witness_layer",
     "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_verify", "gkr_sumcheck_prod", "gkr_dev_table_synth", "gkr_dev_table_synth_strided", "gkr_comm_unique_id", "gkr_comm_init", "gkr_comm_destroy", "gkr_comm_create",
     "gkr_sumcheck_prod_sharded",
-    "gkr_dev_table_upload", "gkr_dev_table_download", "gkr_dev_table_free", "gkr_fr_binop", "gkr_eq_table",
+    "gkr_dev_table_upload", "gkr_dev_table_download", "gkr_dev_table_free", "gkr_dev_table_eval", "gkr_fr_binop", "gkr_eq_table",
     "gkr_mobius", "gkr_line_restrict", "gkr_ctx_stats", "gkr_ctx_profile", "gkr_bench_field_mul", "gkr_fold_f64_constants", "gkr_selftest",
 ]
 
@@ -144,6 +144,8 @@ def lib():
     L.gkr_dev_table_upload.argtypes = [vp, vp, u64, C.POINTER(vp)]
     L.gkr_dev_table_download.argtypes = [vp, vp, u64, vp]
     L.gkr_dev_table_free.argtypes = [vp, vp]
+    if hasattr(L, "gkr_dev_table_eval"):
+        L.gkr_dev_table_eval.argtypes = [vp, vp, u32, vp, vp]
     L.gkr_dev_table_free.restype = None
     L.gkr_fr_binop.argtypes = [vp, i32, vp, vp, vp, u64]
     L.gkr_eq_table.argtypes = [vp, vp, u32, vp]

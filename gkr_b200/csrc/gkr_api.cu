@@ -1126,7 +1126,7 @@ static int gather_shards(gkr_ctx *ctx, const Fr *const cur[3], bool pending_fold
             ctx->end_launch(KC_OTHER, 96.0 * m);
             GKR_TRY(ctx->check_launch("fold"));
         } else {
-            GKR_CUDA_TRY(cudaMemcpyAsync(send + i * m, cur[i], m * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+            GKR_CUDA_TRY(cudaMemcpyAsync(send + i * m, cur[i], m * sizeof(Fr), cudaMemcpyDefault, ctx->stream));   // send may be mapped host memory
         }
     }
     GKR_TRY(ctx->shard_mini.ensure(sizeof(Fr) * 3 * m * (size_t)P));
@@ -2105,6 +2105,31 @@ extern "C" int gkr_dev_table_download(gkr_ctx *ctx, const void *dev, uint64_t n,
     if (!ctx || !dev || !host_out) return GKR_ERR_INVALID;
     GKR_TRY(ctx->bind());
     return download_table(ctx, static_cast<const Fr *>(dev), n, host_out);
+}
+// MLE evaluation of a device table at a point: sum_idx eq(point, idx) T[idx], point[0] paired with the most significant
+// index bit (the order in which the sumcheck rounds bind the variables).  Independent of the folding kernels: the eq
+// table is built from the point and one dot product is taken -- what a verifier uses for the final check.
+extern "C" int gkr_dev_table_eval(gkr_ctx *ctx, const void *dev, uint32_t n_vars, const gkr_fr *point, gkr_fr *out) {
+    if (!ctx || !dev || !point || !out || n_vars == 0 || n_vars > 32) return GKR_ERR_INVALID;
+    GKR_TRY(ctx->bind());
+    std::vector<HFr> z(n_vars);
+    for (uint32_t j = 0; j < n_vars; ++j)
+        if (!hfr_from_canonical(&z[j], &point[j])) return GKR_ERR_RANGE;
+    const uint64_t n = (uint64_t)1 << n_vars;
+    DevBuf eq;
+    eq.owner = ctx;
+    struct Rel { DevBuf &b; ~Rel() { b.release(); } } rel{eq};
+    GKR_TRY(eq.ensure(sizeof(Fr) * n));
+    GKR_TRY(eq_table_dev(ctx, z.data(), n_vars, eq.as<Fr>()));
+    const uint32_t s = ctx->next_seq();
+    ctx->begin_launch();
+    launch_dot(eq.as<Fr>(), static_cast<const Fr *>(dev), n, ctx->ws, ctx->slot_dev(s), s, ctx->stream);
+    ctx->end_launch(KC_OTHER, 64.0 * n);
+    GKR_TRY(ctx->check_launch("dot"));
+    const HostSlot *slot;
+    GKR_TRY(ctx->wait_slot(s, &slot));
+    hfr_to_canonical(out, to_host(slot->v[0]));
+    return GKR_OK;
 }
 extern "C" void gkr_dev_table_free(gkr_ctx *ctx, void *dev) {
     if (!ctx || !dev) return;

@@ -271,6 +271,15 @@ class Prover:
         _lib.check(self._L.gkr_dev_table_download(self._ctx, table.ptr, table.n, _vp(out)))
         return out
 
+    def dev_table_eval(self, table: DevTable, point) -> int:
+        """MLE of a device table at `point` (list of ints, point[0] <-> most significant index bit): eq table + dot"""
+        n_vars = len(point)
+        assert table.n == 1 << n_vars
+        pt = as_fr_array(ints_to_fr(point)) if not isinstance(point, np.ndarray) else point
+        out = np.zeros((1, 8), np.uint32)
+        _lib.check(self._L.gkr_dev_table_eval(self._ctx, table.ptr, n_vars, _vp(pt), _vp(out)))
+        return fr_to_ints(out)[0]
+
     def sumcheck_prod_raw(self, tables, n_vars: int, challenge=None):
         """tables: list of 3 DevTable (device resident) or host arrays.  Returns numpy outputs."""
         on_dev = all(isinstance(t, DevTable) for t in tables)

@@ -188,6 +188,10 @@ int gkr_dev_table_synth_strided(gkr_ctx *ctx, uint64_t seed, uint64_t stream, ui
                                 void **dev_table_out);
 int gkr_dev_table_upload(gkr_ctx *ctx, const gkr_fr *host_values, uint64_t n, void **dev_table_out);
 int gkr_dev_table_download(gkr_ctx *ctx, const void *dev_table, uint64_t n, gkr_fr *host_out);
+/* MLE evaluation of a device table of 2^n_vars entries at `point` (point[0] pairs with the most significant index bit, the
+ * order the sumcheck rounds bind the variables): eq table from the point, one dot product.  This is the verifier's final
+ * check of gkr_sumcheck_prod: final_vals[i] == eval(table i, challenges). */
+int gkr_dev_table_eval(gkr_ctx *ctx, const void *dev, uint32_t n_vars, const gkr_fr *point, gkr_fr *out);
 void gkr_dev_table_free(gkr_ctx *ctx, void *dev_table);
 
 /* ---- building blocks, exposed so that each kernel can be checked against the oracle --------------- */

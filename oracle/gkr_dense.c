@@ -29,6 +29,13 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 static fr_t *load_table(const uint8_t *bytes, size_t n, int *err) {
     fr_t *t = (fr_t *)malloc(n * sizeof(fr_t) + 32);
@@ -252,13 +259,18 @@ int orc_gkr_prove(uint32_t n_layers, const orc_layer_t *layers, const uint8_t *c
             memcpy(W, Wfull, N * sizeof(fr_t));
             memset(H, 0, N * sizeof(fr_t)); memset(A, 0, N * sizeof(fr_t));
             if (phase == 0) {
-                /* H[b] = sum_{add: l=b} eqz[g] + sum_{mul: l=b} eqz[g] W[r_g];  A[b] = sum_{add: l=b} eqz[g] W[r_g] */
+                /* H[b] = sum_{add: l=b} eqz[g] + sum_{mul: l=b} eqz[g] W[r_g];  A[b] = sum_{add: l=b} eqz[g] W[r_g]
+                 * (products on all threads, the scatter of the sums in gate order on one: modular sums are exact, so the
+                 * order does not matter for the result -- only the multiplications are worth spreading) */
+                fr_t *ew = (fr_t *)malloc((size_t)L->n_gates * sizeof(fr_t));
+#pragma omp parallel for if (L->n_gates >= 4096)
+                for (uint32_t g = 0; g < L->n_gates; ++g) ew[g] = fr_mul(eqz[g], Wfull[L->right[g]]);
                 for (uint32_t g = 0; g < L->n_gates; ++g) {
-                    uint32_t l = L->left[g], r = L->right[g];
-                    fr_t ew = fr_mul(eqz[g], Wfull[r]);
-                    if (L->type[g] == 0) { H[l] = fr_add(H[l], eqz[g]); A[l] = fr_add(A[l], ew); }
-                    else H[l] = fr_add(H[l], ew);
+                    uint32_t l = L->left[g];
+                    if (L->type[g] == 0) { H[l] = fr_add(H[l], eqz[g]); A[l] = fr_add(A[l], ew[g]); }
+                    else H[l] = fr_add(H[l], ew[g]);
                 }
+                free(ew);
             } else {
                 /* u = b* ; W(u) = fully folded phase-1 W;  equ = eq(u, .) */
                 fr_t *equ = (fr_t *)malloc(N * sizeof(fr_t));
@@ -271,12 +283,19 @@ int orc_gkr_prove(uint32_t n_layers, const orc_layer_t *layers, const uint8_t *c
                     for (uint32_t j = 0; j < k; ++j) { fold_table(t, n, rs[j]); n /= 2; }
                     wu = t[0]; free(t);
                 }
+                fr_t *e = (fr_t *)malloc((size_t)L->n_gates * sizeof(fr_t));
+                fr_t *we = (fr_t *)malloc((size_t)L->n_gates * sizeof(fr_t));
+#pragma omp parallel for if (L->n_gates >= 4096)
                 for (uint32_t g = 0; g < L->n_gates; ++g) {
-                    uint32_t l = L->left[g], r = L->right[g];
-                    fr_t e = fr_mul(eqz[g], equ[l]);
-                    if (L->type[g] == 0) { H[r] = fr_add(H[r], e); A[r] = fr_add(A[r], fr_mul(wu, e)); }
-                    else H[r] = fr_add(H[r], fr_mul(wu, e));
+                    e[g] = fr_mul(eqz[g], equ[L->left[g]]);
+                    we[g] = fr_mul(wu, e[g]);
                 }
+                for (uint32_t g = 0; g < L->n_gates; ++g) {
+                    uint32_t r = L->right[g];
+                    if (L->type[g] == 0) { H[r] = fr_add(H[r], e[g]); A[r] = fr_add(A[r], we[g]); }
+                    else H[r] = fr_add(H[r], we[g]);
+                }
+                free(e); free(we);
                 free(equ);
             }
             size_t n = N;

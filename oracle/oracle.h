@@ -62,6 +62,7 @@ int orc_gkr_prove(uint32_t n_layers, const orc_layer_t *layers, const uint8_t *c
 int orc_sumcheck_prod(uint32_t n_tables, uint32_t n_vars, const uint8_t *const *tables,
                       uint8_t *msgs, uint8_t *msg_len, uint8_t *chal, uint8_t *final_vals);
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -248,3 +248,8 @@ def sumcheck_prod(tables, n_vars: int):
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the C oracle (torchrun exports OMP_NUM_THREADS=1 to its workers)"""
+    lib().orc_set_num_threads(int(n))

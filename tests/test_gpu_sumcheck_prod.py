@@ -88,6 +88,21 @@ def test_paranoid_mode_and_lazy_path(pv):
     pp.close()
 
 
+def test_dev_table_eval_is_the_final_check(pv):
+    """gkr_dev_table_eval (eq table + dot product, independent of the folding kernels) reproduces final_vals: the
+    verifier's last step, usable at sizes where no CPU oracle fits"""
+    rng = random.Random(8)
+    v = 9
+    vals = [rng.randrange(P) for _ in range(1 << v)]
+    point = [rng.randrange(P) for _ in range(v)]
+    tab = pv.dev_table_upload(ints_to_fr(vals))
+    assert pv.dev_table_eval(tab, point) == verifier.mle_eval(vals, point)
+    v, seed = 22, 6
+    tabs = [pv.dev_table_synth(seed, syn.TABLE_STREAM + t, 1 << v) for t in range(3)]
+    msgs, chal, fin = pv.sumcheck_prod(tabs, v)
+    assert [pv.dev_table_eval(t, chal) for t in tabs] == fin
+
+
 def test_device_selftest(pv):
     """lazy 512-bit accumulation == Montgomery sums after every one of 600 products per thread (random and maximal
     operands), FP64-pipe fold == integer fold: the identities behind the streaming kernels, checked on the device"""
