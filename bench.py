@@ -549,10 +549,45 @@ def run_ours(args):
                 dist.all_reduce(okt, op=dist.ReduceOp.SUM)
             parity["batch_sample_verified"] = {"verified": int(okt[0].item()), "of": int(okt[1].item()),
                                                "ok": int(okt[0].item()) == int(okt[1].item())}
+            # ---- one recursive round (config 5: "plus one recursive C'_i verifier-circuit round"), rank 0: the 12 proofs
+            # of input 0 are packaged, the combined circuit C'_1 = t.circom + one VerifyGKR instance per proof is built
+            # as a constraint system (hand-written stand-in for what circom would emit, see
+            # frontend.aggregated_constraint_system), compiled by the native front end and proved and verified
+            recursive = None
+            if rank == 0:
+                from gkr_b200.prover import dense_to_proof
+                prev = []
+                for lay, inp in jobs[:12]:
+                    cj = pv.circuit(lay)
+                    wj = pv.witness_eval(cj, inp)
+                    prev.append(dense_to_proof(pv.prove(cj, wj)))
+                    wj.close()
+                    cj.close()
+                t_fe = time.perf_counter()
+                r2, w2 = fe.aggregated_constraint_system(2 + 1, prev)
+                subs2 = fe.compile_native(fe.write_r1cs(r2), fe.write_wtns(w2))
+                t_fe = time.perf_counter() - t_fe
+                jobs2 = [(sc.layers, sc.input_values) for sc in subs2]
+                timed_prove_stage(jobs2, min(len(jobs2), workers), local)                     # warm-up
+                dt2 = min(timed_prove_stage(jobs2, min(len(jobs2), workers), local) for _ in range(3))
+                ok2 = 0
+                for lay, inp in jobs2:
+                    cj = pv.circuit(lay)
+                    wj = pv.witness_eval(cj, inp)
+                    ok2 += 1 if pv.verify(cj, pv.prove(cj, wj), inp)[0] else 0
+                    wj.close()
+                    cj.close()
+                parity["recursive_round_verified"] = {"verified": ok2, "of": len(jobs2), "ok": ok2 == len(jobs2)}
+                recursive = {"constraints": len(r2.constraints), "of_which_user_circuit": 364, "sub_circuits": len(jobs2),
+                             "max_k": max(max(sc.k) for sc in subs2), "gkr_stage_ms": 1e3 * dt2,
+                             "front_end_ms": 1e3 * t_fe,
+                             "note": "synthetic stand-in for C'_1: the Horner steps VerifyGKR(meta) adds for the 12 proofs of "
+                                     "input 0 (verifier.circom:39-71 with circom's linear constraints simplified away) on top "
+                                     "of the t.circom constraints; circom itself is not available here"}
             tcircom = {"inputs": args.tcircom_inputs, "constraints_per_input": 364, "sub_circuits_per_input": 12,
                        "proofs": 12 * args.tcircom_inputs, "host_threads_per_gpu": workers, "ms_total": 1e3 * dt,
                        "ms_per_input": 1e3 * dt / args.tcircom_inputs, "proofs_per_s": 12 * args.tcircom_inputs / dt,
-                       "ms_one_input_alone": 1e3 * one, "host_cores": os.cpu_count(),
+                       "ms_one_input_alone": 1e3 * one, "host_cores": os.cpu_count(), "recursive_round": recursive,
                        "note": "hand-built constraint system of the shape circom emits for rust/t.circom (no circom "
                                "here): an approximation; wall clock of the GKR stage alone (circuits uploaded and "
                                "witnesses evaluated beforehand, as the reference times it, aggregator.rs:406-418), "

@@ -352,6 +352,66 @@ def mimc7_constraint_system(x_in: int, negated: bool = True):
     return R1cs(header, cons, list(range(n))), wires
 
 
+def aggregated_constraint_system(x_in: int, proofs, negated: bool = True):
+    """Stand-in for the combined circuit C'_i of a recursion round (aggregator.rs:316-363): the user circuit
+    (rust/t.circom, mimc7_constraint_system) plus what one `VerifyGKR(meta)` instance per previous proof adds
+    (gkr-verifier-circuits/circom/circom/verifier.circom:39-71, sumcheck/sumcheckVerify.circom:17-40,
+    poly/univariate.circom:10-14).  circom is not available here, so the system is written by hand under the assumption
+    that its simplifier removes the linear constraints: what remains are the Horner steps
+    `evaluated[i] <== evaluated[i-1] * x + coeffs[i]` of the evaluations at a signal --
+      * per layer and round j < 2 k_i - 1: g_j(r_j)       (meta[4] - 1 products, `next[i]`),
+      * per layer: m_i = q_i(r*_i)                        (meta[5] - 1 products);
+    evaluations at the constants 0 and 1 (`qZero`, `qOne`), the equality checks and the wiring of the padded arrays are
+    linear, and `evalMultivariate` assigns with `<--` (no constraints).  Witness values are computed from the real
+    (padded) proofs, so every constraint is satisfied.  An approximation of the real artefact, flagged as such wherever it
+    is reported.  proofs: gkr_b200.prover.Proof objects of the previous round.  Returns (R1cs, witness values)."""
+    from .packaging import get_meta, modify_proof_for_circom
+    base, wires = mimc7_constraint_system(x_in, negated)
+    cons = list(base.constraints)
+    one_w = 0
+    metas = get_meta(proofs)
+    padded = modify_proof_for_circom(proofs, metas)
+
+    def new_wire(val):
+        wires.append(val % P)
+        return len(wires) - 1
+
+    def mul(a_lc, b_lc, c_lc):
+        if negated and len(cons) % 2 == 0:
+            cons.append(([((P - k) % P, x) for k, x in a_lc], list(b_lc), [((P - k) % P, x) for k, x in c_lc]))
+        else:
+            cons.append((list(a_lc), list(b_lc), list(c_lc)))
+
+    def horner(coeff_wires, coeff_vals, x_wire, x_val):
+        """evaluated[i] = evaluated[i-1] * x + coeffs[i]: one product constraint per step, A = evaluated[i-1], B = x,
+        C = evaluated[i] - coeffs[i]"""
+        acc_w, acc_v = coeff_wires[0], coeff_vals[0]
+        for cw, cv in zip(coeff_wires[1:], coeff_vals[1:]):
+            nv = (acc_v * x_val + cv) % P
+            nw = new_wire(nv)
+            mul([(1, acc_w)], [(1, x_wire)], [(1, nw), (MINUS_ONE, cw)])
+            acc_w, acc_v = nw, nv
+        return acc_w, acc_v
+
+    for pr, meta in zip(padded, metas):
+        d = meta[0]
+        for i in range(d - 1):
+            k_i = meta[i + 9]                                  # verifier.circom:40 (SumcheckVerify(2 * meta[i + 9], meta[4]))
+            rounds = 2 * k_i
+            for j in range(rounds - 1):                        # `if (i != v - 1)`: no evaluation after the last round
+                cw = [new_wire(c) for c in pr.sumcheck_proofs[i][j]]
+                rw = new_wire(pr.sumcheck_r[i][j])
+                horner(cw, pr.sumcheck_proofs[i][j], rw, pr.sumcheck_r[i][j])
+            qw = [new_wire(c) for c in pr.q[i]]
+            sw = new_wire(pr.r[i])
+            horner(qw, pr.q[i], sw, pr.r[i])
+    n = len(wires)
+    header = R1csHeader(32, P, n, base.header.n_pub_out, base.header.n_pub_in, n - 1 - base.header.n_pub_out - base.header.n_pub_in,
+                        n, len(cons))
+    _ = one_w
+    return R1cs(header, cons, list(range(n))), wires
+
+
 @dataclass
 class IntermediateLayer:            # convert.rs:102-106
     node_types: list                # "A" | "M"

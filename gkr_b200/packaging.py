@@ -2,7 +2,8 @@
 into the padded signal arrays the circom `VerifyGKR(meta)` template consumes.
 
 Mirrors, on the host, rust/src/aggregator.rs:92-141 (`get_meta`), :143-213 (`modify_proof_for_circom`),
-:22-82 (`CircomInputProof`), and rust/src/file_utils.rs:20-28 (`stringify_fr`), :49-67
+:215-314 (`modify_circom_file`, the splice of one `VerifyGKR(meta)` instance per previous proof into the user's
+circom template), :22-82 (`CircomInputProof`), and rust/src/file_utils.rs:20-28 (`stringify_fr`), :49-67
 (`write_aggregated_input`).  The array shapes are the contract of
 gkr-verifier-circuits/circom/circom/verifier.circom:22-29.  Pure host glue: no field arithmetic happens here.
 """
@@ -100,3 +101,96 @@ def write_aggregated_input(path: str, user_input: dict, circom_proofs) -> str:
     with open(path, "w") as f:
         json.dump(aggregated_input(user_input, circom_proofs), f, indent=2)
     return path
+
+
+# ------------------------------------------------------------------------------------------------
+# circom template splice (aggregator.rs:215-314).  The reference renders two Tera templates; the text below is what
+# those templates expand to -- the wire contract is the circom source `circom` then compiles, so it is reproduced
+# character for character (including the reference's habit of dropping everything before the pragma line and of
+# gluing the text after the first closing brace onto it).
+# ------------------------------------------------------------------------------------------------
+VERIFIER_INCLUDE = 'include "../gkr-verifier-circuits/circom/circom/verifier.circom";'
+
+
+def _verifier_block(num: int, meta) -> str:
+    m = [str(x) for x in meta]
+    n = str(num)
+    meta_dbg = "[" + ", ".join(m) + "]"                    # format!("{:?}", Vec<usize>)
+    return f"""
+    var d{n} = {m[0]};
+    var largest_k{n} = {m[1]};
+    signal input sumcheckProof{n}[d{n} - 1][2 * largest_k{n}][{m[4]}];
+    signal input sumcheckr{n}[d{n} - 1][2 * largest_k{n}];
+    signal input q{n}[d{n} - 1][{m[5]}];
+    signal input D{n}[{m[3]}][{m[2]} + 1];
+    signal input z{n}[d{n}][largest_k{n}];
+    signal input r{n}[d{n} - 1];
+    signal input inputFunc{n}[{m[6]}][{m[7]} + 1];
+    verifier[{n}] = VerifyGKR({meta_dbg});
+    var a{n} = {m[0]} - 1;
+    for (var i = 0; i < a{n}; i++) {{
+        for (var j = 0; j < 2 * {m[1]}; j++) {{
+            for (var k = 0; k < {m[4]}; k++) {{
+                verifier[{n}].sumcheckProof[i][j][k] <== sumcheckProof{n}[i][j][k];
+            }}
+        }}
+    }}
+    for (var i = 0; i < a{n}; i++) {{
+        for (var j = 0; j < 2 * {m[1]}; j++) {{
+            verifier[{n}].sumcheckr[i][j] <== sumcheckr{n}[i][j];
+        }}
+    }}
+    for (var i = 0; i < a{n}; i++) {{
+        for (var j = 0; j < {m[5]}; j++) {{
+            verifier[{n}].q[i][j] <== q{n}[i][j];
+        }}
+    }}
+    for (var i = 0; i < {m[3]}; i++) {{
+        for (var j = 0; j < {m[2]} + 1; j++) {{
+            verifier[{n}].D[i][j] <== D{n}[i][j];
+        }}
+    }}
+    for (var i = 0; i < a{n} + 1; i++) {{
+        for (var j = 0; j < {m[1]}; j++) {{
+            verifier[{n}].z[i][j] <== z{n}[i][j];
+        }}
+    }}
+    for (var i = 0; i < a{n}; i++) {{
+        verifier[{n}].r[i] <== r{n}[i];
+    }}
+    for (var i = 0; i < {m[6]}; i++) {{
+        for (var j = 0; j < {m[7]} + 1; j++) {{
+            verifier[{n}].inputFunc[i][j] <== inputFunc{n}[i][j];
+        }}
+    }}
+    """
+
+
+def modify_circom_source(source: str, metas) -> str:
+    """aggregator.rs:215-314 on text: the user's circom source with the verifier include after the pragma line and,
+    before the first line that is exactly `}`, a `verifier[...]` array with one VerifyGKR(meta) instance per proof."""
+    v = f"""
+    component verifier[{len(metas)}];
+    """
+    for i, meta in enumerate(metas):
+        v = f"{v}\n{_verifier_block(i, meta)}"
+    new_circuit = ""
+    is_added = False
+    for line in source.splitlines():
+        if line == "pragma circom 2.0.0;":
+            new_circuit = f"{line}\n{VERIFIER_INCLUDE}\n"          # (re-assigned, not appended: aggregator.rs:299-302)
+        elif line == "}" and not is_added:
+            new_circuit = f"{new_circuit}\n{v}\n}}"
+            is_added = True
+        else:
+            new_circuit = f"{new_circuit}{line}\n"
+    return new_circuit
+
+
+def modify_circom_file(path: str, metas, out_path: str = "aggregated.circom") -> str:
+    """the same on files: reads `path`, writes `aggregated.circom` (in the working directory, as the reference does)"""
+    with open(path) as f:
+        text = modify_circom_source(f.read(), metas)
+    with open(out_path, "w") as f:
+        f.write(text)
+    return out_path

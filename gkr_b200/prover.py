@@ -55,6 +55,11 @@ class DenseProof:
         return coef_table_to_terms(self.input_coef, self.k[-1])
 
 
+def dense_to_proof(dp: "DenseProof"):
+    """DenseProof -> the reference's `Proof` (term lists for d / input_func), as `prove` returns it"""
+    return Proof(dp.sumcheck_proofs, dp.sumcheck_r, dp.d_terms(), dp.q, dp.z, dp.r, dp.depth, dp.input_func_terms(), dp.k)
+
+
 def coef_table_to_terms(coef, k):
     """dense monomial table -> reference term list [[coeff, e_1..e_k]] (zero coefficients omitted,
     ascending monomial mask; the reference order is HashMap iteration order, poly.rs:526-535).

@@ -279,6 +279,38 @@ def test_native_front_end_rejects_hostile_sizes():
         fe.compile_native(rb, bytes(wbad))
 
 
+def test_aggregated_constraint_system_stand_in():
+    """C'_i stand-in of a recursion round (aggregator.rs:316-363, verifier.circom:39-71): t.circom's constraints plus the
+    Horner steps VerifyGKR adds for the 12 proofs of the previous input.  Every constraint holds on the generated
+    witness, the count follows the formula, both front ends compile it identically and every sub-circuit is valid."""
+    from gkr_b200.prover import DenseProof, dense_to_proof
+    from gkr_b200.packaging import get_meta
+    r1, w1 = mimc7_r1cs(5)
+    subs, _ = fe.convert_r1cs_wtns_gkr(r1, w1)
+    proofs = []
+    for sc in subs:
+        ol = [orc.DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in sc.layers]
+        dp = orc.gkr_prove(ol, orc.evaluate_circuit(ol, sc.input_values.view(np.uint8).reshape(-1, 32)))
+        proofs.append(dense_to_proof(DenseProof(dp.sumcheck_proofs, dp.sumcheck_r, dp.q, dp.z, dp.r, dp.depth, dp.k,
+                                                dp.d_coef, dp.input_coef)))
+    r2, w2 = fe.aggregated_constraint_system(7, proofs)
+
+    def ev(lc):
+        return sum(c * w2[x] for c, x in lc) % P
+    assert all(ev(a) * ev(b) % P == ev(c) for a, b, c in r2.constraints)
+    want = 364
+    for m in get_meta(proofs):
+        want += sum((2 * m[i + 9] - 1) * (m[4] - 1) + (m[5] - 1) for i in range(m[0] - 1))
+    assert len(r2.constraints) == want
+    subs2, _ = fe.convert_r1cs_wtns_gkr(r2, w2)
+    assert 12 < len(subs2) <= 20                      # WIDTH_LIMIT (convert.rs:11)
+    _same_subcircuits(fe.compile_native(fe.write_r1cs(r2), fe.write_wtns(w2)), subs2)
+    for sc in subs2:
+        ol = [orc.DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in sc.layers]
+        vals = orc.evaluate_circuit(ol, sc.input_values.view(np.uint8).reshape(-1, 32))
+        assert not np.asarray(vals[0]).any()          # every output of a satisfied system evaluates to zero
+
+
 def _as_sets(terms):
     return sorted(tuple(t) for t in terms)
 

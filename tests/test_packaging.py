@@ -66,3 +66,61 @@ def test_stringify_and_empty():
     assert pk.stringify_fr(0) == lp.stringify_fr(0) == "0"
     e = pk.CircomInputProof.empty()
     assert e.sumcheckProof == [[["0"]]] and e.r == ["0"]
+
+
+T_CIRCOM = """pragma circom 2.0.0;
+include "../gkr-verifier-circuits/circom/node_modules/circomlib/circuits/mimc.circom";
+
+template A(){
+    signal input in1;
+    signal input in2;
+    signal output out;
+
+    component hasher = MiMC7(91);
+    hasher.x_in <== in1;
+    hasher.k <== 0;
+    
+    out <== hasher.out;
+}
+
+component main {public [in1]}= A();
+"""
+
+
+def test_modify_circom_source_matches_hand_expansion(tmp_path):
+    """aggregator.rs:215-314 on the reference's own rust/t.circom text (inlined: /root/reference is not read at test
+    time).  Expected text worked out by hand from the Tera templates and the line loop: include after the pragma,
+    the verifier block before the template's closing brace, `}` glued to the following (empty) line."""
+    from gkr_b200 import packaging as pk
+    meta = [3, 2, 1, 2, 3, 2, 4, 2, 1, 2, 2]
+    got = pk.modify_circom_source(T_CIRCOM, [meta])
+    lines = got.split("\n")
+    assert lines[0] == "pragma circom 2.0.0;"
+    assert lines[1] == 'include "../gkr-verifier-circuits/circom/circom/verifier.circom";'
+    assert lines[2] == 'include "../gkr-verifier-circuits/circom/node_modules/circomlib/circuits/mimc.circom";'
+    body = got[got.index("    out <== hasher.out;\n") + len("    out <== hasher.out;\n"):]
+    want_head = ("\n\n    component verifier[1];\n    \n\n"
+                 "    var d0 = 3;\n    var largest_k0 = 2;\n"
+                 "    signal input sumcheckProof0[d0 - 1][2 * largest_k0][3];\n"
+                 "    signal input sumcheckr0[d0 - 1][2 * largest_k0];\n"
+                 "    signal input q0[d0 - 1][2];\n"
+                 "    signal input D0[2][1 + 1];\n"
+                 "    signal input z0[d0][largest_k0];\n"
+                 "    signal input r0[d0 - 1];\n"
+                 "    signal input inputFunc0[4][2 + 1];\n"
+                 "    verifier[0] = VerifyGKR([3, 2, 1, 2, 3, 2, 4, 2, 1, 2, 2]);\n"
+                 "    var a0 = 3 - 1;\n")
+    assert body.startswith(want_head)
+    assert "            for (var k = 0; k < 3; k++) {\n                verifier[0].sumcheckProof[i][j][k] <== sumcheckProof0[i][j][k];" in body
+    assert "    for (var i = 0; i < a0 + 1; i++) {\n        for (var j = 0; j < 2; j++) {\n            verifier[0].z[i][j] <== z0[i][j];" in body
+    # the closing brace of the template follows the block without a newline of its own, then the rest of the file
+    assert body.endswith("            verifier[0].inputFunc[i][j] <== inputFunc0[i][j];\n        }\n    }\n    \n}\ncomponent main {public [in1]}= A();\n")
+    # two proofs: two instances, numbered; everything before the pragma line is dropped like in the reference
+    two = pk.modify_circom_source("// comment\n" + T_CIRCOM, [meta, [2, 1, 1, 1, 2, 1, 2, 1, 1, 1]])
+    assert two.startswith("pragma circom 2.0.0;\n") and "component verifier[2];" in two
+    assert "verifier[1] = VerifyGKR([2, 1, 1, 1, 2, 1, 2, 1, 1, 1]);" in two and "signal input z1[d1][largest_k1];" in two
+    # file form
+    src = tmp_path / "t.circom"
+    src.write_text(T_CIRCOM)
+    out = pk.modify_circom_file(str(src), [meta], str(tmp_path / "aggregated.circom"))
+    assert open(out).read() == got
