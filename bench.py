@@ -538,10 +538,11 @@ def run_ours(args):
             # a sample of the batch through the complete verifier (every rank checks some of its own proofs)
             ok_n = 0
             sample = jobs[:: max(1, len(jobs) // 24)][:24]
+            pq = gkr_b200.Prover(local)          # a context without a communicator (pv has one at N > 1)
             for lay, inp in sample:
-                cj = pv.circuit(lay)
-                wj = pv.witness_eval(cj, inp)
-                ok_n += 1 if pv.verify(cj, pv.prove(cj, wj), inp)[0] else 0
+                cj = pq.circuit(lay)
+                wj = pq.witness_eval(cj, inp)
+                ok_n += 1 if pq.verify(cj, pq.prove(cj, wj), inp)[0] else 0
                 wj.close()
                 cj.close()
             okt = torch.tensor([ok_n, len(sample)], dtype=torch.int64, device="cuda")
@@ -558,9 +559,9 @@ def run_ours(args):
                 from gkr_b200.prover import dense_to_proof
                 prev = []
                 for lay, inp in jobs[:12]:
-                    cj = pv.circuit(lay)
-                    wj = pv.witness_eval(cj, inp)
-                    prev.append(dense_to_proof(pv.prove(cj, wj)))
+                    cj = pq.circuit(lay)
+                    wj = pq.witness_eval(cj, inp)
+                    prev.append(dense_to_proof(pq.prove(cj, wj)))
                     wj.close()
                     cj.close()
                 t_fe = time.perf_counter()
@@ -572,9 +573,9 @@ def run_ours(args):
                 dt2 = min(timed_prove_stage(jobs2, min(len(jobs2), workers), local) for _ in range(3))
                 ok2 = 0
                 for lay, inp in jobs2:
-                    cj = pv.circuit(lay)
-                    wj = pv.witness_eval(cj, inp)
-                    ok2 += 1 if pv.verify(cj, pv.prove(cj, wj), inp)[0] else 0
+                    cj = pq.circuit(lay)
+                    wj = pq.witness_eval(cj, inp)
+                    ok2 += 1 if pq.verify(cj, pq.prove(cj, wj), inp)[0] else 0
                     wj.close()
                     cj.close()
                 parity["recursive_round_verified"] = {"verified": ok2, "of": len(jobs2), "ok": ok2 == len(jobs2)}
@@ -584,6 +585,7 @@ def run_ours(args):
                              "note": "synthetic stand-in for C'_1: the Horner steps VerifyGKR(meta) adds for the 12 proofs of "
                                      "input 0 (verifier.circom:39-71 with circom's linear constraints simplified away) on top "
                                      "of the t.circom constraints; circom itself is not available here"}
+            pq.close()
             tcircom = {"inputs": args.tcircom_inputs, "constraints_per_input": 364, "sub_circuits_per_input": 12,
                        "proofs": 12 * args.tcircom_inputs, "host_threads_per_gpu": workers, "ms_total": 1e3 * dt,
                        "ms_per_input": 1e3 * dt / args.tcircom_inputs, "proofs_per_s": 12 * args.tcircom_inputs / dt,

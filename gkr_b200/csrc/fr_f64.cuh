@@ -86,9 +86,35 @@ FR_HD uint32_t limb24(const uint32_t (&w)[8]) {
 }
 }  // namespace frf64
 
+// constant sources for fold2_f64: anything with  D2 pair(int i, int jj) const  (digits 2 jj and 2 jj + 1 of row i)
+struct FoldKParam {                 // the table itself (kernel parameter / host memory)
+    const FrFoldF64 &K;
+    FR_HD frf64::D2 pair(int i, int jj) const { return reinterpret_cast<const frf64::D2 *>(K.c[i])[jj]; }
+};
+#if defined(__CUDACC__)
+// a copy in shared memory, read with volatile 128-bit loads: the compiler can neither hoist the 121 constants out of
+// the caller's loop into registers (242 of them: spills) nor share one set of loads between several folds
+struct FoldKSmem {
+    uint32_t base;                  // shared-memory address of an FrFoldF64
+    __device__ __forceinline__ frf64::D2 pair(int i, int jj) const {
+        frf64::D2 v{0.0, 0.0};
+#if defined(__CUDA_ARCH__)
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base + (uint32_t)(96 * i + 16 * jj)));
+#endif
+        return v;
+    }
+};
+#endif
+
+template <class KS>
+FR_HD Fr fold2_f64_src(const Fr &lo, const Fr &hi, const KS &K);
 // lo + r * (hi - lo), canonical inputs (< p) in Montgomery form, canonical output; r enters through K
 template <class KT>
 FR_HD Fr fold2_f64(const Fr &lo, const Fr &hi, const KT &K) {
+    return fold2_f64_src(lo, hi, FoldKParam{K});
+}
+template <class KS>
+FR_HD Fr fold2_f64_src(const Fr &lo, const Fr &hi, const KS &K) {
     using namespace frf64;
     uint32_t dw[8];
     fr_sub8(dw, hi.l, lo.l);                                  // two's complement difference, |d| < 2^254
@@ -110,10 +136,9 @@ FR_HD Fr fold2_f64(const Fr &lo, const Fr &hi, const KT &K) {
     for (int j = 0; j < 12; ++j) S[j] = BIAS;
 #pragma unroll
     for (int i = 0; i < 11; ++i) {
-        const D2 *row = reinterpret_cast<const D2 *>(K.c[i]);
 #pragma unroll
         for (int jj = 0; jj < 6; ++jj) {
-            const D2 c2 = row[jj];
+            const D2 c2 = K.pair(i, jj);
             S[2 * jj] = fmad(d[i], c2.x, S[2 * jj]);
             if (jj < 5) S[2 * jj + 1] = fmad(d[i], c2.y, S[2 * jj + 1]);
         }

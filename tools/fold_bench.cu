@@ -20,7 +20,7 @@ template <int MODE, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_fold(Fr *out, int iters, const __grid_constant__ FrConstMul r,
                                                          const __grid_constant__ FrFoldF64 rf) {
     __shared__ FrFoldF64 srf;
-    if (MODE == 2) {
+    if (MODE == 2 || MODE == 5 || MODE == 6) {
         for (int i = threadIdx.x; i < 11 * 12; i += blockDim.x) (&srf.c[0][0])[i] = (&rf.c[0][0])[i];
         __syncthreads();
     }
@@ -31,7 +31,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_fold(Fr *out, int iters, con
         const FrFoldF64 &rfz = *reinterpret_cast<const FrFoldF64 *>(reinterpret_cast<const char *>(&rf) + (size_t)(it >> 30) * 16);
         if (MODE == 0) { x = fold2(x, y, r); y = fold2(y, x, r); }
         if (MODE == 1) { x = fold2_f64(x, y, rfz); y = fold2_f64(y, x, rfz); }
-        if (MODE == 2) { x = fold2_f64(x, y, srf); y = fold2_f64(y, x, srf); }
+        if (MODE == 2) { const FoldKSmem ks{(uint32_t)__cvta_generic_to_shared(&srf)}; x = fold2_f64_src(x, y, ks); y = fold2_f64_src(y, x, ks); }
+        if (MODE == 5) { const FoldKSmem ks{(uint32_t)__cvta_generic_to_shared(&srf)}; x = fold2(x, y, r); u = fold2_f64_src(u, v, ks); y = fold2(y, x, r); v = fold2_f64_src(v, u, ks); }
+        if (MODE == 6) { const FoldKSmem ks{(uint32_t)__cvta_generic_to_shared(&srf)}; x = fold2(x, y, r); u = fold2_f64_src(u, v, ks); y = fold2(y, x, r); v = fold2(v, u, r); }
         if (MODE == 3) { x = fold2_f64(x, y, rf); y = fold2_f64(y, x, rf); }
         if (MODE == 4) { x = fold2(x, y, r); u = fold2_f64(u, v, rfz); y = fold2(y, x, r); v = fold2_f64(v, u, rfz); }
     }
@@ -73,6 +75,7 @@ int main() {
     run("f64s", k_fold<2, 4>, 4, 2);
     run("f64r", k_fold<3, 1>, 1, 2);
     run("mix(int+f64u)", k_fold<4, 2>, 2, 4);
-    run("mix(int+f64u)", k_fold<4, 3>, 3, 4);
+    run("mix(2 int + 2 f64s)", k_fold<5, 2>, 2, 4);
+    run("mix(3 int + 1 f64s)", k_fold<6, 2>, 2, 4);
     return 0;
 }
