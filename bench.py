@@ -158,7 +158,9 @@ def run_reference(args):
     if rank != 0:
         return
     k, layers = args.k, args.layers
-    sample_layers = 1 if k >= 20 else 2
+    # a quarter of the layers per step (the per-proof fixed work -- two Moebius transforms, the witness -- is then
+    # over-counted x4 instead of x16; bench.py's own cpu_baseline object times the whole proof once)
+    sample_layers = max(1, layers // 4) if k >= 18 else layers
     _all_host_threads()
     for _ in range(args.warmup):
         cpu_sample_ms(k, layers, sample_layers)
@@ -197,6 +199,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; gkr_b200 has no CPU fallback")
+    placement = None
+    if world > 1 and os.environ.get("GKR_BENCH_PIN", "1") != "0":
+        from gkr_b200 import dist as gd0
+        placement = gd0.pin_rank_near_gpu(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -524,7 +530,8 @@ def run_ours(args):
                 r1, w1 = fe.mimc7_constraint_system(2 + j)
                 subs, _ = fe.convert_r1cs_wtns_gkr(r1, w1)
                 jobs += [(sc.layers, sc.input_values) for sc in subs]
-            workers = int(os.environ.get("GKR_BATCH_WORKERS", 0)) or max(1, min(16, (os.cpu_count() or 1) // world))
+            n_cpus = len(os.sched_getaffinity(0)) if placement and placement.get("pinned") else (os.cpu_count() or 1) // world
+            workers = int(os.environ.get("GKR_BATCH_WORKERS", 0)) or max(1, min(16, n_cpus))
             from gkr_b200.batch import timed_prove_stage
             barrier()
             dt_local = timed_prove_stage(jobs, workers, local)
@@ -623,7 +630,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (BN254 Fr, 254-bit integers)", "data": "synthetic",
             "config": {"workload": _workload_name(k, layers), "k": k, "layers": layers,
-                       "parallelism": "1 proof per GPU" if world > 1 else "single GPU",
+                       "parallelism": "1 proof per GPU" if world > 1 else "single GPU", "placement_rank0": placement,
                        "l2": "256 MiB flush between timed iterations; witness tables total %d MiB" % ((layers + 1) * (32 << k) >> 20),
                        "timing": "CUDA events on the prover stream, per step, summed; max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st2["h2d_bytes"] // n_e2e,

@@ -1114,11 +1114,12 @@ static int gather_shards(gkr_ctx *ctx, const Fr *const cur[3], bool pending_fold
                          uint64_t *n_out) {
     const int P = ctx->n_ranks;
     const uint64_t m = pending_fold ? n / 2 : n;
-    if (ctx->xchg && 3 * m > sizeof(ctx->xchg->host->stage[0]) / sizeof(Fr)) {
+    const int par = ctx->xchg ? (int)(ctx->xchg->gathers++ & 1u) : 0;
+    if (ctx->xchg && 3 * m > sizeof(ctx->xchg->host->stage[0][0]) / sizeof(Fr)) {
         set_last_error("gather_shards: %llu entries per table exceed the staging area", (unsigned long long)m);
         return GKR_ERR_INTERNAL;
     }
-    Fr *send = ctx->xchg ? ctx->xchg->dev->stage[ctx->rank] : ctx->comm_send + 8;
+    Fr *send = ctx->xchg ? ctx->xchg->dev->stage[par][ctx->rank] : ctx->comm_send + 8;
     for (int i = 0; i < 3; ++i) {
         if (pending_fold) {
             ctx->begin_launch();
@@ -1142,7 +1143,7 @@ static int gather_shards(gkr_ctx *ctx, const Fr *const cur[3], bool pending_fold
         const HostSlot *unused;
         GKR_TRY(xchg_wait(ctx, xa, 0, 0, &dummy, &unused));
         StagedPtrs sp{};
-        for (int rk = 0; rk < P; ++rk) sp.p[rk] = ctx->xchg->dev->stage[rk];
+        for (int rk = 0; rk < P; ++rk) sp.p[rk] = ctx->xchg->dev->stage[par][rk];
         ctx->begin_launch();
         launch_interleave_staged(sp, mini, P, 3, m, ctx->stream);
         ctx->end_launch(KC_OTHER, 192.0 * m * P);
@@ -1567,6 +1568,55 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
     return GKR_OK;
 }
 
+// q_i machinery: W restricted to the line b -> c, k+1 ascending coefficients in canonical form at out_canonical (device).
+// Levels 0..2 in one register-resident pass, then one launch per level while the table is large, then every remaining
+// level in one single-CTA launch (k = 20: 8 launches instead of 21; k <= 11: one).
+static int line_restrict_dev(gkr_ctx *ctx, const Fr *W, uint32_t k, const HFr *bs, const HFr *cs, Fr *out_canonical, cudaStream_t st,
+                             bool account) {
+    const Fr *cur = W;
+    uint64_t cnt = (uint64_t)1 << k;
+    uint32_t j = 0;                                  // levels done == degree of the entries of cur
+    int flip = 0;
+    auto next_buf = [&] { return (flip++ & 1) ? ctx->lineB.as<Fr>() : ctx->lineA.as<Fr>(); };
+    if (cnt > kLineTailEntries && k >= 3) {
+        FrConstMul b3[3], g3[3];
+        for (int i = 0; i < 3; ++i) {
+            b3[i] = make_const_mul(bs[i]);
+            g3[i] = make_const_mul(hfr_sub(cs[i], bs[i]));
+        }
+        Fr *nxt = next_buf();
+        if (account) ctx->begin_launch(st);
+        launch_line_fold_first3(cur, nxt, cnt, b3, g3, st);
+        if (account) ctx->end_launch(KC_LINE, 32.0 * (double)cnt + 32.0 * (double)(cnt / 2), 1, st);
+        GKR_TRY(ctx->check_launch("line_fold_first3"));
+        cur = nxt;
+        cnt /= 8;
+        j = 3;
+    }
+    while (cnt > kLineTailEntries) {
+        Fr *nxt = next_buf();
+        if (account) ctx->begin_launch(st);
+        launch_line_fold(cur, nxt, cnt, j, make_const_mul(bs[j]), make_const_mul(hfr_sub(cs[j], bs[j])), st);
+        if (account) ctx->end_launch(KC_LINE, 32.0 * (double)(cnt * (j + 1)) + 32.0 * (double)(cnt / 2 * (j + 2)), 1, st);
+        GKR_TRY(ctx->check_launch("line_fold"));
+        cur = nxt;
+        cnt /= 2;
+        ++j;
+    }
+    FrVec bv, gv;
+    std::memset(&bv, 0, sizeof bv);
+    std::memset(&gv, 0, sizeof gv);
+    for (uint32_t lv = 0; j + lv < k; ++lv) {
+        bv.v[lv] = to_dev(bs[j + lv]);
+        gv.v[lv] = to_dev(hfr_sub(cs[j + lv], bs[j + lv]));
+    }
+    Fr *buf_a = next_buf(), *buf_b = next_buf();     // buf_a is never the buffer cur lives in
+    if (account) ctx->begin_launch(st);
+    launch_line_fold_tail(cur, buf_a, buf_b, (uint32_t)cnt, j, k - j, bv, gv, out_canonical, st);
+    if (account) ctx->end_launch(KC_LINE, 64.0 * (double)(cnt * (j + 1)), 1, st);
+    return ctx->check_launch("line_fold_tail");
+}
+
 // ------------------------------------------------------------------------------------------------
 // prove
 // ------------------------------------------------------------------------------------------------
@@ -1855,24 +1905,8 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
             Fr *qd = ctx->qdev.as<Fr>() + P->q_off[li];
             gkr_fr *q_dst = P->q_stage + P->q_off[li];
             // the launches go through the helper thread unless per-launch profiling needs them inline
-            auto line_job = [ctx, W, N, k, qd, q_dst, rs_copy = rs]() -> int {
-                const Fr *cur = W;
-                uint64_t cnt = N;
-                for (uint32_t j = 0; j < k; ++j) {
-                    Fr *nxt = (j & 1) ? ctx->lineB.as<Fr>() : ctx->lineA.as<Fr>();
-                    const HFr g = hfr_sub(rs_copy[k + j], rs_copy[j]);
-                    if (ctx->profiling) ctx->begin_launch(ctx->aux);
-                    launch_line_fold(cur, nxt, cnt, j, make_const_mul(rs_copy[j]), make_const_mul(g), ctx->aux);
-                    if (ctx->profiling)
-                        ctx->end_launch(KC_LINE, 32.0 * (double)(cnt * (j + 1)) + 32.0 * (double)(cnt / 2 * (j + 2)), 1, ctx->aux);
-                    GKR_TRY(ctx->check_launch("line_fold"));
-                    cur = nxt;
-                    cnt /= 2;
-                }
-                if (ctx->profiling) ctx->begin_launch(ctx->aux);
-                launch_from_mont(cur, qd, k + 1, ctx->aux);                 // ascending coefficients
-                if (ctx->profiling) ctx->end_launch(KC_OTHER, 64.0 * (k + 1), 1, ctx->aux);
-                GKR_TRY(ctx->check_launch("from_mont"));
+            auto line_job = [ctx, W, k, qd, q_dst, rs_copy = rs]() -> int {
+                GKR_TRY(line_restrict_dev(ctx, W, k, rs_copy.data(), rs_copy.data() + k, qd, ctx->aux, ctx->profiling));
                 GKR_CUDA_TRY(cudaMemcpyAsync(q_dst, qd, (k + 1) * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->aux));
                 return GKR_OK;
             };
@@ -1880,7 +1914,12 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
                 GKR_TRY(line_job());
             } else {
                 ctx->aux_pending.push_back(std::move(line_job));
-                ctx->stats.kernel_launches += k + 1;
+                {   // launches line_restrict_dev will make (counted here: the job itself runs on the helper thread)
+                    uint64_t cnt = N, n_launch = 1;
+                    if (cnt > kLineTailEntries && k >= 3) { cnt /= 8; ++n_launch; }
+                    while (cnt > kLineTailEntries) { cnt /= 2; ++n_launch; }
+                    ctx->stats.kernel_launches += n_launch;
+                }
                 worker_used = true;
                 // the job is held back until the next phase's large kernels are queued (release_aux_jobs in
                 // run_phase_poly): it then runs in the device's idle time during the small-table rounds.  Releasing it
@@ -2408,18 +2447,13 @@ extern "C" int gkr_line_restrict(gkr_ctx *ctx, const gkr_fr *values, uint32_t k,
     GKR_TRY(ctx->lineA.ensure(sizeof(Fr) * std::max<uint64_t>(n, 64)));
     GKR_TRY(ctx->lineB.ensure(sizeof(Fr) * std::max<uint64_t>(n, 64)));
     GKR_TRY(upload_table(ctx, values, n, ctx->mob.as<Fr>()));
-    const Fr *cur = ctx->mob.as<Fr>();
-    uint64_t cnt = n;
-    for (uint32_t j = 0; j < k; ++j) {
-        HFr bj, cj;
-        if (!hfr_from_canonical(&bj, &b[j]) || !hfr_from_canonical(&cj, &c[j])) return GKR_ERR_RANGE;
-        Fr *nxt = (j & 1) ? ctx->lineB.as<Fr>() : ctx->lineA.as<Fr>();
-        ctx->begin_launch();
-        launch_line_fold(cur, nxt, cnt, j, make_const_mul(bj), make_const_mul(hfr_sub(cj, bj)), ctx->stream);
-        ctx->end_launch(KC_LINE, 32.0 * (double)(cnt * (j + 1)) + 32.0 * (double)(cnt / 2 * (j + 2)));
-        GKR_TRY(ctx->check_launch("line_fold"));
-        cur = nxt;
-        cnt /= 2;
-    }
-    return download_table(ctx, cur, k + 1, coef_ascending);
+    std::vector<HFr> bs(k), cs(k);
+    for (uint32_t j = 0; j < k; ++j)
+        if (!hfr_from_canonical(&bs[j], &b[j]) || !hfr_from_canonical(&cs[j], &c[j])) return GKR_ERR_RANGE;
+    GKR_TRY(ctx->qdev.ensure(sizeof(Fr) * (k + 1)));
+    GKR_TRY(line_restrict_dev(ctx, ctx->mob.as<Fr>(), k, bs.data(), cs.data(), ctx->qdev.as<Fr>(), ctx->stream, true));
+    GKR_CUDA_TRY(cudaMemcpyAsync(coef_ascending, ctx->qdev.ptr, (k + 1) * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.d2h_bytes += (k + 1) * sizeof(Fr);
+    return GKR_OK;
 }

@@ -163,6 +163,15 @@ void launch_table_flags(const Fr *T, uint64_t n, unsigned int *dev_words3, HostS
 // one level: cnt entries with (deg+1) coefficients each (coefficient-major) -> cnt/2 entries with deg+2
 void launch_line_fold(const Fr *cur, Fr *nxt, uint64_t cnt, uint32_t deg, const FrConstMul &b, const FrConstMul &g,
                       cudaStream_t s);
+// levels 0..2 in one pass over plain values: cnt entries -> cnt/8 entries with 4 coefficients (cnt >= 8)
+void launch_line_fold_first3(const Fr *W, Fr *nxt, uint64_t cnt, const FrConstMul b[3], const FrConstMul g[3], cudaStream_t s);
+// n_levels further levels in ONE single-CTA launch (cnt <= kLineTailEntries entries with deg + 1 coefficients each);
+// b, g: the levels' challenges b_j and c_j - b_j in Montgomery form; intermediate levels ping-pong between buf_a and
+// buf_b (each >= cnt/2 * (deg + 2) entries; cur may alias neither); if the last level leaves one entry, its
+// coefficients go to out_canonical (ascending, canonical form) when that is non-null
+constexpr uint32_t kLineTailEntries = 2048;
+void launch_line_fold_tail(const Fr *cur, Fr *buf_a, Fr *buf_b, uint32_t cnt, uint32_t deg, uint32_t n_levels, const FrVec &b,
+                           const FrVec &g, Fr *out_canonical, cudaStream_t s);
 
 // ---- verifier ---------------------------------------------------------------------------------------
 // publishes v[0] = add_i(z,b,c), v[1] = mult_i(z,b,c) from the three eq tables

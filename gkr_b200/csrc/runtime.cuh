@@ -116,7 +116,11 @@ struct LocalGroup {
 // The block of pinned host memory all ranks share (kernels.cuh: XchgEntry): exchange rows, then one staging area per rank
 struct XchgBlock {
     XchgEntry row[kXchgRing][kMaxRanks];
-    Fr stage[kMaxRanks][3 * (kGatherEntries / 2)];      // a rank's folded shard at the gather: 3 tables x <= 2^10 entries
+    // a rank's folded shard at a gather (3 tables x <= 2^10 entries), double-buffered by gather parity: a rank may
+    // already be staging gather n+1 while a slower peer still reads its gather-n area; it cannot reach gather n+2
+    // before that peer has finished reading, because gather n+1 waits for the peer's flag, which the peer raises
+    // behind its gather-n read in stream order
+    Fr stage[2][kMaxRanks][3 * (kGatherEntries / 2)];
 };
 // one rank's view of it
 struct XchgState {
@@ -127,6 +131,7 @@ struct XchgState {
     char shm_name[64] = {};
     uint32_t seq = 0;               // exchange counter; all ranks advance it in lockstep
     uint32_t next() { if (++seq == 0) ++seq; return seq; }
+    uint32_t gathers = 0;           // gathers done (parity selects the staging buffer)
     LocalGroup *group = nullptr;    // in-process groups only
 };
 int default_f64_folds();       // GKR_F64_FOLDS, else the built-in default

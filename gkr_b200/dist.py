@@ -23,6 +23,61 @@ def world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def _parse_cpulist(text: str) -> list:
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out += list(range(int(a), int(b or a) + 1))
+    return out
+
+
+def pin_rank_near_gpu(local_rank: int, ranks_on_host: int) -> dict:
+    """Bind this process to a disjoint share of the CPUs of the NUMA node its GPU hangs off (call before the first CUDA
+    allocation, so that pinned host memory -- result slots, exchange block, proof tables -- is allocated there too).
+    The proving thread spins on device-written host memory and hashes on one core: with several ranks per host the
+    default placement puts them on each other's hyperthreads and across sockets.  Best effort: returns what it did."""
+    info = {"pinned": False}
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+        node = -1
+        try:
+            node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        except OSError:
+            pass
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = allowed
+        if node >= 0:
+            try:
+                on_node = set(_parse_cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read()))
+                if on_node & set(allowed):
+                    cpus = sorted(on_node & set(allowed))
+            except OSError:
+                pass
+        # the ranks whose GPUs share this node split its CPUs evenly, in local-rank order
+        peers = []
+        for r in range(ranks_on_host):
+            pr = torch.cuda.get_device_properties(r)
+            b = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+            try:
+                n = int(open(f"/sys/bus/pci/devices/{b}/numa_node").read().strip())
+            except OSError:
+                n = -1
+            if n == node:
+                peers.append(r)
+        share = max(1, len(cpus) // max(1, len(peers)))
+        idx = peers.index(local_rank) if local_rank in peers else 0
+        mine = cpus[idx * share:(idx + 1) * share] or cpus
+        os.sched_setaffinity(0, mine)
+        info = {"pinned": True, "numa_node": node, "cpus": mine, "pci": bus}
+    except Exception as e:  # noqa: BLE001 - placement is an optimisation, never a requirement
+        info["error"] = str(e)
+    return info
+
+
 def assign_round_robin(n_items: int, rank: int, world_size: int) -> list:
     """indices of the independent proofs this rank owns"""
     return list(range(rank, n_items, world_size))

@@ -126,3 +126,45 @@ def test_in_process_group_sharded_gkr(world):
     finally:
         for pv in pvs:
             pv.close()
+
+
+def test_in_process_group_tiny_layers_repeated():
+    """layers with 2 rows per rank gather their shards at the start of every phase with no exchange in between: a rank
+    must not overwrite its staging area while a slower peer still reads the previous gather (the staging areas are
+    double-buffered for exactly this; a single buffer failed this test most of the time)"""
+    import random
+
+    import numpy as np
+
+    import gkr_b200
+    from gkr_b200.field import P as MOD, ints_to_fr
+    from oracle import oracle as orc
+    rng = random.Random(5)
+    ks = [0, 2, 6, 1, 7]
+    layers = []
+    for i in range(len(ks) - 1):
+        n_g = 1 << ks[i]
+        layers.append(gkr_b200.DenseLayer(ks[i], ks[i + 1], np.array([rng.randrange(2) for _ in range(n_g)], np.uint8),
+                                          np.array([rng.randrange(1 << ks[i + 1]) for _ in range(n_g)], np.uint32),
+                                          np.array([rng.randrange(1 << ks[i + 1]) for _ in range(n_g)], np.uint32)))
+    inputs = ints_to_fr([rng.randrange(MOD) for _ in range(1 << ks[-1])])
+    ol = [orc.DenseLayer(L.k_out, L.k_in, L.gtype, L.left, L.right) for L in layers]
+    want = orc.gkr_prove(ol, orc.evaluate_circuit(ol, inputs.view(np.uint8).reshape(-1, 32)))
+    for _ in range(6):
+        pvs = gkr_b200.Prover.group(_devices_for(2))
+        try:
+            def one(rank, pv):
+                out = []
+                for _ in range(3):
+                    c = pv.circuit(layers)
+                    w = pv.witness_eval(c, inputs)
+                    out.append(pv.prove(c, w))
+                    w.close()
+                    c.close()
+                return out
+            for proofs in _run_ranks(pvs, one):
+                for got in proofs:
+                    assert got.sumcheck_proofs == want.sumcheck_proofs and got.q == want.q and got.z == want.z
+        finally:
+            for pv in pvs:
+                pv.close()
