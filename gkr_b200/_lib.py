@@ -36,6 +36,10 @@ class LayerDesc(C.Structure):
                 ("type", C.c_void_p), ("left", C.c_void_p), ("right", C.c_void_p)]
 
 
+class Job(C.Structure):
+    _fields_ = [("n_layers", C.c_uint32), ("layers", C.POINTER(LayerDesc)), ("input_values", C.c_void_p)]
+
+
 CHALLENGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(FrT), C.c_uint32, C.POINTER(FrT))
 
 
@@ -71,6 +75,8 @@ EXPORTS = [
     "gkr_sumcheck_prod_sharded",
     "gkr_dev_table_upload", "gkr_dev_table_download", "gkr_dev_table_free", "gkr_dev_table_eval", "gkr_fr_binop", "gkr_eq_table",
     "gkr_mobius", "gkr_line_restrict", "gkr_ctx_stats", "gkr_ctx_profile", "gkr_bench_field_mul", "gkr_fold_f64_constants", "gkr_selftest",
+    "gkr_batch_create", "gkr_batch_load", "gkr_batch_prove", "gkr_batch_threads", "gkr_batch_lanes", "gkr_batch_simd_hash", "gkr_batch_destroy",
+    "gkr_prove_many", "gkr_mimc7_multi_hash_many",
 ]
 
 _LIB = None
@@ -156,6 +162,16 @@ def lib():
     L.gkr_bench_field_mul.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_double)]
     if hasattr(L, "gkr_selftest"):
         L.gkr_selftest.argtypes = [vp, u32, vp, vp]
+    if hasattr(L, "gkr_batch_create"):
+        L.gkr_batch_create.argtypes = [i32, i32, i32, C.POINTER(vp)]
+        L.gkr_batch_load.argtypes = [vp, C.POINTER(Job), C.c_size_t]
+        L.gkr_batch_prove.argtypes = [vp, C.POINTER(C.POINTER(ProofC)), C.POINTER(C.c_double)]
+        L.gkr_batch_threads.argtypes = [vp]
+        L.gkr_batch_lanes.argtypes = [vp]
+        L.gkr_batch_destroy.argtypes = [vp]
+        L.gkr_batch_destroy.restype = None
+        L.gkr_prove_many.argtypes = [i32, C.POINTER(Job), C.c_size_t, i32, i32, C.POINTER(C.POINTER(ProofC))]
+        L.gkr_mimc7_multi_hash_many.argtypes = [vp, vp, u32, u32, vp]
     if hasattr(L, "gkr_fold_f64_constants"):       # absent from older builds loaded through GKR_B200_LIB for A/B runs
         L.gkr_fold_f64_constants.argtypes = [vp, vp]
     _LIB = L

@@ -33,6 +33,13 @@ using namespace gkr;
 // ------------------------------------------------------------------------------------------------
 namespace gkr {
 static thread_local char g_err[512] = "";
+thread_local FiberHooks *tl_fiber = nullptr;
+cudaError_t stream_sync(cudaStream_t st) {
+    if (!tl_fiber) return cudaStreamSynchronize(st);
+    cudaError_t e;
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) tl_fiber->yield(tl_fiber->self);
+    return e;
+}
 void set_last_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -371,6 +378,7 @@ int gkr_ctx::wait_slot(uint32_t s, const HostSlot **out) {
     double next_check = t0 + 2.0;
     while (slot->seq != s) {
         _mm_pause();
+        if (tl_fiber && (spins & 0xF) == 0xF) tl_fiber->yield(tl_fiber->self);     // let the other proofs of the batch run
         if ((++spins & 0xFFF) != 0) continue;
         const double now = now_seconds();
         if (now < next_check) continue;
@@ -608,6 +616,8 @@ static int challenge_for(gkr_ctx *ctx, const gkr_transcript *t, const HFr *msg, 
             set_last_error("transcript callback returned a value >= p");
             rc = GKR_ERR_RANGE;
         }
+    } else if (tl_fiber) {
+        tl_fiber->hash(tl_fiber->self, msg, n, r_out);        // hashed together with the other proofs of the batch
     } else {
         *r_out = mimc7_multi_hash(msg, n, hfr_zero());
     }
@@ -922,6 +932,7 @@ struct ProofHolder {
     std::vector<gkr_fr> msgs, chal, q, z, r;
     gkr_fr *d_coef = nullptr, *input_coef = nullptr, *q_stage = nullptr;     // pinned (pool)
     size_t d_n = 0, input_n = 0, q_stage_n = 0;
+    std::vector<gkr_fr> own_d, own_input;                                     // after proof_unpin
     ~ProofHolder() {
         pinned_put(d_coef, d_n * sizeof(gkr_fr));
         pinned_put(input_coef, input_n * sizeof(gkr_fr));
@@ -940,6 +951,26 @@ extern "C" void gkr_proof_free(gkr_proof *p) {
     // the public struct is the first member of its holder
     delete reinterpret_cast<ProofHolder *>(reinterpret_cast<char *>(p) - offsetof(ProofHolder, pub));
 }
+namespace gkr {
+int proof_unpin(gkr_proof *p) {
+    if (!p) return GKR_ERR_INVALID;
+    ProofHolder *h = reinterpret_cast<ProofHolder *>(reinterpret_cast<char *>(p) - offsetof(ProofHolder, pub));
+    try {
+        h->own_d.assign(h->d_coef, h->d_coef + h->d_n);
+        h->own_input.assign(h->input_coef, h->input_coef + h->input_n);
+    } catch (const std::bad_alloc &) {
+        return GKR_ERR_OOM;
+    }
+    pinned_put(h->d_coef, h->d_n * sizeof(gkr_fr));
+    pinned_put(h->input_coef, h->input_n * sizeof(gkr_fr));
+    pinned_put(h->q_stage, h->q_stage_n * sizeof(gkr_fr));
+    h->d_coef = h->input_coef = h->q_stage = nullptr;
+    h->q_stage_n = 0;
+    h->pub.d_coef = h->own_d.data();
+    h->pub.input_coef = h->own_input.data();
+    return GKR_OK;
+}
+}  // namespace gkr
 
 // ------------------------------------------------------------------------------------------------
 // one phase of the per-layer sumcheck: k rounds over (H, W, A), first table size N = 2^k
@@ -1270,7 +1301,7 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
                     ctx->prelaunched_pending--;
                     any = true;
                 }
-            if (any) cudaStreamSynchronize(ctx->stream);
+            if (any) stream_sync(ctx->stream);
         }
     } guard{ctx, plan};
     const bool can_prelaunch = ctx->prelaunch && !ctx->profiling;
@@ -1402,7 +1433,7 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
                     ctx->prelaunched_pending--;
                     any = true;
                 }
-            if (any) cudaStreamSynchronize(ctx->stream);
+            if (any) stream_sync(ctx->stream);
         }
     } guard{ctx, P};
     const bool can_prelaunch = ctx->prelaunch && !ctx->profiling;
@@ -1620,6 +1651,32 @@ static int line_restrict_dev(gkr_ctx *ctx, const Fr *W, uint32_t k, const HFr *b
 // ------------------------------------------------------------------------------------------------
 // prove
 // ------------------------------------------------------------------------------------------------
+namespace gkr {
+int reserve_for_circuit(gkr_ctx *ctx, const gkr_circuit *c) {
+    const uint64_t Nmax = (uint64_t)1 << c->max_k;
+    GKR_TRY(ctx->H.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->A.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->eqz.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->equ.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->lineA.ensure(sizeof(Fr) * std::max<uint64_t>(Nmax, 64)));
+    GKR_TRY(ctx->lineB.ensure(sizeof(Fr) * std::max<uint64_t>(Nmax, 64)));
+    GKR_TRY(ctx->mob.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
+    uint32_t max_gates = 1;
+    uint64_t q_total = 1;
+    for (size_t i = 0; i < c->layers.size(); ++i) {
+        max_gates = std::max(max_gates, c->layers[i].n_gates);
+        q_total += c->k[i + 1] + 1;
+    }
+    GKR_TRY(ctx->wP.ensure(sizeof(Fr) * max_gates));
+    GKR_TRY(ctx->wQ.ensure(sizeof(Fr) * max_gates));
+    GKR_TRY(ctx->aux_mob.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->aux_stage.ensure(sizeof(Fr) * Nmax));
+    GKR_TRY(ctx->qdev.ensure(sizeof(Fr) * q_total));
+    return GKR_OK;
+}
+}  // namespace gkr
+
 extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *w, const gkr_transcript *t,
                          gkr_proof **out) {
     if (!ctx || !c || !w || !out) return GKR_ERR_INVALID;
@@ -1642,7 +1699,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
     // whatever path leaves this function, no aux-stream copy may still target the proof's pinned tables
     struct AuxDrain {
         cudaStream_t st;
-        ~AuxDrain() { cudaStreamSynchronize(st); }
+        ~AuxDrain() { stream_sync(st); }
     } aux_drain{ctx->aux};
     // (declared after aux_drain => destroyed first: on an error path the helper thread stops enqueueing before the
     //  stream is drained)
@@ -1684,26 +1741,10 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
     P->r.assign(n_layers, gkr_fr{});
 
     const uint64_t Nmax = (uint64_t)1 << c->max_k;
-    GKR_TRY(ctx->H.ensure(sizeof(Fr) * Nmax));
-    GKR_TRY(ctx->A.ensure(sizeof(Fr) * Nmax));
-    GKR_TRY(ctx->eqz.ensure(sizeof(Fr) * Nmax));
-    GKR_TRY(ctx->equ.ensure(sizeof(Fr) * Nmax));
-    GKR_TRY(ctx->lineA.ensure(sizeof(Fr) * std::max<uint64_t>(Nmax, 64)));
-    GKR_TRY(ctx->lineB.ensure(sizeof(Fr) * std::max<uint64_t>(Nmax, 64)));
-    GKR_TRY(ctx->mob.ensure(sizeof(Fr) * Nmax));
-    GKR_TRY(ctx->misc.ensure(sizeof(Fr) * 64));
-    {
-        uint32_t max_gates = 1;
-        for (const LayerDev &L : c->layers) max_gates = std::max(max_gates, L.n_gates);
-        GKR_TRY(ctx->wP.ensure(sizeof(Fr) * max_gates));
-        GKR_TRY(ctx->wQ.ensure(sizeof(Fr) * max_gates));
-    }
+    GKR_TRY(reserve_for_circuit(ctx, c));
 
     // d and input_func as dense monomial tables (prover.rs:88,93; get_multi_ext, poly.rs:502-536):
     // Moebius transform + D2H into pinned proof memory on the low-priority stream, overlapped with the rounds
-    GKR_TRY(ctx->aux_mob.ensure(sizeof(Fr) * Nmax));
-    GKR_TRY(ctx->aux_stage.ensure(sizeof(Fr) * Nmax));
-    GKR_TRY(ctx->qdev.ensure(sizeof(Fr) * (P->q_off[n_layers] + 1)));
     P->q_stage_n = P->q_off[n_layers] + 1;
     P->q_stage = static_cast<gkr_fr *>(pinned_get(P->q_stage_n * sizeof(gkr_fr)));
     for (int which = 0; which < 2; ++which) {
@@ -1858,7 +1899,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
                 fprintf(stderr, "[gkr_b200] a pre-launched kernel never saw its challenge (kernels serialised by a tool?): "
                                 "pre-launching disabled for this context\n");
                 ctx->prelaunch = false;
-                GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                GKR_CUDA_TRY(stream_sync(ctx->stream));
                 io.first_round_seq = 0;
             }
         };
@@ -1945,7 +1986,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
             worker_guard.armed = false;
             if (ctx->aux_worker) GKR_TRY(ctx->aux_worker->drain());
         }
-        GKR_CUDA_TRY(cudaStreamSynchronize(ctx->aux));
+        GKR_CUDA_TRY(stream_sync(ctx->aux));
     }
     for (uint32_t li = 0; li < n_layers; ++li) {
         const uint32_t k = c->k[li + 1], len = P->q_len[li];

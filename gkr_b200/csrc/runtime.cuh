@@ -135,6 +135,25 @@ struct XchgState {
     LocalGroup *group = nullptr;    // in-process groups only
 };
 int default_f64_folds();       // GKR_F64_FOLDS, else the built-in default
+
+// Lockstep batches (batch.cpp): several proofs advance as cooperative fibers on one host thread so that their round
+// messages can be hashed together in SIMD lanes (mimc7_lanes.cpp).  While a fiber runs, tl_fiber points at the hooks
+// of its scheduler: the transcript hands every message to `hash` (which suspends the fiber until the scheduler has
+// hashed the pending messages of all its fibers) and every wait for the device calls `yield` between polls instead
+// of spinning, so that no fiber can starve the one whose command the device is waiting for.
+struct FiberHooks {
+    void *self;
+    void (*yield)(void *self);
+    void (*hash)(void *self, const HFr *msg, uint32_t n, HFr *out);
+};
+extern thread_local FiberHooks *tl_fiber;
+// cudaStreamSynchronize, or a query/yield loop on a fiber
+cudaError_t stream_sync(cudaStream_t st);
+// moves the proof's pinned tables to ordinary memory and returns the pinned blocks to the pool (a batch keeps
+// thousands of proofs alive at once)
+int proof_unpin(gkr_proof *p);
+// sizes every workspace gkr_prove needs for this circuit (so that no proof of a timed batch allocates)
+int reserve_for_circuit(gkr_ctx *ctx, const gkr_circuit *c);
 void *pinned_get(size_t bytes);
 void pinned_put(void *ptr, size_t bytes);
 

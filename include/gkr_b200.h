@@ -141,6 +141,36 @@ typedef struct {
 int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *w, const gkr_transcript *t, gkr_proof **out);
 void gkr_proof_free(gkr_proof *p);
 
+/* ---- batches of independent proofs (the reference proves the sub-circuits of one input under rayon par_iter,
+ * rust/src/aggregator.rs:352-355 and :413-416; one OS thread and one serial transcript per proof) -------------------
+ * A gkr_batch owns n_threads worker threads (0 = one per allowed CPU, at most 16), each pinned to a CPU of its own and
+ * advancing `lanes` proofs (0 = default: 4..16 depending on n_threads; at most 32) in lockstep, so that one round message of
+ * every proof is hashed per SIMD call (MiMC7 multi_hash, 8 or 16 lanes) and the device work of one proof overlaps
+ * the host work of the others.  Every proof is bit-identical to gkr_prove's.
+ * gkr_batch_load uploads the circuits and evaluates the witnesses on the device (the job descriptions are not
+ * referenced after it returns; a new load replaces the previous one); gkr_batch_prove proves every loaded job and
+ * may be called repeatedly.  proofs_out[n_jobs] receives the proofs in job order (free each with gkr_proof_free), or
+ * is NULL to discard them; seconds_out (optional) = wall clock of the proving alone, from the moment all workers
+ * stand ready to the last proof (what aggregator.rs:406-418 times).  The calling thread blocks meanwhile. */
+typedef struct gkr_batch gkr_batch;
+typedef struct {
+    uint32_t n_layers;
+    const gkr_layer_desc *layers;
+    const gkr_fr *input_values;       /* 2^(k_in of the last layer) values of the input layer */
+} gkr_job;
+int gkr_batch_create(int device, int n_threads, int lanes, gkr_batch **out);
+int gkr_batch_load(gkr_batch *b, const gkr_job *jobs, size_t n_jobs);
+int gkr_batch_prove(gkr_batch *b, gkr_proof **proofs_out, double *seconds_out);
+int gkr_batch_threads(const gkr_batch *b);
+int gkr_batch_lanes(const gkr_batch *b);
+int gkr_batch_simd_hash(void);        /* 1 when this CPU runs the AVX-512 IFMA lane hash */
+void gkr_batch_destroy(gkr_batch *b);
+/* create + load + prove + destroy */
+int gkr_prove_many(int device, const gkr_job *jobs, size_t n_jobs, int n_threads, int lanes, gkr_proof **proofs_out);
+/* `count` independent multi_hash(msg_i, key 0) evaluations: message i = msgs[i * stride .. + n[i]) (n[i] <= stride).
+ * Uses the lane hash when the CPU has it, else the scalar one; the results are identical (host only). */
+int gkr_mimc7_multi_hash_many(const gkr_fr *msgs, const uint32_t *n, uint32_t stride, uint32_t count, gkr_fr *out);
+
 /* ---- verifier (complete check of the reference protocol; the reference's own verifiers are partial:
  * gkr-verifier-circuits/circom/circom/verifier.circom:39-71 never evaluates add_i/mult_i nor the hashes,
  * python/gkr.py:202-231 never ties the last sumcheck claim to q) -----------------------------------------

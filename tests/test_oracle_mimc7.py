@@ -44,3 +44,18 @@ def test_multi_hash_empty_and_agreement():
     for _ in range(20):
         arr = [rng.randrange(l0.P) for _ in range(rng.randrange(1, 5))]
         assert l0.multi_hash(arr, 0) == orc.multi_hash(arr, 0)
+
+
+def test_lane_hash_matches_oracle():
+    """the library's many-at-once multi_hash (AVX-512 IFMA lanes where the CPU has them, csrc/mimc7_lanes.cpp; the
+    scalar chain otherwise) against the oracle, on ragged batches: empty messages, 0, p-1, 1..40 messages"""
+    import random
+
+    from gkr_b200.batch import multi_hash_many
+    from gkr_b200.field import P
+    rng = random.Random(77)
+    assert multi_hash_many([[1, 2, 3], [12, 45, 78, 41]]) == [MH_123, MH_4]
+    for count in (1, 2, 7, 8, 9, 15, 16, 17, 33, 40):
+        msgs = [[rng.randrange(P) for _ in range(rng.randrange(0, 5))] for _ in range(count)]
+        msgs[0] = [0, P - 1, 0][: 1 + count % 3]
+        assert multi_hash_many(msgs) == [orc.multi_hash(m, 0) for m in msgs]
