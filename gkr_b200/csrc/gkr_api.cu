@@ -455,8 +455,10 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     GKR_CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->cmds_dev, (void *)ctx->cmds_host, 0));
     ctx->ws.max_blocks = device_sm_count() * 4;
     GKR_CUDA_TRY(cudaMalloc((void **)&ctx->ws.partials, sizeof(Fr) * 6 * (size_t)ctx->ws.max_blocks));
-    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->ws.counter, sizeof(unsigned int)));
-    GKR_CUDA_TRY(cudaMemsetAsync(ctx->ws.counter, 0, sizeof(unsigned int), ctx->stream));
+    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->ws.counter, 2 * sizeof(unsigned int)));
+    GKR_CUDA_TRY(cudaMemsetAsync(ctx->ws.counter, 0, 2 * sizeof(unsigned int), ctx->stream));
+    ctx->ws.tile_counter = ctx->ws.counter + 1;
+    ctx->ws.tile_base = 0;
     GKR_CUDA_TRY(cudaMalloc((void **)&ctx->words, sizeof(unsigned int) * 8));
     GKR_CUDA_TRY(cudaMemsetAsync(ctx->words, 0, sizeof(unsigned int) * 8, ctx->stream));
     GKR_CUDA_TRY(cudaEventCreate(&ctx->ev0));

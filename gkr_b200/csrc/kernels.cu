@@ -338,9 +338,156 @@ __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
     }
     grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, xa);
 }
+// ------------------------------------------------------------------------------------------------
+// The same computation, tiled per CTA instead of per warp (tables of >= kWiringTiledMin rows).  A tile is 256 row pairs
+// (b, b + N/2); its two contiguous CSR edge ranges are walked edge-parallel by all 256 threads: the two gathers of an edge
+// go straight into shared memory with cp.async (no registers held while they are in flight, up to 8 per thread
+// outstanding), the products then run back to back from shared memory (full warps, four independent products per
+// thread), and after one barrier every thread adds up the staged segments of its own two rows.  Tiles are handed out
+// by an atomic counter (field sums are exact, so the order cannot change a bit of the result).
+// ------------------------------------------------------------------------------------------------
+constexpr int kWTile = 256;
+constexpr int kWCap = 1024;                    // staged edges per pass (2 x 32 KB of shared memory)
+constexpr uint64_t kWiringTiledMin = 1024;
+__device__ __forceinline__ void cp_async_fr(Fr *dst_smem, const Fr *src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n\tcp.async.cg.shared.global [%2], [%3], 16;"
+                 :: "r"(d), "l"(src), "r"(d + 16), "l"(reinterpret_cast<const char *>(src) + 16) : "memory");
+}
+template <bool PHASE2, bool FULL>
+__global__ void __launch_bounds__(kWTile, 2)
+    k_wiring_round1_tiled(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ csr_gate, const uint32_t *__restrict__ csr_other,
+                          const Fr *__restrict__ X, const Fr *__restrict__ Y, const Fr *__restrict__ wu_ptr, const Fr *__restrict__ Wtab,
+                          Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n, Fr *partials, unsigned int *counter, HostSlot *slot,
+                          uint32_t seq, XchgArg xa, unsigned int *tile_counter, uint32_t tile_base) {
+    constexpr int K = FULL ? 3 : 2;
+    extern __shared__ __align__(16) unsigned char wiring_smem[];
+    Fr *GX = reinterpret_cast<Fr *>(wiring_smem), *GY = GX + kWCap;
+    __shared__ uint32_t s_tile;
+    const int tid = threadIdx.x;
+    const uint64_t half = n / 2;
+    const uint32_t n_tiles = (uint32_t)((half + kWTile - 1) / kWTile);
+    Fr wu = fr_zero();
+    if (PHASE2) wu = ld_fr(wu_ptr);
+    Fr acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] = fr_zero();
+    for (;;) {
+        __syncthreads();                       // the previous tile's staging buffers and s_tile are no longer read
+        if (tid == 0) s_tile = atomicAdd(tile_counter, 1u) - tile_base;
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const uint64_t r0 = (uint64_t)tile * kWTile;
+        const uint32_t rows = (uint32_t)(half - r0 < (uint64_t)kWTile ? half - r0 : (uint64_t)kWTile);
+        const bool valid = (uint32_t)tid < rows;
+        const uint64_t rowL = r0 + tid, rowH = rowL + half;
+        const uint32_t EL0 = rowptr[r0], EL1 = rowptr[r0 + rows], EH0 = rowptr[r0 + half], EH1 = rowptr[r0 + half + rows];
+        uint32_t eL0 = 0, eL1 = 0, eH0 = 0, eH1 = 0;
+        Fr wl = fr_zero(), wh = fr_zero();
+        if (valid) {
+            eL0 = rowptr[rowL]; eL1 = rowptr[rowL + 1]; eH0 = rowptr[rowH]; eH1 = rowptr[rowH + 1];
+            wl = ld_fr(Wtab + rowL);
+            wh = ld_fr(Wtab + rowH);
+        }
+        const uint32_t nL = EL1 - EL0, total = nL + (EH1 - EH0);
+        // this thread's two segments in the tile's combined edge numbering (L edges first, then H edges)
+        const uint32_t sL0 = eL0 - EL0, sL1 = eL1 - EL0, sH0 = nL + (eH0 - EH0), sH1 = nL + (eH1 - EH0);
+        Fr uL = fr_zero(), vL = fr_zero(), uH = fr_zero(), vH = fr_zero();
+        for (uint32_t cs = 0; cs < total; cs += kWCap) {
+            const uint32_t len = total - cs < (uint32_t)kWCap ? total - cs : (uint32_t)kWCap;
+            uint32_t mulmask = 0;
+#pragma unroll
+            for (int st = 0; st < kWCap / kWTile; ++st) {
+                const uint32_t i = st * kWTile + tid;
+                if (i < len) {
+                    const uint32_t ci = cs + i;
+                    const uint32_t e = ci < nL ? EL0 + ci : EH0 + (ci - nL);
+                    const uint32_t g = csr_gate[e], o = csr_other[e];
+                    mulmask |= (o >> 31) << st;
+                    cp_async_fr(&GX[i], X + g);
+                    cp_async_fr(&GY[i], Y + (o & 0x7fffffffu));
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+            for (int st = 0; st < kWCap / kWTile; ++st) {
+                const uint32_t i = st * kWTile + tid;
+                if (i < len) {
+                    const Fr x = GX[i], y = GY[i];
+                    const Fr p = fr_mul(x, y);
+                    const bool is_mul = (mulmask >> st) & 1u;
+                    if (PHASE2) {                // u: sum over add gates of p, v: sum over mult gates of p
+                        GX[i] = is_mul ? fr_zero() : p;
+                        GY[i] = is_mul ? p : fr_zero();
+                    } else {                     // u: what multiplies W(b) (H), v: the constant part (A)
+                        GX[i] = is_mul ? p : x;
+                        GY[i] = is_mul ? fr_zero() : p;
+                    }
+                }
+            }
+            __syncthreads();
+            {
+                uint32_t lo = sL0 > cs ? sL0 : cs, hi = sL1 < cs + len ? sL1 : cs + len;
+                for (uint32_t q = lo; q < hi; ++q) {
+                    uL = fr_add(uL, GX[q - cs]);
+                    vL = fr_add(vL, GY[q - cs]);
+                }
+                lo = sH0 > cs ? sH0 : cs;
+                hi = sH1 < cs + len ? sH1 : cs + len;
+                for (uint32_t q = lo; q < hi; ++q) {
+                    uH = fr_add(uH, GX[q - cs]);
+                    vH = fr_add(vH, GY[q - cs]);
+                }
+            }
+            if (cs + kWCap < total) __syncthreads();
+        }
+        if (valid) {
+            Fr hL = uL, aL = vL, hH = uH, aH = vH;
+            if (PHASE2) {                        // H2 = S_add + W(u) S_mul, A2 = W(u) S_add
+                aL = fr_zero();
+                aH = fr_zero();
+                if (eL1 > eL0) { hL = fr_add(uL, fr_mul(wu, vL)); aL = fr_mul(wu, uL); }
+                if (eH1 > eH0) { hH = fr_add(uH, fr_mul(wu, vH)); aH = fr_mul(wu, uH); }
+            }
+            st_fr(H + rowL, hL);
+            st_fr(A + rowL, aL);
+            st_fr(H + rowH, hH);
+            st_fr(A + rowH, aH);
+            acc[0] = fr_add(acc[0], fr_add(fr_mul(hL, wl), aL));
+            acc[1] = fr_add(acc[1], fr_mul(fr_sub(hH, hL), fr_sub(wh, wl)));
+            if (FULL) acc[K - 1] = fr_add(acc[K - 1], fr_add(fr_mul(hH, wh), aH));
+        }
+    }
+    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, xa);
+}
+static bool wiring_tiled_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("GKR_WIRING_TILED");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
+
 void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
                           const Fr *X, const Fr *Y, const Fr *wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
                           HostSlot *slot, uint32_t seq, cudaStream_t s, XchgArg xa) {
+    if (n >= kWiringTiledMin && wiring_tiled_enabled()) {
+        const uint32_t n_tiles = (uint32_t)((n / 2 + kWTile - 1) / kWTile);
+        int grid = device_sm_count() * 2;
+        if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
+        if (grid > ws.max_blocks) grid = ws.max_blocks;
+        const size_t smem = sizeof(Fr) * 2 * kWCap;
+        const uint32_t base = ws.tile_base;
+        ws.tile_base += n_tiles + (uint32_t)grid;           // every CTA draws one ticket past the end
+#define GKR_WR1T(P2, F)                                                                                         \
+    k_wiring_round1_tiled<P2, F><<<grid, kWTile, smem, s>>>(rowptr, csr_gate, csr_other, X, Y, wu, Wtab, H, A, n,       \
+                                                            ws.partials, ws.counter, slot, seq, xa, ws.tile_counter, base)
+        if (phase2) { if (full) GKR_WR1T(true, true); else GKR_WR1T(true, false); }
+        else { if (full) GKR_WR1T(false, true); else GKR_WR1T(false, false); }
+#undef GKR_WR1T
+        return;
+    }
     const uint64_t n_blocks = n / 64;
     int grid = (int)((n_blocks + kWarps - 1) / kWarps);
     const int resident = device_sm_count() * GKR_WIRING_MINB;      // one wave: block pairs are uneven, a second wave only adds a tail
@@ -1243,6 +1390,11 @@ int kernels_device_init(int device) {
         cudaError_t e = cudaFuncSetAttribute(k_gkr_poly_tail_cmd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gkr_poly_tail_cmd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mobius_low, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMobTile);
+        const int wiring_smem = (int)(sizeof(Fr) * 2 * kWCap);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wiring_round1_tiled<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wiring_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wiring_round1_tiled<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wiring_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wiring_round1_tiled<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wiring_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wiring_round1_tiled<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wiring_smem);
         g_dev_init_rc[device] = (int)e;
     });
     return g_dev_init_rc[device];

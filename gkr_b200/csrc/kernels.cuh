@@ -36,6 +36,10 @@ struct ReduceWs {
     Fr *partials;         // [max_blocks * 6]
     unsigned int *counter;
     int max_blocks;
+    // work distribution of the tiled wiring kernel: a device counter that only ever grows; the host keeps the value it
+    // will have when the next launch starts (launches of one context are ordered on its stream)
+    unsigned int *tile_counter;
+    mutable uint32_t tile_base;
 };
 
 // ---- multi-GPU exchange of the per-round partial sums -------------------------------------------------
