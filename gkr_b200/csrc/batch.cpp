@@ -370,7 +370,7 @@ extern "C" int gkr_batch_create(int device, int n_threads, int lanes, gkr_batch 
     }
     // proofs in lockstep per thread: wide when few threads share the device (the hash lanes fill up), narrow when many do
     // (beyond ~64 proofs in flight per device the launches of the small kernels are the limit, measured on B200)
-    if (lanes <= 0) lanes = mimc7_lanes_available() ? std::max(4, std::min(16, 96 / n_threads)) : 4;
+    if (lanes <= 0) lanes = mimc7_lanes_available() ? std::max(4, std::min(16, 64 / n_threads)) : 4;
     if (n_threads > 256 || lanes > kMaxLanes) {
         set_last_error("gkr_batch_create: at most 256 threads and %d proofs in lockstep per thread", kMaxLanes);
         return GKR_ERR_INVALID;

@@ -859,6 +859,10 @@ struct gkr_witness {
     gkr_ctx *owner = nullptr;     // tables go back to the owner's pool (the context must outlive its witnesses)
     std::vector<Fr *> vals;       // Montgomery tables, layer 0 .. depth
     std::vector<uint32_t> k;
+    // static shape of every table, found once when the witness is made: is the coefficient of x_1 ... x_k (the
+    // alternating sum of the table) non-zero?  Then W depends on every variable with full degree -- the common case;
+    // gkr_prove runs the full Moebius transform only for the others
+    std::vector<uint8_t> top_nonzero;
 };
 extern "C" void gkr_witness_destroy(gkr_witness *w) {
     if (!w) return;
@@ -883,6 +887,27 @@ static int witness_alloc(gkr_ctx *ctx, const gkr_circuit *c, std::unique_ptr<gkr
     }
     return GKR_OK;
 }
+static int witness_shapes(gkr_ctx *ctx, gkr_witness *w) {
+    const size_t n = w->vals.size();
+    w->top_nonzero.assign(n, 1);
+    for (size_t first = 1; first < n; first += 32) {            // at most 32 result slots in flight (the ring holds 64)
+        const size_t last = std::min(n, first + 32);
+        uint32_t seqs[32];
+        for (size_t i = first; i < last; ++i) {
+            seqs[i - first] = ctx->next_seq();
+            ctx->begin_launch();
+            launch_alt_sum(w->vals[i], (uint64_t)1 << w->k[i], ctx->ws, ctx->slot_dev(seqs[i - first]), seqs[i - first], ctx->stream);
+            ctx->end_launch(KC_MOBIUS, 32.0 * (double)((uint64_t)1 << w->k[i]));
+            GKR_TRY(ctx->check_launch("alt_sum"));
+        }
+        for (size_t i = first; i < last; ++i) {
+            const HostSlot *slot;
+            GKR_TRY(ctx->wait_slot(seqs[i - first], &slot));
+            w->top_nonzero[i] = slot->aux[1] != 0;
+        }
+    }
+    return GKR_OK;
+}
 extern "C" int gkr_witness_create(gkr_ctx *ctx, const gkr_circuit *c, const gkr_fr *const *layer_values,
                                   gkr_witness **out) {
     if (!ctx || !c || !layer_values || !out) return GKR_ERR_INVALID;
@@ -894,6 +919,7 @@ extern "C" int gkr_witness_create(gkr_ctx *ctx, const gkr_circuit *c, const gkr_
         if (!layer_values[i]) return GKR_ERR_INVALID;
         GKR_TRY(upload_table(ctx, layer_values[i], (uint64_t)1 << c->k[i], w->vals[i]));
     }
+    GKR_TRY(witness_shapes(ctx, w.get()));
     *out = w.release();
     return GKR_OK;
 }
@@ -913,6 +939,7 @@ extern "C" int gkr_witness_eval(gkr_ctx *ctx, const gkr_circuit *c, const gkr_fr
         ctx->end_launch(KC_OTHER, 96.0 * L.n_gates);
         GKR_TRY(ctx->check_launch("layer_eval"));
     }
+    GKR_TRY(witness_shapes(ctx, w.get()));
     GKR_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     *out = w.release();
     return GKR_OK;
@@ -1809,15 +1836,8 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         const uint64_t N = (uint64_t)1 << k;
         const Fr *W = w->vals[li + 1];
         Fr *H = ctx->H.as<Fr>(), *A = ctx->A.as<Fr>();
-        Fr *wu = ctx->misc.as<Fr>();
 
-        // static shape of W_{i+1}: non-zero top coefficient => depends on every variable, degree k
         const double t_setup0 = g_trace ? now_seconds() : 0.0;
-        const uint32_t s_alt = ctx->next_seq();
-        ctx->begin_launch();
-        launch_alt_sum(W, N, ctx->ws, ctx->slot_dev(s_alt), s_alt, ctx->stream);
-        ctx->end_launch(KC_MOBIUS, 32.0 * N);
-        GKR_TRY(ctx->check_launch("alt_sum"));
 
         // table-sharded layer: this rank owns rows idx = i * P + rank of H, A and of the W copy the rounds fold;
         // eq tables and W_{i+1} itself stay replicated (the wiring sums gather from them at random)
@@ -1849,7 +1869,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         if (fuse_wiring) {
             seq_first = ctx->next_seq();
             first_xa = L.sharded ? xchg_begin(ctx, "wiring1") : XchgArg{};
-            launch_wiring_round1(false, true, L.rowptr1, L.gate1, L.other1, ctx->eqz.as<Fr>(), W, nullptr, Wrounds, H, A, Nrows, ctx->ws,
+            launch_wiring_round1(false, true, L.rowptr1, L.gate1, L.other1, ctx->eqz.as<Fr>(), W, WuArg{}, Wrounds, H, A, Nrows, ctx->ws,
                                  ctx->slot_dev(seq_first), seq_first, ctx->stream, first_xa);
             ctx->end_launch(KC_WIRING, 76.0 * L.n_edges1 + 96.0 * Nrows);
             if (L.sharded) GKR_TRY(xchg_finish_round(ctx, 3, seq_first));
@@ -1862,16 +1882,11 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         if (g_trace) { g_trace_t[TS_SETUP_LAUNCH] += now_seconds() - t_setup0; g_trace_n[TS_SETUP_LAUNCH]++; }
 
         uint32_t dep_mask = (uint32_t)(N - 1), max_deg = k;
-        {
-            const HostSlot *slot;
-            g_wait_site = TS_WAIT_SHAPE;
-            GKR_TRY(ctx->wait_slot(s_alt, &slot));
-            g_wait_site = TS_WAIT_OTHER;
-            if (slot->aux[1] == 0) {
-                // degenerate W: exact shape from the full Moebius transform
-                GKR_CUDA_TRY(cudaMemcpyAsync(ctx->mob.ptr, W, N * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
-                GKR_TRY(mobius_support(ctx, ctx->mob.as<Fr>(), k, &dep_mask, &max_deg, nullptr));
-            }
+        // static shape of W_{i+1} (found when the witness was made): a non-zero top coefficient means it depends on
+        // every variable with degree k; a degenerate W gets its exact shape from the full Moebius transform
+        if (!w->top_nonzero[li + 1]) {
+            GKR_CUDA_TRY(cudaMemcpyAsync(ctx->mob.ptr, W, N * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+            GKR_TRY(mobius_support(ctx, ctx->mob.as<Fr>(), k, &dep_mask, &max_deg, nullptr));
         }
 
         rs.assign(2 * k, hfr_zero());
@@ -1910,10 +1925,10 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         }
         // W(u): fold the last size-2 W table with r_k
         const double t_setup1 = g_trace ? now_seconds() : 0.0;
-        ctx->begin_launch();
-        launch_fold(io.W_last, wu, make_const_mul(rs[k - 1]), 1, ctx->stream);
-        ctx->end_launch(KC_OTHER, 96.0);
-        GKR_TRY(ctx->check_launch("fold"));
+        // W(u) = the last size-2 table of phase 1 folded by its last challenge: the phase-2 kernels do that themselves
+        WuArg wu;
+        wu.w_last = io.W_last;
+        wu.r = make_const_mul(rs[k - 1]);
 
         // ---- phase 2: variables c ----
         GKR_TRY(eq_table_dev(ctx, rs.data(), k, ctx->equ.as<Fr>()));

@@ -198,9 +198,9 @@ __global__ void __launch_bounds__(kThreads) k_wiring_rows1(const uint32_t *__res
 }
 __global__ void __launch_bounds__(kThreads) k_wiring_rows2(const uint32_t *__restrict__ rowptr,
                                                            const uint32_t *__restrict__ csr_other,
-                                                           const Fr *__restrict__ P, const Fr *__restrict__ wu_ptr,
+                                                           const Fr *__restrict__ P, const WuArg wua,
                                                            Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n) {
-    const Fr wu = ld_fr(wu_ptr);
+    const Fr wu = fold2(ld_fr(wua.w_last), ld_fr(wua.w_last + 1), wua.r);
     for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
         Fr sa = fr_zero(), sm = fr_zero();
         const uint32_t e0 = rowptr[c], e1 = rowptr[c + 1];
@@ -223,7 +223,7 @@ void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, cons
     k_wiring_rows1<<<stream_grid(n), kThreads, 0, s>>>(rowptr, csr_other, P, Q, H, A, n);
 }
 void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, uint32_t n_edges,
-                          const Fr *eqz, const Fr *equ, const Fr *wu, Fr *P, Fr *H, Fr *A, uint64_t n, cudaStream_t s) {
+                          const Fr *eqz, const Fr *equ, const WuArg &wu, Fr *P, Fr *H, Fr *A, uint64_t n, cudaStream_t s) {
     k_wiring_edges<<<stream_grid(n_edges), kThreads, 0, s>>>(csr_gate, csr_other, eqz, equ, P, nullptr, n_edges);
     k_wiring_rows2<<<stream_grid(n), kThreads, 0, s>>>(rowptr, csr_other, P, wu, H, A, n);
 }
@@ -283,7 +283,7 @@ __device__ __forceinline__ void wiring_row_block(const uint32_t *__restrict__ cs
 template <bool PHASE2, bool FULL>
 __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
     k_wiring_round1(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ csr_gate, const uint32_t *__restrict__ csr_other,
-                    const Fr *__restrict__ X, const Fr *__restrict__ Y, const Fr *__restrict__ wu_ptr, const Fr *__restrict__ Wtab,
+                    const Fr *__restrict__ X, const Fr *__restrict__ Y, const WuArg wua, const Fr *__restrict__ Wtab,
                     Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n, Fr *partials, unsigned int *counter, HostSlot *slot,
                     uint32_t seq, XchgArg xa) {
     constexpr int K = FULL ? 3 : 2;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
     Fr *stU = stage[warp][0], *stV = stage[warp][1];
     const uint64_t half = n / 2, n_blocks = half / 32;
     Fr wu = fr_zero();
-    if (PHASE2) wu = ld_fr(wu_ptr);
+    if (PHASE2) wu = fold2(ld_fr(wua.w_last), ld_fr(wua.w_last + 1), wua.r);
     Fr acc[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) acc[j] = fr_zero();
@@ -357,7 +357,7 @@ __device__ __forceinline__ void cp_async_fr(Fr *dst_smem, const Fr *src) {
 template <bool PHASE2, bool FULL>
 __global__ void __launch_bounds__(kWTile, 2)
     k_wiring_round1_tiled(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ csr_gate, const uint32_t *__restrict__ csr_other,
-                          const Fr *__restrict__ X, const Fr *__restrict__ Y, const Fr *__restrict__ wu_ptr, const Fr *__restrict__ Wtab,
+                          const Fr *__restrict__ X, const Fr *__restrict__ Y, const WuArg wua, const Fr *__restrict__ Wtab,
                           Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n, Fr *partials, unsigned int *counter, HostSlot *slot,
                           uint32_t seq, XchgArg xa, unsigned int *tile_counter, uint32_t tile_base) {
     constexpr int K = FULL ? 3 : 2;
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kWTile, 2)
     const uint64_t half = n / 2;
     const uint32_t n_tiles = (uint32_t)((half + kWTile - 1) / kWTile);
     Fr wu = fr_zero();
-    if (PHASE2) wu = ld_fr(wu_ptr);
+    if (PHASE2) wu = fold2(ld_fr(wua.w_last), ld_fr(wua.w_last + 1), wua.r);
     Fr acc[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) acc[j] = fr_zero();
@@ -470,7 +470,7 @@ static bool wiring_tiled_enabled() {
 }
 
 void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
-                          const Fr *X, const Fr *Y, const Fr *wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
+                          const Fr *X, const Fr *Y, const WuArg &wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
                           HostSlot *slot, uint32_t seq, cudaStream_t s, XchgArg xa) {
     if (n >= kWiringTiledMin && wiring_tiled_enabled()) {
         const uint32_t n_tiles = (uint32_t)((n / 2 + kWTile - 1) / kWTile);

@@ -86,15 +86,21 @@ void launch_eq_table(const FrVec &z_mont, uint32_t k, Fr *out, Fr *scratch, cuda
 // ---- wiring-predicate sums (implicit in rust/src/gkr/sumcheck.rs:49-78,97-124) ------------------
 // Two passes: edge-parallel products P[e] (and Q[e] = eqz[gate[e]] in phase 1), then row sums.  P, Q: n_edges Fr.
 // CSR by left operand: row b lists (gate, right|type<<31)
+// W(u) of phase 2, taken from where the last round of phase 1 left it: the size-2 table w_last folded by the last challenge
+// (done by the phase-2 kernels themselves: no launch of its own between the two phases)
+struct WuArg {
+    const Fr *w_last = nullptr;
+    FrConstMul r{};
+};
 void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, uint32_t n_edges,
                           const Fr *eqz, const Fr *W, Fr *P, Fr *Q, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
 // CSR by right operand: row c lists (gate, left|type<<31); wu = W(u) on device
 void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, uint32_t n_edges,
-                          const Fr *eqz, const Fr *equ, const Fr *wu, Fr *P, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
+                          const Fr *eqz, const Fr *equ, const WuArg &wu, Fr *P, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
 // wiring sums of a phase fused with its first sumcheck round (n >= 64 rows): writes H, A and publishes the round's
 // sums like launch_gkr_round(fold = false, full, ...) would.  phase2: Y = equ and wu = W(u); else Y = W, wu unused.
 void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
-                          const Fr *X, const Fr *Y, const Fr *wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
+                          const Fr *X, const Fr *Y, const WuArg &wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
                           HostSlot *slot_dev, uint32_t seq, cudaStream_t s, XchgArg xa = XchgArg{});
 
 // ---- sumcheck rounds --------------------------------------------------------------------------
