@@ -1012,7 +1012,8 @@ struct PhaseIO {
     gkr_fr *msgs;              // out: [k][3]
     uint8_t *msg_len;          // out: [k]
     gkr_fr *chal_out;          // out: [k] canonical
-    const Fr *W_last;          // out: device pointer to the size-2 W table of the last round
+    const Fr *W_last;          // out: device pointer to the size-2 W table of the last round ...
+    bool W_last_quad = false;  //      ... or, if set, to the size-4 table of the round before (not yet folded with r_{k-1})
     uint32_t shard_bits = 0;   // > 0: H, W, A hold this rank's shard (2^(k - shard_bits) rows each)
     uint32_t first_round_seq = 0;   // != 0: round 1 was already launched (fused with the wiring sums) under this sequence number
     XchgArg first_round_xa{};       // ... and, on a sharded layer, with this exchange
@@ -1274,6 +1275,7 @@ static int run_phase_sharded(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io,
         GKR_TRY(consume_round(ctx, t, io, j, full, slot, st, last_hash));
     }
     io.W_last = Wc;
+    io.W_last_quad = false;
     if (claim_out) *claim_out = st.claim;
     return GKR_OK;
 }
@@ -1317,6 +1319,7 @@ static int run_phase(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *la
             }
         }
         io.W_last = Wc;
+        io.W_last_quad = false;
     }
     // if anything fails after kernels were pre-launched, release them (abort tag) before unwinding
     struct AbortGuard {
@@ -1614,15 +1617,13 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
     }
     // the W table of the last round (T_k, 2 entries)
     if (s <= k - 1 && k >= 2) {
-        // T_k was never materialised by the look-ahead kernels: fold T_{k-1}.W (4 entries) with r_{k-1}
-        Fr *w2 = ctx->misc.as<Fr>() + 16;
-        ctx->begin_launch();
-        launch_fold(T[k - 1].W, w2, make_const_mul(io.challenges[k - 2]), 2, ctx->stream);
-        ctx->end_launch(KC_OTHER, 192.0);
-        GKR_TRY(ctx->check_launch("fold"));
-        io.W_last = w2;
+        // T_k was never materialised by the look-ahead kernels: T_{k-1}.W (4 entries) is still to be folded with
+        // r_{k-1}; whoever needs W(u) does both folds itself (WuArg)
+        io.W_last = T[k - 1].W;
+        io.W_last_quad = true;
     } else {
         io.W_last = T[k].W;       // produced by the last direct round (or the inputs when k == 1)
+        io.W_last_quad = false;
     }
     if (claim_out) *claim_out = st.claim;
     return GKR_OK;
@@ -1929,6 +1930,8 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         WuArg wu;
         wu.w_last = io.W_last;
         wu.r = make_const_mul(rs[k - 1]);
+        wu.quad = io.W_last_quad ? 1 : 0;
+        if (io.W_last_quad) wu.r_prev = make_const_mul(rs[k - 2]);
 
         // ---- phase 2: variables c ----
         GKR_TRY(eq_table_dev(ctx, rs.data(), k, ctx->equ.as<Fr>()));

@@ -196,11 +196,19 @@ __global__ void __launch_bounds__(kThreads) k_wiring_rows1(const uint32_t *__res
         st_fr(A + b, a);
     }
 }
+__device__ __forceinline__ Fr wu_value(const WuArg &a) {
+    if (a.quad) {
+        const Fr lo = fold2(ld_fr(a.w_last), ld_fr(a.w_last + 2), a.r_prev);
+        const Fr hi = fold2(ld_fr(a.w_last + 1), ld_fr(a.w_last + 3), a.r_prev);
+        return fold2(lo, hi, a.r);
+    }
+    return fold2(ld_fr(a.w_last), ld_fr(a.w_last + 1), a.r);
+}
 __global__ void __launch_bounds__(kThreads) k_wiring_rows2(const uint32_t *__restrict__ rowptr,
                                                            const uint32_t *__restrict__ csr_other,
                                                            const Fr *__restrict__ P, const WuArg wua,
                                                            Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n) {
-    const Fr wu = fold2(ld_fr(wua.w_last), ld_fr(wua.w_last + 1), wua.r);
+    const Fr wu = wu_value(wua);
     for (uint64_t c = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; c < n; c += (uint64_t)gridDim.x * blockDim.x) {
         Fr sa = fr_zero(), sm = fr_zero();
         const uint32_t e0 = rowptr[c], e1 = rowptr[c + 1];
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
     Fr *stU = stage[warp][0], *stV = stage[warp][1];
     const uint64_t half = n / 2, n_blocks = half / 32;
     Fr wu = fr_zero();
-    if (PHASE2) wu = fold2(ld_fr(wua.w_last), ld_fr(wua.w_last + 1), wua.r);
+    if (PHASE2) wu = wu_value(wua);
     Fr acc[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) acc[j] = fr_zero();
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(kWTile, 2)
     const uint64_t half = n / 2;
     const uint32_t n_tiles = (uint32_t)((half + kWTile - 1) / kWTile);
     Fr wu = fr_zero();
-    if (PHASE2) wu = fold2(ld_fr(wua.w_last), ld_fr(wua.w_last + 1), wua.r);
+    if (PHASE2) wu = wu_value(wua);
     Fr acc[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) acc[j] = fr_zero();

@@ -91,6 +91,8 @@ void launch_eq_table(const FrVec &z_mont, uint32_t k, Fr *out, Fr *scratch, cuda
 struct WuArg {
     const Fr *w_last = nullptr;
     FrConstMul r{};
+    int quad = 0;               // w_last still holds 4 entries: fold them with r_prev first
+    FrConstMul r_prev{};
 };
 void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, uint32_t n_edges,
                           const Fr *eqz, const Fr *W, Fr *P, Fr *Q, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
