@@ -1852,7 +1852,17 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
             GKR_TRY(ctx->check_launch("take_strided"));
             Wrounds = ctx->shard_w.as<Fr>();
         }
-        GKR_TRY(eq_table_dev(ctx, z.data(), L.k_out, ctx->eqz.as<Fr>()));
+        // small layers build their eq tables inside the fused wiring kernels (no launches of their own)
+        const bool eq_inline = ctx->lookahead && !ctx->paranoid && !L.sharded && N >= 2 && k <= kEqInlineMaxK &&
+                               L.k_out <= kEqInlineMaxK && !ctx->profiling;
+        EqPoints eqp;
+        if (eq_inline) {
+            eqp.use = 1;
+            eqp.kx = L.k_out;
+            for (uint32_t j = 0; j < L.k_out; ++j) eqp.x[j] = to_dev(z[j]);
+        } else {
+            GKR_TRY(eq_table_dev(ctx, z.data(), L.k_out, ctx->eqz.as<Fr>()));
+        }
         // sharded layers run the same look-ahead phases on their shards (GKR_SHARDED_LOOKAHEAD=0: the plain round chain)
         static const bool sharded_lookahead = [] {
             const char *e = getenv("GKR_SHARDED_LOOKAHEAD");
@@ -1860,7 +1870,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         }();
         const bool lookahead = ctx->lookahead && !ctx->paranoid && (!L.sharded || sharded_lookahead);
         // single pass: wiring sums + first round of the phase (needs whole 32-row blocks in both halves of this rank's rows)
-        const bool fuse_wiring = lookahead && Nrows >= 64;
+        const bool fuse_wiring = lookahead && (Nrows >= 64 || eq_inline);
         uint32_t seq_first = 0;
         XchgArg first_xa{};
         if (getenv("GKR_XCHG_TRACE"))
@@ -1871,7 +1881,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
             seq_first = ctx->next_seq();
             first_xa = L.sharded ? xchg_begin(ctx, "wiring1") : XchgArg{};
             launch_wiring_round1(false, true, L.rowptr1, L.gate1, L.other1, ctx->eqz.as<Fr>(), W, WuArg{}, Wrounds, H, A, Nrows, ctx->ws,
-                                 ctx->slot_dev(seq_first), seq_first, ctx->stream, first_xa);
+                                 ctx->slot_dev(seq_first), seq_first, ctx->stream, first_xa, eq_inline ? &eqp : nullptr);
             ctx->end_launch(KC_WIRING, 76.0 * L.n_edges1 + 96.0 * Nrows);
             if (L.sharded) GKR_TRY(xchg_finish_round(ctx, 3, seq_first));
         } else {
@@ -1934,13 +1944,18 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
         if (io.W_last_quad) wu.r_prev = make_const_mul(rs[k - 2]);
 
         // ---- phase 2: variables c ----
-        GKR_TRY(eq_table_dev(ctx, rs.data(), k, ctx->equ.as<Fr>()));
+        if (eq_inline) {
+            eqp.ky = k;
+            for (uint32_t j = 0; j < k; ++j) eqp.y[j] = to_dev(rs[j]);
+        } else {
+            GKR_TRY(eq_table_dev(ctx, rs.data(), k, ctx->equ.as<Fr>()));
+        }
         ctx->begin_launch();
         if (fuse_wiring) {
             seq_first = ctx->next_seq();
             first_xa = L.sharded ? xchg_begin(ctx, "wiring2") : XchgArg{};
             launch_wiring_round1(true, false, L.rowptr2, L.gate2, L.other2, ctx->eqz.as<Fr>(), ctx->equ.as<Fr>(), wu, Wrounds, H, A, Nrows,
-                                 ctx->ws, ctx->slot_dev(seq_first), seq_first, ctx->stream, first_xa);
+                                 ctx->ws, ctx->slot_dev(seq_first), seq_first, ctx->stream, first_xa, eq_inline ? &eqp : nullptr);
             ctx->end_launch(KC_WIRING, 76.0 * L.n_edges2 + 96.0 * Nrows);
             if (L.sharded) GKR_TRY(xchg_finish_round(ctx, 2, seq_first));
         } else {

@@ -249,10 +249,11 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 #define GKR_WIRING_MINB 2
 #endif
 // one staged edge: gathers + product, written to the warp's staging arrays at position pos
-template <bool PHASE2>
+template <bool PHASE2, bool XS, bool YS>
 __device__ __forceinline__ void wiring_stage_edge(uint32_t g, uint32_t o, const Fr *__restrict__ X, const Fr *__restrict__ Y,
                                                   Fr *stU, Fr *stV, int pos) {
-    const Fr x = ld_fr(X + g), y = ld_fr(Y + (o & 0x7fffffffu));
+    // XS / YS: the table lives in shared memory (built by this kernel), else in global memory
+    const Fr x = XS ? X[g] : ld_fr(X + g), y = YS ? Y[o & 0x7fffffffu] : ld_fr(Y + (o & 0x7fffffffu));
     const Fr p = fr_mul(x, y);
     const bool is_mul = o >> 31;
     if (PHASE2) {                    // u: sum over add gates of p, v: sum over mult gates of p
@@ -264,12 +265,13 @@ __device__ __forceinline__ void wiring_stage_edge(uint32_t g, uint32_t o, const 
     }
 }
 constexpr int kWiringChunk = 64;     // edges staged per pass: two per lane, four gathers in flight per lane
-template <bool PHASE2>
+template <bool PHASE2, bool XS, bool YS>
 __device__ __forceinline__ void wiring_row_block(const uint32_t *__restrict__ csr_gate, const uint32_t *__restrict__ csr_other,
                                                  const Fr *__restrict__ X, const Fr *__restrict__ Y, uint32_t e0, uint32_t e1,
-                                                 Fr *stU, Fr *stV, Fr &u, Fr &v) {
+                                                 int last_lane, Fr *stU, Fr *stV, Fr &u, Fr &v) {
     const int lane = threadIdx.x & 31;
-    const uint32_t E0 = __shfl_sync(0xffffffffu, e0, 0), E1 = __shfl_sync(0xffffffffu, e1, 31);
+    // rows of the block = lanes 0..last_lane (lanes beyond it carry the empty segment e0 = e1 = 0)
+    const uint32_t E0 = __shfl_sync(0xffffffffu, e0, 0), E1 = __shfl_sync(0xffffffffu, e1, last_lane);
     u = fr_zero();
     v = fr_zero();
     for (uint32_t cs = E0; cs < E1; cs += kWiringChunk) {
@@ -277,8 +279,8 @@ __device__ __forceinline__ void wiring_row_block(const uint32_t *__restrict__ cs
         uint32_t ga = 0, oa = 0, gb = 0, ob = 0;
         if (ea < E1) { ga = csr_gate[ea]; oa = csr_other[ea]; }
         if (eb < E1) { gb = csr_gate[eb]; ob = csr_other[eb]; }
-        if (ea < E1) wiring_stage_edge<PHASE2>(ga, oa, X, Y, stU, stV, lane);
-        if (eb < E1) wiring_stage_edge<PHASE2>(gb, ob, X, Y, stU, stV, 32 + lane);
+        if (ea < E1) wiring_stage_edge<PHASE2, XS, YS>(ga, oa, X, Y, stU, stV, lane);
+        if (eb < E1) wiring_stage_edge<PHASE2, XS, YS>(gb, ob, X, Y, stU, stV, 32 + lane);
         __syncwarp();
         const uint32_t lo = e0 > cs ? e0 : cs, hi = e1 < cs + kWiringChunk ? e1 : cs + kWiringChunk;
         for (uint32_t q = lo; q < hi; ++q) {
@@ -288,17 +290,49 @@ __device__ __forceinline__ void wiring_row_block(const uint32_t *__restrict__ cs
         __syncwarp();
     }
 }
-template <bool PHASE2, bool FULL>
+// eq(point, .) over nv variables into shared memory, by doubling (variable 0 = most significant index bit, as k_eq_small)
+__device__ __forceinline__ void build_eq_shared(Fr *E, const Fr *point, uint32_t nv) {
+    if (threadIdx.x == 0) E[0] = fr_one();
+    __syncthreads();
+    for (uint32_t j = 0; j < nv; ++j) {
+        const uint32_t have = 1u << j;
+        const Fr zj = point[j];
+        // at most 2^(kEqInlineMaxK - 1) = 256 = blockDim.x entries to split per level
+        Fr e = fr_zero();
+        if (threadIdx.x < have) e = E[threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x < have) {
+            const Fr hi = fr_mul(e, zj);
+            E[2 * threadIdx.x + 1] = hi;
+            E[2 * threadIdx.x] = fr_sub(e, hi);
+        }
+        __syncthreads();
+    }
+}
+// EQS: single-CTA launch for small layers; X (and Y in phase 2) are built here from their points (EqPoints) into dynamic
+// shared memory, and the last row block may be partial (tables down to 2 rows)
+template <bool PHASE2, bool FULL, bool EQS>
 __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
     k_wiring_round1(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ csr_gate, const uint32_t *__restrict__ csr_other,
                     const Fr *__restrict__ X, const Fr *__restrict__ Y, const WuArg wua, const Fr *__restrict__ Wtab,
                     Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n, Fr *partials, unsigned int *counter, HostSlot *slot,
-                    uint32_t seq, XchgArg xa) {
+                    uint32_t seq, XchgArg xa, const EqPoints eqp) {
     constexpr int K = FULL ? 3 : 2;
+    constexpr bool YS = EQS && PHASE2;
     __shared__ Fr stage[kWarps][2][kWiringChunk];
+    extern __shared__ __align__(16) unsigned char eq_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Fr *stU = stage[warp][0], *stV = stage[warp][1];
-    const uint64_t half = n / 2, n_blocks = half / 32;
+    if (EQS) {
+        Fr *EX = reinterpret_cast<Fr *>(eq_smem), *EY = EX + ((size_t)1 << eqp.kx);
+        build_eq_shared(EX, eqp.x, eqp.kx);
+        X = EX;
+        if (PHASE2) {
+            build_eq_shared(EY, eqp.y, eqp.ky);
+            Y = EY;
+        }
+    }
+    const uint64_t half = n / 2, n_blocks = EQS ? (half + 31) / 32 : half / 32;
     Fr wu = fr_zero();
     if (PHASE2) wu = wu_value(wua);
     Fr acc[K];
@@ -310,22 +344,27 @@ __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
     uint32_t nL0 = 0, nL1 = 0, nH0 = 0, nH1 = 0;
     if (blk_first < n_blocks) {
         const uint64_t r = blk_first * 32 + lane;
-        nL0 = rowptr[r]; nL1 = rowptr[r + 1]; nH0 = rowptr[r + half]; nH1 = rowptr[r + half + 1];
+        if (!EQS || r < half) { nL0 = rowptr[r]; nL1 = rowptr[r + 1]; nH0 = rowptr[r + half]; nH1 = rowptr[r + half + 1]; }
     }
     for (uint64_t blk = blk_first; blk < n_blocks; blk += blk_step) {
         const uint64_t rowL = blk * 32 + lane, rowH = rowL + half;
         const uint32_t eL0 = nL0, eL1 = nL1, eH0 = nH0, eH1 = nH1;
+        nL0 = nL1 = nH0 = nH1 = 0;
         if (blk + blk_step < n_blocks) {
             const uint64_t r = (blk + blk_step) * 32 + lane;
-            nL0 = rowptr[r]; nL1 = rowptr[r + 1]; nH0 = rowptr[r + half]; nH1 = rowptr[r + half + 1];
+            if (!EQS || r < half) { nL0 = rowptr[r]; nL1 = rowptr[r + 1]; nH0 = rowptr[r + half]; nH1 = rowptr[r + half + 1]; }
         }
-        const Fr wl = ld_fr(Wtab + rowL), wh = ld_fr(Wtab + rowH);
+        // a partial block (EQS only): lanes beyond the last row carry empty segments and store nothing
+        const bool valid = !EQS || rowL < half;
+        const int last_lane = !EQS || half - blk * 32 >= 32 ? 31 : (int)(half - blk * 32) - 1;
+        Fr wl = fr_zero(), wh = fr_zero();
+        if (valid) { wl = ld_fr(Wtab + rowL); wh = ld_fr(Wtab + rowH); }
         Fr h[2], a[2];
 #pragma unroll
         for (int side = 0; side < 2; ++side) {
             const uint32_t e0 = side ? eH0 : eL0, e1 = side ? eH1 : eL1;
             Fr u, v;
-            wiring_row_block<PHASE2>(csr_gate, csr_other, X, Y, e0, e1, stU, stV, u, v);
+            wiring_row_block<PHASE2, EQS, YS>(csr_gate, csr_other, X, Y, e0, e1, last_lane, stU, stV, u, v);
             if (PHASE2) {                    // H2 = S_add + W(u) S_mul, A2 = W(u) S_add
                 h[side] = u;
                 a[side] = fr_zero();
@@ -337,9 +376,12 @@ __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
                 h[side] = u;
                 a[side] = v;
             }
-            st_fr(H + (side ? rowH : rowL), h[side]);
-            st_fr(A + (side ? rowH : rowL), a[side]);
+            if (valid) {
+                st_fr(H + (side ? rowH : rowL), h[side]);
+                st_fr(A + (side ? rowH : rowL), a[side]);
+            }
         }
+        // (lanes of a partial block beyond its last row hold h = a = w = 0 and add nothing)
         acc[0] = fr_add(acc[0], fr_add(fr_mul(h[0], wl), a[0]));
         acc[1] = fr_add(acc[1], fr_mul(fr_sub(h[1], h[0]), fr_sub(wh, wl)));
         if (FULL) acc[K - 1] = fr_add(acc[K - 1], fr_add(fr_mul(h[1], wh), a[1]));
@@ -479,7 +521,17 @@ static bool wiring_tiled_enabled() {
 
 void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
                           const Fr *X, const Fr *Y, const WuArg &wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
-                          HostSlot *slot, uint32_t seq, cudaStream_t s, XchgArg xa) {
+                          HostSlot *slot, uint32_t seq, cudaStream_t s, XchgArg xa, const EqPoints *eqp) {
+    if (eqp && eqp->use) {
+        // small layer: one CTA, eq tables in shared memory
+        const size_t smem = sizeof(Fr) * (((size_t)1 << eqp->kx) + (phase2 ? ((size_t)1 << eqp->ky) : 0));
+#define GKR_WR1S(P2, F) \
+    k_wiring_round1<P2, F, true><<<1, kThreads, smem, s>>>(rowptr, csr_gate, csr_other, nullptr, Y, wu, Wtab, H, A, n, ws.partials, ws.counter, slot, seq, xa, *eqp)
+        if (phase2) { if (full) GKR_WR1S(true, true); else GKR_WR1S(true, false); }
+        else { if (full) GKR_WR1S(false, true); else GKR_WR1S(false, false); }
+#undef GKR_WR1S
+        return;
+    }
     if (n >= kWiringTiledMin && wiring_tiled_enabled()) {
         const uint32_t n_tiles = (uint32_t)((n / 2 + kWTile - 1) / kWTile);
         int grid = device_sm_count() * 2;
@@ -503,7 +555,7 @@ void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const 
     if (grid > ws.max_blocks) grid = ws.max_blocks;
     if (grid < 1) grid = 1;
 #define GKR_WR1(P2, F) \
-    k_wiring_round1<P2, F><<<grid, kThreads, 0, s>>>(rowptr, csr_gate, csr_other, X, Y, wu, Wtab, H, A, n, ws.partials, ws.counter, slot, seq, xa)
+    k_wiring_round1<P2, F, false><<<grid, kThreads, 0, s>>>(rowptr, csr_gate, csr_other, X, Y, wu, Wtab, H, A, n, ws.partials, ws.counter, slot, seq, xa, EqPoints{})
     if (phase2) { if (full) GKR_WR1(true, true); else GKR_WR1(true, false); }
     else { if (full) GKR_WR1(false, true); else GKR_WR1(false, false); }
 #undef GKR_WR1
@@ -1398,6 +1450,11 @@ int kernels_device_init(int device) {
         cudaError_t e = cudaFuncSetAttribute(k_gkr_poly_tail_cmd<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gkr_poly_tail_cmd<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mobius_low, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << kMobTile);
+        const int eq_smem = (int)(sizeof(Fr) * 2 * ((size_t)1 << kEqInlineMaxK));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wiring_round1<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eq_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wiring_round1<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eq_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wiring_round1<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eq_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wiring_round1<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, eq_smem);
         const int wiring_smem = (int)(sizeof(Fr) * 2 * kWCap);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wiring_round1_tiled<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wiring_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wiring_round1_tiled<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wiring_smem);

@@ -94,6 +94,15 @@ struct WuArg {
     int quad = 0;               // w_last still holds 4 entries: fold them with r_prev first
     FrConstMul r_prev{};
 };
+// Small layers (every table of at most 2^kEqInlineMaxK entries): the fused wiring kernel builds eq(z, .) -- and in
+// phase 2 eq(u, .) -- in shared memory itself instead of gathering from tables a separate launch made
+constexpr uint32_t kEqInlineMaxK = 9;
+struct EqPoints {
+    Fr x[kEqInlineMaxK];          // point of the X table (z)
+    Fr y[kEqInlineMaxK];          // point of the Y table (u; phase 2 only)
+    uint32_t kx = 0, ky = 0;      // variables of the two points
+    uint32_t use = 0;             // 0: not used, gather from the X / Y tables
+};
 void launch_wiring_phase1(const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other, uint32_t n_edges,
                           const Fr *eqz, const Fr *W, Fr *P, Fr *Q, Fr *H, Fr *A, uint64_t n, cudaStream_t s);
 // CSR by right operand: row c lists (gate, left|type<<31); wu = W(u) on device
@@ -103,7 +112,7 @@ void launch_wiring_phase2(const uint32_t *rowptr, const uint32_t *csr_gate, cons
 // sums like launch_gkr_round(fold = false, full, ...) would.  phase2: Y = equ and wu = W(u); else Y = W, wu unused.
 void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const uint32_t *csr_gate, const uint32_t *csr_other,
                           const Fr *X, const Fr *Y, const WuArg &wu, const Fr *Wtab, Fr *H, Fr *A, uint64_t n, const ReduceWs &ws,
-                          HostSlot *slot_dev, uint32_t seq, cudaStream_t s, XchgArg xa = XchgArg{});
+                          HostSlot *slot_dev, uint32_t seq, cudaStream_t s, XchgArg xa = XchgArg{}, const EqPoints *eqp = nullptr);
 
 // ---- sumcheck rounds --------------------------------------------------------------------------
 // GKR round (degree 2) on (H, W, A).  Publishes v[0] = g(0), v[1] = X^2 coefficient, and v[2] = g(1)
