@@ -1400,6 +1400,13 @@ static uint64_t lookahead_entries() {
 // device stays one round ahead: kernel P_j folds T_{j-1} with r_{j-1} into T_j and publishes the six sums that give
 // message j+1 as a quadratic in r_j (k_gkr_poly; P_s has no fold, it reads T_s), so that when the host has hashed r_j
 // it evaluates message j+1 at once -- a round then costs max(hash, device) instead of hash + device.
+static bool tail_from_first_level() {
+    static const bool on = [] {
+        const char *e = getenv("GKR_TAIL_FROM_FIRST");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
 static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HFr *last_hash, const HFr *claim_in,
                           HFr *claim_out) {
     // Table-sharded layers (io.shard_bits > 0): H, W, A hold this rank's rows and every reducing kernel that runs on
@@ -1495,6 +1502,27 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         }
         const Level &in = fold ? T[j - 1] : T[j];
         const uint64_t quads = T[j].n / 4;
+        // small tables: the first look-ahead level (no fold, no command) and every level after it run as ONE
+        // single-CTA kernel that waits for its challenges on the device
+        if (!fold && j == s && can_prelaunch && !sharded && quads <= (uint64_t)gkr_poly_tail_max_quads() && tail_from_first_level()) {
+            const uint32_t n_levels = k - s;                             // levels s .. k-1
+            const uint32_t seq0 = ctx->next_seq_run(n_levels);
+            for (uint32_t v = s; v + 1 <= k; ++v) {
+                P[v].seq = seq0 + (v - s);
+                P[v].launched = true;
+                if (v > s) {
+                    write_cmd(ctx->cmds_host + (P[v].seq % gkr_ctx::kSlots), nullptr, 0u);
+                    ctx->prelaunched_pending++;
+                }
+            }
+            p.commanded = true;
+            PolyTailArgs a = tail_args(s + 1, n_levels, seq0);            // (tail_args takes T[u0 - 1] = T_s as the input)
+            a.u0 = s;
+            a.first_nofold = 1;
+            launch_gkr_poly_tail(a, ctx->stream);
+            ctx->stats.kernel_launches += 1;
+            return ctx->check_launch("gkr_poly_tail");
+        }
         p.seq = ctx->next_seq();
         const FrConstMul rc = fold ? make_const_mul(st.r) : FrConstMul{};
         const XchgArg xa = local_level(j) ? xchg_begin(ctx, "poly") : XchgArg{};

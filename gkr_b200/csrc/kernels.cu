@@ -889,7 +889,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_gkr_poly_tail_cmd(PolyTailArgs a
         HostSlot *slot = a.slots + (seq % a.n_slots);
         unsigned long long t_enter = 0, t_cmd = 0;
         if (a.trace && t == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_enter));
-        if (!wait_cmd(a.cmds + (seq % a.n_slots), seq, raw, &ok)) {
+        const bool nofold0 = a.first_nofold && lv == 0;
+        if (!nofold0 && !wait_cmd(a.cmds + (seq % a.n_slots), seq, raw, &ok)) {
             if (t == 0) {
                 slot->aux[2] = 0xDEADu;
                 __threadfence_system();
@@ -906,7 +907,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gkr_poly_tail_cmd(PolyTailArgs a
         if (active) {
             const uint32_t e = i + sq * q4;             // entry of T_u; folds entries e and e + n of T_{u-1}
             Fr h, w, av;
-            if (lv == 0) {
+            if (nofold0) {                              // T_u0 itself (it already lives in global memory: no copy back)
+                h = ld_fr(a.H0 + e);
+                w = ld_fr(a.W0 + e);
+                av = ld_fr(a.A0 + e);
+            } else if (lv == 0) {
                 h = fold2(ld_fr(a.H0 + e), ld_fr(a.H0 + e + n), r);
                 w = fold2(ld_fr(a.W0 + e), ld_fr(a.W0 + e + n), r);
                 av = fold2(ld_fr(a.A0 + e), ld_fr(a.A0 + e + n), r);
@@ -915,9 +920,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gkr_poly_tail_cmd(PolyTailArgs a
                 w = fold2(in_s[2 * n + e], in_s[2 * n + e + n], r);
                 av = fold2(in_s[4 * n + e], in_s[4 * n + e + n], r);
             }
-            st_fr(gout + e, h);
-            st_fr(gout + n + e, w);
-            st_fr(gout + 2 * n + e, av);
+            if (!nofold0) {
+                st_fr(gout + e, h);
+                st_fr(gout + n + e, w);
+                st_fr(gout + 2 * n + e, av);
+            }
             out_s[e] = h;
             out_s[n + e] = w;
             out_s[2 * n + e] = av;

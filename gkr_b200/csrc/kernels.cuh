@@ -144,6 +144,7 @@ struct PolyTailArgs {
     HostSlot *slots;
     uint32_t n_slots, seq0;
     uint32_t trace;            // also publish a device timeline of each level (development aid)
+    uint32_t first_nofold;     // the first level has no fold and no command: H0/W0/A0 ARE T_u0 (the first look-ahead level)
 };
 void launch_gkr_poly_tail(const PolyTailArgs &a, cudaStream_t s);
 int gkr_poly_tail_max_quads();
