@@ -60,15 +60,26 @@ def _workload_name(k, layers):
 # clocks sampler (nvidia-smi in the background during the timed region)
 # --------------------------------------------------------------------------------------------------
 class Clocks:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+
+        def away_from_the_prover():
+            # the proof is a serial chain of host hashes on one core: keep the sampler (NVML start-up and one query
+            # every 250 ms) on the last CPU this process may use, where the scheduler will not put that thread
+            try:
+                cpus = sorted(os.sched_getaffinity(0))
+                if len(cpus) > 1:
+                    os.sched_setaffinity(0, {cpus[-1]})
+            except OSError:
+                pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "250", "-i", str(index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+                                          "-lms", "250", "-i", str(index)], stdout=self.tmp, stderr=subprocess.DEVNULL,
+                                         preexec_fn=away_from_the_prover)
         except Exception:
             self.proc = None
 
@@ -86,14 +97,14 @@ class Clocks:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.tmp.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 6:
                 continue
             try:
                 sm.append(float(parts[0]))
                 mx.append(float(parts[1]))
             except ValueError:
                 continue
-            for nm, val in zip(names, parts[3:7]):
+            for nm, val in zip(names, parts[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         try:
