@@ -546,6 +546,9 @@ void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const 
         if (phase2) { if (full) GKR_WR1T(true, true); else GKR_WR1T(true, false); }
         else { if (full) GKR_WR1T(false, true); else GKR_WR1T(false, false); }
 #undef GKR_WR1T
+        // a launch that was refused never draws its tickets: keep the host's count in step with the device counter
+        // (the error itself stays pending for the caller's check)
+        if (cudaPeekAtLastError() != cudaSuccess) ws.tile_base = base;
         return;
     }
     const uint64_t n_blocks = n / 64;

@@ -36,4 +36,19 @@ w.close()
 for v in (2, 9, 13):
     tabs = [pv.dev_table_synth(1, syn.TABLE_STREAM + t, 1 << v) for t in range(3)]
     assert pv.sumcheck_prod(tabs, v) == orc.sumcheck_prod([orc.synth_values(1, syn.TABLE_STREAM + t, 1 << v) for t in range(3)], v)
+# the lockstep batch prover (fibers, lane hash) on a few small circuits, against one-at-a-time proofs
+from gkr_b200.batch import NativeBatch  # noqa: E402
+jobs = []
+for sd, (k, nl) in enumerate(((3, 2), (5, 3), (6, 2), (4, 4), (7, 2), (2, 1))):
+    jobs.append((syn.layered_circuit(10 + sd, k, nl), syn.input_values(10 + sd, k)))
+with NativeBatch(2, 3) as nb:
+    nb.load(jobs)
+    got_b = nb.prove()
+for (layers, inputs), g in zip(jobs, got_b):
+    c = pv.circuit(layers)
+    w = pv.witness_eval(c, inputs)
+    want = pv.prove(c, w)
+    assert g.sumcheck_proofs == want.sumcheck_proofs and g.q == want.q and g.z == want.z and g.d_coef == want.d_coef
+    w.close()
+    c.close()
 print("sanitize smoke ok,", pv.stats()["kernel_launches"], "launches")
