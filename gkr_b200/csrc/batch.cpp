@@ -7,9 +7,10 @@
 // for a challenge the scheduler hashes all pending messages in one AVX-512 IFMA call (mimc7_lanes.cpp, 8 or 16 lanes)
 // and resumes them.  Waits for the device yield to the scheduler between polls, so the device work of one proof
 // overlaps the host work of the others and no fiber can starve the one whose command a kernel is waiting for.
+// A proof switches about 180 times (one suspend per challenge, ~30 yields): the switch is a dozen instructions of
+// our own (callee-saved registers + stack pointer); glibc's swapcontext makes a signal-mask system call each way.
 #include <sched.h>
 #include <sys/mman.h>
-#include <ucontext.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -28,6 +29,36 @@
 
 using namespace gkr;
 
+#if !defined(__x86_64__)
+#error "the batch scheduler's context switch is written for x86-64 (System V ABI)"
+#endif
+// gkr_fiber_switch(&save, load): park the caller (callee-saved registers on its stack, stack pointer into *save) and
+// continue the context whose stack pointer is `load` (parked the same way, or prepared by Worker::prove)
+extern "C" void gkr_fiber_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl gkr_fiber_switch
+.hidden gkr_fiber_switch
+.type gkr_fiber_switch,@function
+gkr_fiber_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size gkr_fiber_switch,.-gkr_fiber_switch
+)");
+
 namespace {
 
 constexpr size_t kStackBytes = 512 << 10;
@@ -36,7 +67,7 @@ constexpr int kMaxLanes = 32;
 struct Worker;
 
 struct Fiber {
-    ucontext_t uc{};
+    void *sp = nullptr;          // parked stack pointer
     void *stack = nullptr;
     gkr_ctx *ctx = nullptr;
     Worker *worker = nullptr;
@@ -90,7 +121,7 @@ struct Worker {
     int index = 0;
     std::thread th;
     std::vector<Fiber> fibers;
-    ucontext_t sched_uc{};
+    void *sched_sp = nullptr;
     Fiber *cur = nullptr;
     FiberHooks hooks{};
     std::vector<Item> items;
@@ -110,7 +141,7 @@ struct Worker {
 void hook_yield(void *self) {
     Worker *w = static_cast<Worker *>(self);
     Fiber *f = w->cur;
-    swapcontext(&f->uc, &w->sched_uc);
+    gkr_fiber_switch(&f->sp, w->sched_sp);
 }
 void hook_hash(void *self, const HFr *msg, uint32_t n, HFr *out) {
     Worker *w = static_cast<Worker *>(self);
@@ -119,7 +150,7 @@ void hook_hash(void *self, const HFr *msg, uint32_t n, HFr *out) {
     f->hash_n = n;
     f->hash_out = out;
     f->state = Fiber::WAIT_HASH;
-    swapcontext(&f->uc, &w->sched_uc);
+    gkr_fiber_switch(&f->sp, w->sched_sp);
 }
 
 thread_local Worker *tl_worker = nullptr;
@@ -128,7 +159,8 @@ void fiber_entry() {
     Fiber *f = w->cur;
     w->fiber_body(f);
     f->state = Fiber::DONE;
-    swapcontext(&f->uc, &w->sched_uc);      // never resumed
+    gkr_fiber_switch(&f->sp, w->sched_sp);      // never resumed
+    abort();
 }
 
 void Worker::fiber_body(Fiber *f) {
@@ -147,6 +179,7 @@ void Worker::fiber_body(Fiber *f) {
     }
 }
 
+std::atomic<uint64_t> g_hash_calls{0}, g_hash_lanes{0};      // development counters (GKR_BATCH_TRACE)
 void Worker::hash_pending() {
     const HFr *msg[kMaxLanes];
     uint32_t n[kMaxLanes];
@@ -160,6 +193,8 @@ void Worker::hash_pending() {
             who[cnt++] = &f;
         }
     if (cnt == 0) return;
+    g_hash_calls.fetch_add(1, std::memory_order_relaxed);
+    g_hash_lanes.fetch_add((uint64_t)cnt, std::memory_order_relaxed);
     if (mimc7_lanes_available() && cnt > 1) {
         mimc7_multi_hash_lanes(msg, n, out, cnt);
     } else {
@@ -259,11 +294,13 @@ void Worker::prove() {
             f.state = Fiber::DONE;
             continue;
         }
-        getcontext(&f.uc);
-        f.uc.uc_stack.ss_sp = static_cast<char *>(f.stack) + 4096;
-        f.uc.uc_stack.ss_size = kStackBytes;
-        f.uc.uc_link = &sched_uc;
-        makecontext(&f.uc, fiber_entry, 0);
+        // a fresh context: six zeroed callee-saved registers, then fiber_entry as the return address, laid out so that
+        // fiber_entry starts with the stack alignment of a called function
+        void **top = reinterpret_cast<void **>((reinterpret_cast<uintptr_t>(f.stack) + 4096 + kStackBytes) & ~(uintptr_t)15);
+        top[-1] = nullptr;
+        top[-2] = reinterpret_cast<void *>(&fiber_entry);
+        for (int r = 3; r <= 8; ++r) top[-r] = nullptr;
+        f.sp = &top[-8];
         f.state = Fiber::RUNNABLE;
         ++alive;
     }
@@ -275,7 +312,7 @@ void Worker::prove() {
             if (f.state != Fiber::RUNNABLE) continue;
             cur = &f;
             tl_fiber = &hooks;
-            swapcontext(&sched_uc, &f.uc);
+            gkr_fiber_switch(&sched_sp, f.sp);
             tl_fiber = nullptr;
             if (f.state == Fiber::DONE) --alive;
         }
@@ -438,6 +475,12 @@ extern "C" int gkr_batch_prove(gkr_batch *b, gkr_proof **proofs_out, double *sec
     const int rc = run_command(b, CMD_PROVE);
     b->proofs = nullptr;
     if (seconds_out) *seconds_out = b->t_end - b->t_start;
+    if (getenv("GKR_BATCH_TRACE"))
+        fprintf(stderr, "[gkr batch] %zu proofs in %.2f ms; since the last report: %llu stream polls, %llu yields while waiting for a round "
+                        "result, %llu hash calls for %llu messages\n",
+                b->n_jobs, 1e3 * (b->t_end - b->t_start), (unsigned long long)g_fiber_stream_polls.exchange(0),
+                (unsigned long long)g_fiber_slot_yields.exchange(0), (unsigned long long)g_hash_calls.exchange(0),
+                (unsigned long long)g_hash_lanes.exchange(0));
     if (rc != GKR_OK && proofs_out)
         for (size_t j = 0; j < b->n_jobs; ++j) {
             if (proofs_out[j]) gkr_proof_free(proofs_out[j]);

@@ -34,10 +34,14 @@ using namespace gkr;
 namespace gkr {
 static thread_local char g_err[512] = "";
 thread_local FiberHooks *tl_fiber = nullptr;
+std::atomic<uint64_t> g_fiber_stream_polls{0}, g_fiber_slot_yields{0};
 cudaError_t stream_sync(cudaStream_t st) {
     if (!tl_fiber) return cudaStreamSynchronize(st);
     cudaError_t e;
-    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) tl_fiber->yield(tl_fiber->self);
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {
+        g_fiber_stream_polls.fetch_add(1, std::memory_order_relaxed);
+        tl_fiber->yield(tl_fiber->self);
+    }
     return e;
 }
 void set_last_error(const char *fmt, ...) {
@@ -378,7 +382,10 @@ int gkr_ctx::wait_slot(uint32_t s, const HostSlot **out) {
     double next_check = t0 + 2.0;
     while (slot->seq != s) {
         _mm_pause();
-        if (tl_fiber && (spins & 0xF) == 0xF) tl_fiber->yield(tl_fiber->self);     // let the other proofs of the batch run
+        if (tl_fiber && (spins & 0xF) == 0xF) {                                    // let the other proofs of the batch run
+            g_fiber_slot_yields.fetch_add(1, std::memory_order_relaxed);
+            tl_fiber->yield(tl_fiber->self);
+        }
         if ((++spins & 0xFFF) != 0) continue;
         const double now = now_seconds();
         if (now < next_check) continue;

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -147,6 +148,7 @@ struct FiberHooks {
     void (*hash)(void *self, const HFr *msg, uint32_t n, HFr *out);
 };
 extern thread_local FiberHooks *tl_fiber;
+extern std::atomic<uint64_t> g_fiber_stream_polls, g_fiber_slot_yields;    // development counters (GKR_BATCH_TRACE)
 // cudaStreamSynchronize, or a query/yield loop on a fiber
 cudaError_t stream_sync(cudaStream_t st);
 // moves the proof's pinned tables to ordinary memory and returns the pinned blocks to the pool (a batch keeps
