@@ -1407,6 +1407,13 @@ static uint64_t lookahead_entries() {
 // device stays one round ahead: kernel P_j folds T_{j-1} with r_{j-1} into T_j and publishes the six sums that give
 // message j+1 as a quadratic in r_j (k_gkr_poly; P_s has no fold, it reads T_s), so that when the host has hashed r_j
 // it evaluates message j+1 at once -- a round then costs max(hash, device) instead of hash + device.
+static uint64_t aux_gate_entries() {
+    static const uint64_t n = [] {
+        const char *e = getenv("GKR_AUX_GATE_LOG2");
+        return (uint64_t)1 << (e ? atoi(e) : 13);   // 2^20 x 16 proof: 24.3 ms released behind the direct rounds, 23.95 at 2^12..2^13
+    }();
+    return n;
+}
 static bool tail_from_first_level() {
     static const bool on = [] {
         const char *e = getenv("GKR_TAIL_FROM_FIRST");
@@ -1570,6 +1577,7 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
 
     // direct rounds 1 .. min(s, k): fused fold + message, exactly as in run_phase
     const uint32_t last_direct = s <= k ? s : k;
+    bool aux_released = false;
     for (uint32_t j = 1; j <= last_direct; ++j) {
         const bool fused_first = j == 1 && io.first_round_seq != 0;
         const uint32_t sq = fused_first ? io.first_round_seq : ctx->next_seq();
@@ -1598,7 +1606,13 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         if (!fused_first && local_level(j)) GKR_TRY(xchg_finish_round(ctx, full ? 3 : 2, sq));
         if (g_trace && !fused_first) { g_trace_t[TS_DIRECT_LAUNCH] += now_seconds() - t_launch0; g_trace_n[TS_DIRECT_LAUNCH]++; }
         if (j == s) GKR_TRY(start_poly(s));           // right behind the kernel that produced T_s: prepares message s+1
-        if (j == last_direct) GKR_TRY(release_aux_jobs(ctx, true));   // bulk work of the previous layer goes behind these
+        // bulk work of the previous layer (its line restriction, ~0.3 ms of kernels on the low-priority stream) goes behind
+        // the large kernels of this phase: behind the direct rounds, or -- if look-ahead levels above aux_gate_entries()
+        // follow -- behind those too (they are device-bound and were measured 20 us slower each with the bulk work beside them)
+        if (j == last_direct && (s > k - 1 || T[s].n <= aux_gate_entries())) {
+            GKR_TRY(release_aux_jobs(ctx, true));
+            aux_released = true;
+        }
         const HostSlot *slot;
         HostSlot xsum;
         g_wait_site = TS_WAIT_DIRECT;
@@ -1613,6 +1627,10 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         if (j + 1 <= k) {                              // device: fold with r_{j-1}, prepare message j+1
             TraceScope ts_start(TS_START_POLY);
             GKR_TRY(start_poly(j));
+            if (!aux_released && T[j].n <= aux_gate_entries()) {
+                GKR_TRY(release_aux_jobs(ctx, true));
+                aux_released = true;
+            }
         }
         const HostSlot *slot;
         HostSlot xsum;
@@ -1650,6 +1668,7 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
         const HFr x2 = hfr_add(E0, hfr_mul(r_prev, hfr_add(hfr_sub(hfr_sub(E1, E0), E2), hfr_mul(E2, r_prev))));
         GKR_TRY(consume_values(ctx, t, io, j - 1, false, x0, x2, hfr_zero(), st, last_hash));
     }
+    if (!aux_released) GKR_TRY(release_aux_jobs(ctx, true));
     // the W table of the last round (T_k, 2 entries)
     if (s <= k - 1 && k >= 2) {
         // T_k was never materialised by the look-ahead kernels: T_{k-1}.W (4 entries) is still to be folded with
