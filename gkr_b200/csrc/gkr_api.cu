@@ -1686,10 +1686,27 @@ static int run_phase_poly(gkr_ctx *ctx, const gkr_transcript *t, PhaseIO &io, HF
 // q_i machinery: W restricted to the line b -> c, k+1 ascending coefficients in canonical form at out_canonical (device).
 // Levels 0..2 in one register-resident pass, then one launch per level while the table is large, then every remaining
 // level in one single-CTA launch (k = 20: 8 launches instead of 21; k <= 11: one).
+// the single-CTA tail is multiplier-bound on its one SM (2048 entries: ~28 k (entry, coefficient) items, 126 us); large
+// tables therefore keep folding with the whole device down to line_tail_entries(k) entries first
+static uint64_t line_tail_entries(uint32_t k) {
+    static const uint64_t small = [] {
+        const char *e = getenv("GKR_LINE_TAIL_LOG2");
+        return (uint64_t)1 << (e ? atoi(e) : 8);
+    }();
+    return ((uint64_t)1 << k) > kLineTailEntries ? std::min<uint64_t>(small, kLineTailEntries) : kLineTailEntries;
+}
+static uint64_t line_launch_count(uint32_t k) {
+    uint64_t cnt = (uint64_t)1 << k, n_launch = 1;
+    const uint64_t tail = line_tail_entries(k);
+    if (cnt > kLineTailEntries && k >= 3) { cnt /= 8; ++n_launch; }
+    while (cnt > tail) { cnt /= 2; ++n_launch; }
+    return n_launch;
+}
 static int line_restrict_dev(gkr_ctx *ctx, const Fr *W, uint32_t k, const HFr *bs, const HFr *cs, Fr *out_canonical, cudaStream_t st,
                              bool account) {
     const Fr *cur = W;
     uint64_t cnt = (uint64_t)1 << k;
+    const uint64_t tail_entries = line_tail_entries(k);
     uint32_t j = 0;                                  // levels done == degree of the entries of cur
     int flip = 0;
     auto next_buf = [&] { return (flip++ & 1) ? ctx->lineB.as<Fr>() : ctx->lineA.as<Fr>(); };
@@ -1708,7 +1725,7 @@ static int line_restrict_dev(gkr_ctx *ctx, const Fr *W, uint32_t k, const HFr *b
         cnt /= 8;
         j = 3;
     }
-    while (cnt > kLineTailEntries) {
+    while (cnt > tail_entries) {
         Fr *nxt = next_buf();
         if (account) ctx->begin_launch(st);
         launch_line_fold(cur, nxt, cnt, j, make_const_mul(bs[j]), make_const_mul(hfr_sub(cs[j], bs[j])), st);
@@ -2045,10 +2062,7 @@ extern "C" int gkr_prove(gkr_ctx *ctx, const gkr_circuit *c, const gkr_witness *
             } else {
                 ctx->aux_pending.push_back(std::move(line_job));
                 {   // launches line_restrict_dev will make (counted here: the job itself runs on the helper thread)
-                    uint64_t cnt = N, n_launch = 1;
-                    if (cnt > kLineTailEntries && k >= 3) { cnt /= 8; ++n_launch; }
-                    while (cnt > kLineTailEntries) { cnt /= 2; ++n_launch; }
-                    ctx->stats.kernel_launches += n_launch;
+                    ctx->stats.kernel_launches += line_launch_count(k);
                 }
                 worker_used = true;
                 // the job is held back until the next phase's large kernels are queued (release_aux_jobs in
