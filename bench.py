@@ -321,6 +321,23 @@ def run_ours(args):
             cc.close()
         seeds[str(seed)]["verified"] = bool(pv.verify(circuit, pv.prove(circuit, witness), pinned_np)[0])
         parity["c3_all_seeds_verified"] = all(v["verified"] for v in seeds.values())
+    # ---- BASELINE.json config 2 (2^16 gates x 8 layers, single GPU): timed and verified beside the headline ----------
+    config2 = None
+    if world == 1 and k == 20 and args.seeds > 1:
+        cl = syn.layered_circuit(1, 16, 8)
+        iv = syn.input_values(1, 16)
+        cc = pv.circuit(cl)
+        ww = pv.witness_eval(cc, iv)
+
+        def step_c2(cc=cc, ww=ww):
+            pv.free_raw(pv.prove_raw(cc, ww))
+        n_c2 = max(4, args.steps)
+        config2 = {"workload": "synthetic layered add/mul circuit, 2^16 gates/layer x 8 layers",
+                   "ms": round(timed(step_c2, n_c2, 3) / n_c2, 4),
+                   "verified": bool(pv.verify(cc, pv.prove(cc, ww), iv)[0])}
+        parity["c2_2p16x8_verified"] = config2["verified"]
+        ww.close()
+        cc.close()
     elif rank == 0:
         parity["c3_proof_verified"] = bool(pv.verify(circuit, pv.prove(circuit, witness), pinned_np)[0])
 
@@ -673,6 +690,7 @@ def run_ours(args):
             "latency_ms_per_proof": ms_per_step, "proofs_per_s": 1e3 * world / ms_per_step,
             "parity": dict(parity, all_ok=all((v.get("ok", True) if isinstance(v, dict) else bool(v)) for v in parity.values())),
             "seeds": seeds,
+            "config2_2p16x8": config2,
             "roofline": roofline, "cpu_baseline": cpu, "sumcheck": sumcheck, "clocks": clock_info,
             "integer_roofline": int_roof, "gkr_rounds_large_tables": gkr_large,
             "kernel_classes": {n: {"launches": x["launches"], "ms": round(x["ms"], 4),
