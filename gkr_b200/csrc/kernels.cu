@@ -396,6 +396,9 @@ __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
 // thread), and after one barrier every thread adds up the staged segments of its own two rows.  Tiles are handed out
 // by an atomic counter (field sums are exact, so the order cannot change a bit of the result).
 // ------------------------------------------------------------------------------------------------
+#ifndef GKR_WTILE_MINB
+#define GKR_WTILE_MINB 2
+#endif
 constexpr int kWTile = 256;
 constexpr int kWCap = 1024;                    // staged edges per pass (2 x 32 KB of shared memory)
 constexpr uint64_t kWiringTiledMin = 1024;
@@ -405,7 +408,7 @@ __device__ __forceinline__ void cp_async_fr(Fr *dst_smem, const Fr *src) {
                  :: "r"(d), "l"(src), "r"(d + 16), "l"(reinterpret_cast<const char *>(src) + 16) : "memory");
 }
 template <bool PHASE2, bool FULL>
-__global__ void __launch_bounds__(kWTile, 2)
+__global__ void __launch_bounds__(kWTile, GKR_WTILE_MINB)
     k_wiring_round1_tiled(const uint32_t *__restrict__ rowptr, const uint32_t *__restrict__ csr_gate, const uint32_t *__restrict__ csr_other,
                           const Fr *__restrict__ X, const Fr *__restrict__ Y, const WuArg wua, const Fr *__restrict__ Wtab,
                           Fr *__restrict__ H, Fr *__restrict__ A, uint64_t n, Fr *partials, unsigned int *counter, HostSlot *slot,
@@ -534,7 +537,7 @@ void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const 
     }
     if (n >= kWiringTiledMin && wiring_tiled_enabled()) {
         const uint32_t n_tiles = (uint32_t)((n / 2 + kWTile - 1) / kWTile);
-        int grid = device_sm_count() * 2;
+        int grid = device_sm_count() * GKR_WTILE_MINB;
         if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
         if (grid > ws.max_blocks) grid = ws.max_blocks;
         const size_t smem = sizeof(Fr) * 2 * kWCap;
