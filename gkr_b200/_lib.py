@@ -75,7 +75,7 @@ EXPORTS = [
     "gkr_sumcheck_prod_sharded",
     "gkr_dev_table_upload", "gkr_dev_table_download", "gkr_dev_table_free", "gkr_dev_table_eval", "gkr_fr_binop", "gkr_eq_table",
     "gkr_mobius", "gkr_line_restrict", "gkr_ctx_stats", "gkr_ctx_profile", "gkr_bench_field_mul", "gkr_fold_f64_constants", "gkr_selftest",
-    "gkr_batch_create", "gkr_batch_load", "gkr_batch_prove", "gkr_batch_threads", "gkr_batch_lanes", "gkr_batch_simd_hash", "gkr_batch_destroy",
+    "gkr_batch_create", "gkr_batch_load", "gkr_batch_prove", "gkr_batch_threads", "gkr_batch_lanes", "gkr_batch_set_option", "gkr_batch_simd_hash", "gkr_batch_destroy",
     "gkr_prove_many", "gkr_mimc7_multi_hash_many",
 ]
 
@@ -168,6 +168,7 @@ def lib():
         L.gkr_batch_prove.argtypes = [vp, C.POINTER(C.POINTER(ProofC)), C.POINTER(C.c_double)]
         L.gkr_batch_threads.argtypes = [vp]
         L.gkr_batch_lanes.argtypes = [vp]
+        L.gkr_batch_set_option.argtypes = [vp, C.c_char_p, i32]
         L.gkr_batch_destroy.argtypes = [vp]
         L.gkr_batch_destroy.restype = None
         L.gkr_prove_many.argtypes = [i32, C.POINTER(Job), C.c_size_t, i32, i32, C.POINTER(C.POINTER(ProofC))]

@@ -33,6 +33,10 @@ class NativeBatch:
         self.n_jobs = 0
         self.seconds = 0.0
 
+    def set_option(self, name: str, value: int):
+        """gkr_ctx_set_option on every context of the batch (e.g. "lookahead_log2")"""
+        _lib.check(self._L.gkr_batch_set_option(self._b, name.encode(), int(value)))
+
     @property
     def n_threads(self) -> int:
         return self._L.gkr_batch_threads(self._b)

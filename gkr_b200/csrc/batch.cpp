@@ -489,6 +489,16 @@ extern "C" int gkr_batch_prove(gkr_batch *b, gkr_proof **proofs_out, double *sec
     return rc;
 }
 
+// gkr_ctx_set_option on every context of the batch (between two commands: the workers are idle then)
+extern "C" int gkr_batch_set_option(gkr_batch *b, const char *name, int value) {
+    if (!b || !name) return GKR_ERR_INVALID;
+    for (Worker *w : b->workers)
+        for (Fiber &f : w->fibers) {
+            const int rc = gkr_ctx_set_option(f.ctx, name, value);
+            if (rc != GKR_OK) return rc;
+        }
+    return GKR_OK;
+}
 extern "C" int gkr_batch_lanes(const gkr_batch *b) { return b ? b->lanes : 0; }
 extern "C" int gkr_batch_threads(const gkr_batch *b) { return b ? b->n_threads : 0; }
 extern "C" int gkr_batch_simd_hash(void) { return mimc7_lanes_available() ? 1 : 0; }

@@ -180,6 +180,7 @@ struct gkr_ctx {
     gkr::HostCmd *cmds_host = nullptr;     // pinned + mapped: challenge tables for pre-launched round kernels
     gkr::HostCmd *cmds_dev = nullptr;
     bool lookahead = true;                 // look-ahead rounds: next message as a polynomial in the pending challenge
+    uint32_t lookahead_log2 = 0;           // option "lookahead_log2": largest table (log2 entries) that uses them; 0 = default
     int f64_folds = gkr::default_f64_folds();   // option "f64_folds": folds per pair on the FP64 pipe in streaming rounds
     bool prelaunch = true;                 // pre-launch the small-table rounds of a phase (option "prelaunch")
     bool test_drop_cmd = false;            // test hook, see gkr_ctx_set_option

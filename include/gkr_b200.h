@@ -161,6 +161,7 @@ typedef struct {
 int gkr_batch_create(int device, int n_threads, int lanes, gkr_batch **out);
 int gkr_batch_load(gkr_batch *b, const gkr_job *jobs, size_t n_jobs);
 int gkr_batch_prove(gkr_batch *b, gkr_proof **proofs_out, double *seconds_out);
+int gkr_batch_set_option(gkr_batch *b, const char *name, int value);   /* gkr_ctx_set_option on every context of the batch */
 int gkr_batch_threads(const gkr_batch *b);
 int gkr_batch_lanes(const gkr_batch *b);
 int gkr_batch_simd_hash(void);        /* 1 when this CPU runs the AVX-512 IFMA lane hash */

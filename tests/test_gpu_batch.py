@@ -113,3 +113,17 @@ def test_batch_rejects_bad_jobs():
     finally:
         L.gkr_batch_destroy(b)
     assert L.gkr_batch_create(0, 1, 99, C.byref(b)) != 0
+
+
+def test_batch_option_lookahead_log2():
+    """look-ahead rounds only for tables of at most 2^6 entries (the setting for many large proofs in flight, where the
+    device is the limit): the larger levels run as direct rounds, the proofs do not change"""
+    from gkr_b200.batch import NativeBatch
+    jobs, wants = _jobs(777, [[3, 4, 3], [11, 12, 11], [9, 10], [13, 13]], 10)
+    with NativeBatch(2, 4) as nb:
+        nb.set_option("lookahead_log2", 6)
+        nb.load(jobs)
+        for a, b in zip(wants, nb.prove()):
+            assert_same_dense(a, b)
+        with pytest.raises(Exception):
+            nb.set_option("no_such_option", 1)
