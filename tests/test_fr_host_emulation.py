@@ -18,7 +18,8 @@ def _lib():
     src = os.path.join(HERE, "csrc", "fr_host_check.cpp")
     hdr = os.path.join(HERE, "..", "gkr_b200", "csrc", "fr.cuh")
     hdr2 = os.path.join(HERE, "..", "gkr_b200", "csrc", "fr_f64.cuh")
-    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)) > os.path.getmtime(so):
+    hdr3 = os.path.join(HERE, "..", "gkr_b200", "csrc", "fr_wide3.cuh")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2), os.path.getmtime(hdr3)) > os.path.getmtime(so):
         subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", src, "-o", so])
     return C.CDLL(so)
 
@@ -92,3 +93,54 @@ def test_mul_by_constant_matches_bigint():
         xm = x * R % P
         want_m = sum(((xm >> (32 * j)) & 0xFFFFFFFF) * (P - 1) for j in range(8)) * pow(2, -64, P) % P
         assert got == want_m * pow(R, -1, P) % P
+
+
+def _u256_bytes(vals):
+    return np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in vals), np.uint8).reshape(-1, 32).copy()
+
+
+def test_exact_8x8_products_match_bigint():
+    """w3_mul8 (fr_wide3.cuh): schoolbook and one-level Karatsuba, operands anywhere below 2^256 (the evaluation
+    operands are not reduced below p), including every carry pattern of the half sums"""
+    lib = _lib()
+    rng = random.Random(11)
+    M = (1 << 256) - 1
+    F = (1 << 128) - 1
+    edge = [0, 1, M, F, F << 128, (F << 128) | 1, 1 << 128, (1 << 128) - 1, (1 << 255), 3 * P - 2, 2 * P - 1, P - 1,
+            ((1 << 128) - 1) | (1 << 128), (0xFFFFFFFF << 96) | (1 << 224)]
+    a = [x for x in edge for _ in edge] + [rng.randrange(1 << 256) for _ in range(4000)]
+    b = [y for _ in edge for y in edge] + [rng.randrange(1 << 256) for _ in range(4000)]
+    A, B = _u256_bytes(a), _u256_bytes(b)
+    for kara in (0, 1):
+        out = np.zeros((len(a), 64), np.uint8)
+        assert lib.frh_mul8(kara, A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                            C.c_ulong(len(a))) == 0
+        got = [int.from_bytes(out[i].tobytes(), "little") for i in range(len(a))]
+        assert got == [x * y for x, y in zip(a, b)]
+
+
+def test_unreduced_triple_product_sums_match_bigint():
+    """the four evaluation sums of a degree-3 round through exact 768-bit products and one reduction (fr_wide3.cuh),
+    every combination of schoolbook / Karatsuba stages and the derived X = -1 product"""
+    lib = _lib()
+    rng = random.Random(12)
+    for n in (1, 3, 50, 600):
+        lo = [[rng.randrange(P) for _ in range(3)] for _ in range(n)]
+        hi = [[rng.randrange(P) for _ in range(3)] for _ in range(n)]
+        if n == 3:          # extremes: hi - lo + p and 2 lo - hi + 2p at both ends of their ranges
+            lo = [[0, 0, 0], [P - 1, P - 1, P - 1], [P - 1, 0, P - 1]]
+            hi = [[P - 1, P - 1, P - 1], [0, 0, 0], [0, P - 1, 1]]
+        if n == 50:         # the accumulator's upper words fill up fastest
+            lo = [[P - 1] * 3] * n
+            hi = [[0] * 3] * n
+        L = orc.to_bytes([x for row in lo for x in row])
+        H = orc.to_bytes([x for row in hi for x in row])
+        want = [sum(l[0] * l[1] * l[2] for l in lo) % P,
+                sum((2 * l[0] - h[0]) * (2 * l[1] - h[1]) * (2 * l[2] - h[2]) for l, h in zip(lo, hi)) % P,
+                sum((h[0] - l[0]) * (h[1] - l[1]) * (h[2] - l[2]) for l, h in zip(lo, hi)) % P,
+                sum(h[0] * h[1] * h[2] for h in hi) % P]
+        for flags in range(8):
+            out = np.zeros((4, 32), np.uint8)
+            assert lib.frh_eval3(flags, L.ctypes.data_as(C.c_void_p), H.ctypes.data_as(C.c_void_p),
+                                 out.ctypes.data_as(C.c_void_p), C.c_ulong(n)) == 0
+            assert orc.from_bytes(out) == want, (n, flags)

@@ -41,6 +41,30 @@ def test_golden(pv, case):
     assert ok, why
 
 
+def _refpy_cases():
+    from tests import test_golden_refpy as rp
+    return rp.CASES, rp.IDS
+
+
+@pytest.mark.parametrize("case", _refpy_cases()[0], ids=_refpy_cases()[1])
+def test_reference_python_prover_vectors(pv, case):
+    """the CUDA path against proofs made by the reference's own Python prover (tests/golden/refpy_vectors.json)"""
+    from tests import test_golden_refpy as rp
+    proof = _gpu_prove(pv, gu.case_layers(case), gu.I(case["input"]))
+    rp.assert_matches_reference_python(case, proof.sumcheck_proofs, proof.sumcheck_r, proof.q, proof.z, proof.r, proof.depth,
+                                       proof.k, {i: c for i, c in enumerate(proof.d_coef) if c},
+                                       {i: c for i, c in enumerate(proof.input_coef) if c})
+    # and through the drop-in on the reference's own types (term lists in, term lists out)
+    import gkr_b200 as g
+    layers = gu.case_layers(case)
+    ref_circ = l0.build_reference_circuit([(k_out, gates) for k_out, _, gates in layers], layers[-1][1])
+    ref_inp, _ = l0.calculate_input([(k_out, gates) for k_out, _, gates in layers], gu.I(case["input"]))
+    got = g.prove(g.GKRCircuit([g.Layer(L.k, L.add, L.mult, L.wire) for L in ref_circ.layer], ref_circ.input_k),
+                  g.Input(ref_inp.w, ref_inp.d), prover=pv)
+    rp.assert_matches_reference_python(case, got.sumcheck_proofs, got.sumcheck_r, got.q, got.z, got.r, got.depth, got.k,
+                                       gu.terms_map(got.d), gu.terms_map(got.input_func))
+
+
 @pytest.mark.parametrize("ks", [[1, 2, 2], [2, 3, 2], [2, 2, 3, 1], [3, 4, 3], [0, 2, 2], [1, 1, 1], [4, 5, 4, 5]])
 @pytest.mark.parametrize("mode", ["mixed", "add", "mult"])
 def test_against_literal_reference_types(pv, ks, mode):

@@ -31,6 +31,22 @@ def test_golden(pv, idx):
         assert verifier.mle_eval(gu.I(t), chal) == f
 
 
+def _refpy():
+    from tests import test_golden_refpy as rp
+    return rp
+
+
+@pytest.mark.parametrize("idx", range(len(_refpy().REFPY["sumcheck_prod"])))
+def test_reference_python_prover_vectors(pv, idx):
+    """the CUDA path against python/sumcheck.py `prove_sumcheck` of the reference (tests/golden/refpy_vectors.json)"""
+    rp = _refpy()
+    g = rp.REFPY["sumcheck_prod"][idx]
+    msgs, chal, fin = pv.sumcheck_prod([ints_to_fr(gu.I(t)) for t in g["tables"]], g["n_vars"])
+    assert [rp.strip(m) for m in msgs] == [rp.strip(m) for m in gu.I(g["msgs"])] and chal == gu.I(g["r"])
+    for t, f in zip(g["tables"], fin):
+        assert verifier.mle_eval(gu.I(t), chal) == f
+
+
 @pytest.mark.parametrize("v", [2, 3, 5, 9, 10, 13, 16])
 def test_against_dense_oracle(pv, v):
     rng = random.Random(v)
