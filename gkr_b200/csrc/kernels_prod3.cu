@@ -1,7 +1,18 @@
 // Degree-3 product sumcheck rounds (BASELINE.json config 4) and the register-resident multiplier benchmark.
 #include "kernels_common.cuh"
+#include "fr_wide3.cuh"
 
 namespace gkr {
+
+#ifndef GKR_P3_EXACT_DEFAULT
+#define GKR_P3_EXACT_DEFAULT 0        // 0: k_prod3_round; 1 + KA: k_prod3_round_x (see p3_exact)
+#endif
+#ifndef GKR_P3X_THREADS_DEFAULT
+#define GKR_P3X_THREADS_DEFAULT 512
+#endif
+#ifndef GKR_P3X_ALL_VARIANTS
+#define GKR_P3X_ALL_VARIANTS 1        // build the schoolbook / half-Karatsuba forms too (experiments)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // product-of-three sumcheck round, degree 3 (generic prove_sumcheck, rust/src/gkr/sumcheck.rs:158-214).
@@ -152,6 +163,137 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1)
     grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, xa);
 }
 
+// ------------------------------------------------------------------------------------------------
+// The streaming rounds with exact triple products (fr_wide3.cuh): no Montgomery reduction inside the loop at all.
+// A term A_t B_t C_t of the evaluation point t is the exact 768-bit integer (P = A_t B_t: 512 bits, then P_lo C_t and
+// P_hi C_t: two 8x8-limb products), added into two 544-bit accumulators per point (low and high half of P) that live in
+// shared memory, word-interleaved across the CTA; the thread's 800-bit sums are reduced once after the loop.
+// KA bit 0 / bit 1: the first- / second-stage products as one level of Karatsuba (48 wide multiplies instead of 64).
+// Wide multiplies per pair: 6 x 82 (folds) + 3 x 144 = 924 with KA = 3 (1095 in k_prod3_round); the first round
+// (FULL, three first-stage products serve four points) 3 x 48 + 4 x 96 = 528 (667).  Same messages bit for bit.
+// ------------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ __forceinline__ void w3_acc17(uint32_t *acc_base, const uint32_t *r16) {
+    FrWide w;
+#pragma unroll
+    for (int i = 0; i < 17; ++i) w.l[i] = acc_base[i * THREADS];
+    uint32_t x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = r16[i];
+    wide_add16(w, x);
+#pragma unroll
+    for (int i = 0; i < 17; ++i) acc_base[i * THREADS] = w.l[i];
+}
+// acc(point) += P * c :  low half of P into the point's first accumulator, high half into its second
+template <int THREADS, bool KARA>
+__device__ __forceinline__ void w3_mac_smem(uint32_t *acc_point, const uint32_t *P, const uint32_t *c) {
+    W3HalfSum hc{};
+    if (KARA) hc = w3_half_sum(c);
+    uint32_t r[16];
+    w3_mul8<KARA>(r, P, c, hc);
+    w3_acc17<THREADS>(acc_point, r);
+    w3_mul8<KARA>(r, P + 8, c, hc);
+    w3_acc17<THREADS>(acc_point + 17 * THREADS, r);
+}
+template <bool KARA>
+__device__ __forceinline__ void w3_mul8_auto(uint32_t *r, const uint32_t *a, const uint32_t *b) {
+    W3HalfSum hb{};
+    if (KARA) hb = w3_half_sum(b);
+    w3_mul8<KARA>(r, a, b, hb);
+}
+
+template <bool FOLD, bool FULL, int THREADS, int KA>
+__global__ void __launch_bounds__(THREADS, 1)
+    k_prod3_round_x(const Fr *__restrict__ Ain, const Fr *__restrict__ Bin, const Fr *__restrict__ Cin, Fr *__restrict__ Aout,
+                    Fr *__restrict__ Bout, Fr *__restrict__ Cout, const __grid_constant__ FrConstMul r, uint64_t q, Fr *partials,
+                    unsigned int *counter, HostSlot *slot, uint32_t seq, XchgArg xa) {
+    constexpr int K = FULL ? 4 : 3;
+    constexpr bool K1 = (KA & 1) != 0, K2 = (KA & 2) != 0;
+    extern __shared__ uint32_t wsm[];                     // [K][2][17][THREADS]
+#pragma unroll
+    for (int w = 0; w < K * 34; ++w) wsm[w * THREADS + threadIdx.x] = 0;
+    uint32_t *const my = wsm + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, i_first = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t i = i_first; i < q; i += stride) {
+        if (!FOLD) {
+            const uint64_t nx = i + stride;
+            if (nx < q) {
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    prefetch_l2(Ain + nx + t * q);
+                    prefetch_l2(Bin + nx + t * q);
+                    prefetch_l2(Cin + nx + t * q);
+                }
+            }
+        }
+        uint32_t P0[16], Pm[16], Pinf[16], P1[FULL ? 16 : 1];
+        {
+            Fr a0, a1, b0, b1;
+            if (FOLD) {
+                a0 = fold2(ld_fr(Ain + i), ld_fr(Ain + i + 2 * q), r);
+                a1 = fold2(ld_fr(Ain + i + q), ld_fr(Ain + i + 3 * q), r);
+                st_fr(Aout + i, a0);
+                st_fr(Aout + i + q, a1);
+                b0 = fold2(ld_fr(Bin + i), ld_fr(Bin + i + 2 * q), r);
+                b1 = fold2(ld_fr(Bin + i + q), ld_fr(Bin + i + 3 * q), r);
+                st_fr(Bout + i, b0);
+                st_fr(Bout + i + q, b1);
+            } else {
+                a0 = ld_fr(Ain + i); a1 = ld_fr(Ain + i + q);
+                b0 = ld_fr(Bin + i); b1 = ld_fr(Bin + i + q);
+            }
+            w3_mul8_auto<K1>(P0, a0.l, b0.l);
+            uint32_t da[8], db[8];
+            w3_diff(da, a1, a0);
+            w3_diff(db, b1, b0);
+            w3_mul8_auto<K1>(Pinf, da, db);
+            if (FULL) {
+                w3_mul8_auto<K1>(P1, a1.l, b1.l);
+                w3_derive_minus1(Pm, P0, P1, Pinf);
+            } else {
+                uint32_t am[8], bm[8];
+                w3_minus1(am, a0, da);
+                w3_minus1(bm, b0, db);
+                w3_mul8_auto<K1>(Pm, am, bm);
+            }
+        }
+        Fr c0, c1;
+        if (FOLD) {
+            c0 = fold2(ld_fr(Cin + i), ld_fr(Cin + i + 2 * q), r);
+            c1 = fold2(ld_fr(Cin + i + q), ld_fr(Cin + i + 3 * q), r);
+            st_fr(Cout + i, c0);
+            st_fr(Cout + i + q, c1);
+        } else {
+            c0 = ld_fr(Cin + i); c1 = ld_fr(Cin + i + q);
+        }
+        if (FULL) w3_mac_smem<THREADS, K2>(my + 3 * 34 * THREADS, P1, c1.l);
+        uint32_t dc[8];
+        w3_diff(dc, c1, c0);
+        w3_mac_smem<THREADS, K2>(my + 0 * 34 * THREADS, P0, c0.l);
+        w3_mac_smem<THREADS, K2>(my + 2 * 34 * THREADS, Pinf, dc);
+        uint32_t cm[8];
+        w3_minus1(cm, c0, dc);
+        w3_mac_smem<THREADS, K2>(my + 1 * 34 * THREADS, Pm, cm);
+    }
+    Fr acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        // total = lo + hi * 2^256
+        FrWide3 w;
+#pragma unroll
+        for (int l = 0; l < 17; ++l) w.l[l] = my[(j * 34 + l) * THREADS];
+#pragma unroll
+        for (int l = 17; l < kW3Limbs; ++l) w.l[l] = 0;
+        uint32_t hi[17];
+#pragma unroll
+        for (int l = 0; l < 17; ++l) hi[l] = my[(j * 34 + 17 + l) * THREADS];
+        w3_add17(w.l + 8, hi);
+        acc[j] = wide3_reduce(w);
+    }
+    __syncthreads();
+    grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, xa);
+}
+
 // Variant selection for the streaming (lazy) rounds.  Default = the measured best (profiles/r02_prod3_variants.md: 2^28
 // sumcheck 36.8 ms with two 256-thread CTAs per SM and register accumulators, 34.0 ms with one 512-thread CTA per SM and
 // shared-memory accumulators; 384 threads 34.6 ms, 448 threads 38.8 ms).  GKR_P3_THREADS=256 selects the old form.
@@ -182,6 +324,51 @@ static void launch_p3_lazy(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *
     const int grid = (int)(want < (uint64_t)cap ? want : (uint64_t)cap);
     kern<<<grid, THREADS, smem, s>>>(A, B, C, Aout, Bout, Cout, r, rf, pairs, ws.partials, ws.counter, slot, seq, xa);
 }
+// Exact-product form of the streaming rounds (k_prod3_round_x).  GKR_P3_EXACT: 0 = off, 1 + KA otherwise (KA bit 0 /
+// bit 1 = Karatsuba in the first / second stage); GKR_P3X_THREADS: CTA size of the fused rounds (the first round's four
+// accumulator pairs only fit 384 threads).
+struct P3Exact { int on; int ka; int threads; };
+static P3Exact p3_exact() {
+    static const P3Exact v = [] {
+        P3Exact x{GKR_P3_EXACT_DEFAULT > 0, GKR_P3_EXACT_DEFAULT > 0 ? GKR_P3_EXACT_DEFAULT - 1 : 0, GKR_P3X_THREADS_DEFAULT};
+        if (const char *e = getenv("GKR_P3_EXACT")) {
+            const int m = atoi(e);
+            x.on = m >= 1 && m <= 4;
+            x.ka = x.on ? m - 1 : 0;
+        }
+        if (const char *t = getenv("GKR_P3X_THREADS")) {
+            const int n = atoi(t);
+            if (n == 384 || n == 512) x.threads = n;
+        }
+        return x;
+    }();
+    return v;
+}
+template <bool FOLD, bool FULL, int THREADS, int KA>
+static void launch_p3_exact(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const FrConstMul &r, uint64_t pairs,
+                            const ReduceWs &ws, HostSlot *slot, uint32_t seq, XchgArg xa, cudaStream_t s) {
+    constexpr int K = FULL ? 4 : 3;
+    const size_t smem = (size_t)K * 34 * THREADS * sizeof(uint32_t);
+    auto kern = k_prod3_round_x<FOLD, FULL, THREADS, KA>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      // per device, idempotent
+    const uint64_t want = (pairs + THREADS - 1) / THREADS;
+    const int cap = device_sm_count();
+    const int grid = (int)(want < (uint64_t)cap ? want : (uint64_t)cap);
+    kern<<<grid, THREADS, smem, s>>>(A, B, C, Aout, Bout, Cout, r, pairs, ws.partials, ws.counter, slot, seq, xa);
+}
+template <bool FOLD, bool FULL, int THREADS>
+static void launch_p3_exact_ka(int ka, const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const FrConstMul &r,
+                               uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq, XchgArg xa, cudaStream_t s) {
+#if GKR_P3X_ALL_VARIANTS
+    switch (ka) {
+        case 0: launch_p3_exact<FOLD, FULL, THREADS, 0>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, xa, s); return;
+        case 1: launch_p3_exact<FOLD, FULL, THREADS, 1>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, xa, s); return;
+        case 2: launch_p3_exact<FOLD, FULL, THREADS, 2>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, xa, s); return;
+        default: break;
+    }
+#endif
+    launch_p3_exact<FOLD, FULL, THREADS, 3>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, xa, s);
+}
 template <bool FOLD, bool FULL>
 static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const FrConstMul &r,
                                  const FrFoldF64 *rf, int nf, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq,
@@ -191,6 +378,16 @@ static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout
         k_prod3_round<FOLD, FULL, false, 0, 256, false><<<round_grid(pairs, ws), kThreads, 0, s>>>(
             A, B, C, Aout, Bout, Cout, r, no_rf, pairs, ws.partials, ws.counter, slot, seq, xa);
         return;
+    }
+    if constexpr (FOLD != FULL) {            // the two forms a streaming sumcheck is made of: first round, fused rounds
+        const P3Exact ex = p3_exact();
+        if (ex.on && !(rf && nf)) {
+            if (FULL || ex.threads == 384)
+                launch_p3_exact_ka<FOLD, FULL, 384>(ex.ka, A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, xa, s);
+            else
+                launch_p3_exact_ka<FOLD, FULL, 512>(ex.ka, A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, xa, s);
+            return;
+        }
     }
     const P3Variant v = p3_variant();
 #define GKR_P3(NF, T, SA) launch_p3_lazy<FOLD, FULL, NF, T, SA>(A, B, C, Aout, Bout, Cout, r, rf ? *rf : no_rf, pairs, ws, slot, seq, xa, s)

@@ -14,7 +14,9 @@
  *   MSB-first wiring / gate indexing ......... rust/src/convert.rs:704-777
  *   forward evaluation, MLE (Moebius) ........ rust/src/convert.rs:787-849, rust/src/gkr/poly.rs:502-536
  *   generic product sumcheck ................. rust/src/gkr/sumcheck.rs:158-214
- * PARITY UNPINNED: the reference holds no golden vectors and cannot be built here (no Rust).
+ * PARITY: equal to the literal restatement (oracle/l0_reference.py) and, through tests/golden/refpy_vectors.json, to the
+ * reference's own Python prover run here (tests/test_golden_refpy.py).  UNPINNED against the Rust binary: the reference
+ * holds no golden vectors and cannot be built here (no Rust).
  */
 #include <stdlib.h>
 #ifdef _OPENMP

@@ -9,7 +9,12 @@ A polynomial is a list of terms; a term is [coeff, e_1 .. e_v] with all entries 
 (the reference stores exponents and chi tags as field elements too, poly.rs:34-37,168).
 The transcript hash is the external `mimc-rs` crate (unpinned, not under /root/reference):
 MiMC7-91, restated from its published algorithm and pinned by the known answers of SURVEY.md A.3.
-PARITY UNPINNED: the reference has no golden vectors and cannot be built here (no Rust toolchain).
+PARITY: pinned against the reference's own PYTHON prover (/root/reference/python/gkr.py + sumcheck.py, run unmodified
+over a stand-in for the absent `ethsnarks`; tests/golden/make_refpy_vectors.py -> tests/golden/refpy_vectors.json,
+tests/test_golden_refpy.py): messages, challenges, q, z, r*, D, input polynomial and f(r) agree on 21 circuits, the
+generic product sumcheck on 4 table sets.  Still UNPINNED against the Rust binary (no Rust toolchain, no golden
+vectors in the reference): what only the Rust code defines -- static message lengths, term-list emission -- rests on
+this literal restatement.
 """
 from __future__ import annotations
 

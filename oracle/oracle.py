@@ -3,7 +3,7 @@ restatement "L1", see oracle/gkr_dense.c).  Only tests/, __graft_entry__.smoke()
 cpu_baseline / --impl reference legs may import this module; the product package gkr_b200 never does.
 
 Field elements are Python ints here and 32-byte little-endian canonical values on the wire
-(`Fr::to_repr()`, rust/src/gkr/sumcheck.rs:14-21).  PARITY UNPINNED: see oracle/gkr_dense.c header.
+(`Fr::to_repr()`, rust/src/gkr/sumcheck.rs:14-21).  PARITY: pinned against the reference's Python prover, unpinned against the Rust binary; see oracle/gkr_dense.c header.
 """
 from __future__ import annotations
 

@@ -1,7 +1,7 @@
 """Generates tests/golden/gkr_l0_vectors.json -- golden input/output vectors for the prover hot path.
 
-The reference itself cannot run here (no Rust toolchain; the Python prototype needs `ethsnarks` and uses
-another MiMC variant and a random z_0), and it holds no golden vectors of its own, so these vectors come
+The Rust reference cannot run here (no toolchain) and holds no golden vectors of its own (vectors made by the reference's
+Python prototype are generated separately: tests/golden/make_refpy_vectors.py), so these vectors come
 from the LITERAL restatement of the reference algorithm (oracle/l0_reference.py, which follows
 rust/src/gkr/{poly,sumcheck,prover}.rs line by line) => "parity unpinned" against the Rust binary, pinned
 against the restatement.  Numbers are decimal strings of canonical values (rust/src/file_utils.rs:20-28).
