@@ -1,9 +1,9 @@
 // Degree-3 product sumcheck rounds (BASELINE.json config 4) and the register-resident multiplier benchmark.
 #include "kernels_common.cuh"
-#include "fr_wide3.cuh"
 
-namespace gkr {
-
+#ifndef GKR_P3X
+#define GKR_P3X 0                     // 1: also build the exact-product form of the streaming rounds (k_prod3_round_x); measured
+#endif                                // slower in every variant (profiles/r02_prod3_exact_variants.md), so the product build omits it
 #ifndef GKR_P3_EXACT_DEFAULT
 #define GKR_P3_EXACT_DEFAULT 0        // 0: k_prod3_round; 1 + KA: k_prod3_round_x (see p3_exact)
 #endif
@@ -13,6 +13,12 @@ namespace gkr {
 #ifndef GKR_P3X_ALL_VARIANTS
 #define GKR_P3X_ALL_VARIANTS 1        // build the schoolbook / half-Karatsuba forms too (experiments)
 #endif
+#if GKR_P3X
+#include "fr_wide3.cuh"
+#endif
+
+namespace gkr {
+
 
 // ------------------------------------------------------------------------------------------------
 // product-of-three sumcheck round, degree 3 (generic prove_sumcheck, rust/src/gkr/sumcheck.rs:158-214).
@@ -163,6 +169,7 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1)
     grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, xa);
 }
 
+#if GKR_P3X
 // ------------------------------------------------------------------------------------------------
 // The streaming rounds with exact triple products (fr_wide3.cuh): no Montgomery reduction inside the loop at all.
 // A term A_t B_t C_t of the evaluation point t is the exact 768-bit integer (P = A_t B_t: 512 bits, then P_lo C_t and
@@ -294,6 +301,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, xa);
 }
 
+#endif  // GKR_P3X
+
 // Variant selection for the streaming (lazy) rounds.  Default = the measured best (profiles/r02_prod3_variants.md: 2^28
 // sumcheck 36.8 ms with two 256-thread CTAs per SM and register accumulators, 34.0 ms with one 512-thread CTA per SM and
 // shared-memory accumulators; 384 threads 34.6 ms, 448 threads 38.8 ms).  GKR_P3_THREADS=256 selects the old form.
@@ -324,6 +333,7 @@ static void launch_p3_lazy(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *
     const int grid = (int)(want < (uint64_t)cap ? want : (uint64_t)cap);
     kern<<<grid, THREADS, smem, s>>>(A, B, C, Aout, Bout, Cout, r, rf, pairs, ws.partials, ws.counter, slot, seq, xa);
 }
+#if GKR_P3X
 // Exact-product form of the streaming rounds (k_prod3_round_x).  GKR_P3_EXACT: 0 = off, 1 + KA otherwise (KA bit 0 /
 // bit 1 = Karatsuba in the first / second stage); GKR_P3X_THREADS: CTA size of the fused rounds (the first round's four
 // accumulator pairs only fit 384 threads).
@@ -369,6 +379,7 @@ static void launch_p3_exact_ka(int ka, const Fr *A, const Fr *B, const Fr *C, Fr
 #endif
     launch_p3_exact<FOLD, FULL, THREADS, 3>(A, B, C, Aout, Bout, Cout, r, pairs, ws, slot, seq, xa, s);
 }
+#endif  // GKR_P3X
 template <bool FOLD, bool FULL>
 static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout, Fr *Bout, Fr *Cout, const FrConstMul &r,
                                  const FrFoldF64 *rf, int nf, uint64_t pairs, const ReduceWs &ws, HostSlot *slot, uint32_t seq,
@@ -379,6 +390,7 @@ static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout
             A, B, C, Aout, Bout, Cout, r, no_rf, pairs, ws.partials, ws.counter, slot, seq, xa);
         return;
     }
+#if GKR_P3X
     if constexpr (FOLD != FULL) {            // the two forms a streaming sumcheck is made of: first round, fused rounds
         const P3Exact ex = p3_exact();
         if (ex.on && !(rf && nf)) {
@@ -389,6 +401,7 @@ static void launch_prod3_round_t(const Fr *A, const Fr *B, const Fr *C, Fr *Aout
             return;
         }
     }
+#endif
     const P3Variant v = p3_variant();
 #define GKR_P3(NF, T, SA) launch_p3_lazy<FOLD, FULL, NF, T, SA>(A, B, C, Aout, Bout, Cout, r, rf ? *rf : no_rf, pairs, ws, slot, seq, xa, s)
 #define GKR_P3_TS(NF)                                            \

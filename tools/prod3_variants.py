@@ -43,10 +43,18 @@ def child(v):
 def main():
     v = int(sys.argv[1]) if len(sys.argv) > 1 else 26
     points = []
-    for threads in (256, 384, 448, 512):
-        for sacc in (0, 1):
-            for nf in (0,):
-                points.append({"GKR_P3_THREADS": str(threads), "GKR_P3_SACC": str(sacc), "GKR_F64_FOLDS": str(nf)})
+    if len(sys.argv) > 2 and sys.argv[2] == "exact":
+        # the exact-product evaluation (k_prod3_round_x, fr_wide3.cuh) next to the default kernel: GKR_P3_EXACT = 1 + KA
+        # (KA bit 0 / 1 = Karatsuba in the first / second stage), CTA size of the fused rounds
+        points.append({})
+        for threads in (512, 384):
+            for mode in (1, 2, 3, 4):
+                points.append({"GKR_P3_EXACT": str(mode), "GKR_P3X_THREADS": str(threads)})
+    else:
+        for threads in (256, 384, 448, 512):
+            for sacc in (0, 1):
+                for nf in (0,):
+                    points.append({"GKR_P3_THREADS": str(threads), "GKR_P3_SACC": str(sacc), "GKR_F64_FOLDS": str(nf)})
     base = None
     for env in points:
         e = dict(os.environ, **env)
