@@ -84,7 +84,11 @@ inline HFr hfr_sub(const HFr &a, const HFr &b) {
 inline HFr hfr_neg(const HFr &a) { return hfr_sub(hfr_zero(), a); }
 
 // Montgomery product, "no-carry" interleaved CIOS: the two carry chains (a*b_i and m*p) advance together
-// and no fifth limb is needed because the top limb of p is below 2^63 - 1.  Inputs < p, output < p.
+// and no fifth limb is needed because the top limb of p is below 2^62.  Output < p.
+// The row arithmetic itself is exact for any a below 2^255: after every row the accumulator is below a + p, the two
+// carry-outs of a row are below a_3 + 1 <= 2^63 and p_3 + 1 < 2^62, so their sum fits a limb, and the value before the
+// final subtraction is below a b / R + p (the transcript chain in transcript.cpp uses this with operands up to 2.32 p).
+// With both inputs below p that is below 1.19 p, which the one conditional subtraction here brings below p.
 namespace hf {
 inline void mac(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t &hi, uint64_t &lo) {
     const u128 r = (u128)a * b + c + d;
@@ -112,7 +116,90 @@ inline HFr hfr_mul(const HFr &a, const HFr &b) {
     if (hf::geq_p(r.l)) hf::sub_p(r.l);
     return r;
 }
-inline HFr hfr_sqr(const HFr &a) { return hfr_mul(a, a); }
+// Montgomery square.  The transcript is a serial chain of x^7 = (x^2)^2 * (x^2 * x): half of its products are squares,
+// and on the host the chain is bound by the 64x64 multiplier port (two independent chains interleaved take twice the
+// time of one).  A square needs the six cross products once (doubled by a shift) plus four squares: 10 multiplies
+// instead of 16 before the 20 of the reduction -- 30 instead of 40 per square, 140 instead of 160 per MiMC round.
+// Same value as hfr_mul(a, a), bit for bit (tests/test_host_logic.py::test_host_square_equals_product).
+#ifndef GKR_HOST_SQR
+#define GKR_HOST_SQR 0           // measured slower on the GPU box (transcript.cpp), faster on the build container
+#endif
+inline HFr hfr_sqr(const HFr &a) {
+#if !GKR_HOST_SQR
+    return hfr_mul(a, a);
+#else
+    using hf::u128;
+    const uint64_t a0 = a.l[0], a1 = a.l[1], a2 = a.l[2], a3 = a.l[3];
+    // cross products a_i a_j (i < j) summed by column: x[1..6], below 2^447
+    uint64_t x1, x2, x3, x4, x5, x6;
+    {
+        u128 t = (u128)a0 * a1;
+        x1 = (uint64_t)t;
+        t = (u128)a0 * a2 + (uint64_t)(t >> 64);
+        x2 = (uint64_t)t;
+        t = (u128)a0 * a3 + (uint64_t)(t >> 64);
+        x3 = (uint64_t)t;
+        x4 = (uint64_t)(t >> 64);
+        t = (u128)a1 * a2 + x3;
+        x3 = (uint64_t)t;
+        t = (u128)a1 * a3 + x4 + (uint64_t)(t >> 64);
+        x4 = (uint64_t)t;
+        x5 = (uint64_t)(t >> 64);
+        t = (u128)a2 * a3 + x5;
+        x5 = (uint64_t)t;
+        x6 = (uint64_t)(t >> 64);
+    }
+    // t = 2 x + sum a_i^2 2^(128 i): eight limbs, below p^2 < 2^508
+    uint64_t t0, t1, t2, t3, t4, t5, t6, t7;
+    {
+        const uint64_t d1 = x1 << 1, d2 = (x2 << 1) | (x1 >> 63), d3 = (x3 << 1) | (x2 >> 63), d4 = (x4 << 1) | (x3 >> 63),
+                       d5 = (x5 << 1) | (x4 >> 63), d6 = (x6 << 1) | (x5 >> 63), d7 = x6 >> 63;
+        u128 s = (u128)a0 * a0;
+        t0 = (uint64_t)s;
+        u128 c = (u128)d1 + (uint64_t)(s >> 64);
+        t1 = (uint64_t)c;
+        s = (u128)a1 * a1;
+        c = (u128)d2 + (uint64_t)s + (uint64_t)(c >> 64);
+        t2 = (uint64_t)c;
+        c = (u128)d3 + (uint64_t)(s >> 64) + (uint64_t)(c >> 64);
+        t3 = (uint64_t)c;
+        s = (u128)a2 * a2;
+        c = (u128)d4 + (uint64_t)s + (uint64_t)(c >> 64);
+        t4 = (uint64_t)c;
+        c = (u128)d5 + (uint64_t)(s >> 64) + (uint64_t)(c >> 64);
+        t5 = (uint64_t)c;
+        s = (u128)a3 * a3;
+        c = (u128)d6 + (uint64_t)s + (uint64_t)(c >> 64);
+        t6 = (uint64_t)c;
+        t7 = d7 + (uint64_t)(s >> 64) + (uint64_t)(c >> 64);
+    }
+    // Montgomery reduction, one limb per step: t += m p 2^(64 i) with m = t_i * (-p^-1); t + sum < 2^508 + 2^256 p < 2^512
+#define GKR_HSQR_STEP(T0, T1, T2, T3, T4, CIN, COUT)                        \
+    {                                                                       \
+        const uint64_t m = T0 * hf::NINV;                                   \
+        u128 r = (u128)m * hf::P[0] + T0;                                   \
+        r = (u128)m * hf::P[1] + T1 + (uint64_t)(r >> 64);                  \
+        T1 = (uint64_t)r;                                                   \
+        r = (u128)m * hf::P[2] + T2 + (uint64_t)(r >> 64);                  \
+        T2 = (uint64_t)r;                                                   \
+        r = (u128)m * hf::P[3] + T3 + (uint64_t)(r >> 64);                  \
+        T3 = (uint64_t)r;                                                   \
+        r = (u128)T4 + (uint64_t)(r >> 64) + CIN;                           \
+        T4 = (uint64_t)r;                                                   \
+        COUT = (uint64_t)(r >> 64);                                         \
+    }
+    uint64_t c0, c1, c2;
+    [[maybe_unused]] uint64_t c3;      // the total stays below 2^512: no carry out of the last step
+    GKR_HSQR_STEP(t0, t1, t2, t3, t4, 0, c0)
+    GKR_HSQR_STEP(t1, t2, t3, t4, t5, c0, c1)
+    GKR_HSQR_STEP(t2, t3, t4, t5, t6, c1, c2)
+    GKR_HSQR_STEP(t3, t4, t5, t6, t7, c2, c3)
+#undef GKR_HSQR_STEP
+    HFr r{{t4, t5, t6, t7}};
+    if (hf::geq_p(r.l)) hf::sub_p(r.l);
+    return r;
+#endif
+}
 
 
 // canonical 32-byte little-endian value <-> Montgomery.  from_canonical returns false if value >= p.

@@ -104,13 +104,81 @@ void keccak256(const uint8_t *data, size_t len, uint8_t out[32]) {
     std::memcpy(out, st, 32);
 }
 
+// ---- the serial chain h -> (h + key + c_i)^7 ------------------------------------------------------------------
+// GKR_HASH_CHAIN 0 (default): fully reduced values everywhere; the conditional subtractions of the products are
+// branches, the two additions per round are branch-free.
+// GKR_HASH_CHAIN 1: nothing on the chain compares against p.  Values are kept below 2.32 p instead of below p:
+//   h < 1.32 p;  t = h + (key + c_i) < 2.32 p  (key + c_i is reduced, and off the chain: it does not depend on h);
+//   products WITHOUT the final conditional subtraction, each below a b / R + p:  t^2 < 2.02 p, t^4 < 1.77 p,
+//   t^3 < 1.89 p, t^7 < 1.63 p < 2^255;  then p is subtracted iff bit 254 is set (t^7 >= 2^254 > p), which leaves
+//   h < max(2^254, 0.63 p) = 1.32 p again.  One plain addition instead of two reduced ones, no data-dependent branch.
+// Same hashes, bit for bit.  Measured per 3-element multi_hash on the GPU box's Xeon (tools/hash_bench.sh,
+// profiles/r02_hash_bench_late.txt): chain 0 21.24 us, chain 1 24.0 us, chain 0 with the dedicated Montgomery square of
+// host_field.hpp (GKR_HOST_SQR, 30 instead of 36 multiplies) 22.06 us -- on the build container's CPU the square is 14 %
+// FASTER (that chain is bound by the multiplier port; the GPU box's is not).  The plain form stays.
+#ifndef GKR_HASH_CHAIN
+#define GKR_HASH_CHAIN 0
+#endif
+// Montgomery product without the final subtraction; operands below 2.32 p (see hfr_mul in host_field.hpp for the bounds)
+inline HFr mul_unreduced(const HFr &a, const HFr &b) {
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    for (int i = 0; i < 4; ++i) {
+        const uint64_t bi = b.l[i];
+        uint64_t A, C, lo;
+        hf::mac(a.l[0], bi, t0, 0, A, t0);
+        const uint64_t m = t0 * hf::NINV;
+        hf::mac(m, hf::P[0], t0, 0, C, lo);
+        hf::mac(a.l[1], bi, t1, A, A, t1);
+        hf::mac(m, hf::P[1], t1, C, C, t0);
+        hf::mac(a.l[2], bi, t2, A, A, t2);
+        hf::mac(m, hf::P[2], t2, C, C, t1);
+        hf::mac(a.l[3], bi, t3, A, A, t3);
+        hf::mac(m, hf::P[3], t3, C, C, t2);
+        t3 = C + A;
+    }
+    return HFr{{t0, t1, t2, t3}};
+}
+inline HFr add_plain(const HFr &a, const HFr &b) {      // no reduction; the caller knows the sum fits
+    HFr r;
+    uint64_t carry = 0;
+    for (int i = 0; i < 4; ++i) {
+        const hf::u128 t = (hf::u128)a.l[i] + b.l[i] + carry;
+        r.l[i] = (uint64_t)t;
+        carry = (uint64_t)(t >> 64);
+    }
+    return r;
+}
+inline HFr sub_p_if_bit254(const HFr &a) {             // a < 2^255
+    const uint64_t mask = (uint64_t)0 - ((a.l[3] >> 62) & 1);
+    HFr r;
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+        const hf::u128 d = (hf::u128)a.l[i] - (hf::P[i] & mask) - borrow;
+        r.l[i] = (uint64_t)d;
+        borrow = (uint64_t)(d >> 64) & 1;
+    }
+    return r;
+}
+// t^7 below 1.32 p from t below 2.32 p
+inline HFr seventh_power_chain(const HFr &t) {
+    const HFr t2 = mul_unreduced(t, t);
+    const HFr t3 = mul_unreduced(t2, t);
+    const HFr t4 = mul_unreduced(t2, t2);
+    return sub_p_if_bit254(mul_unreduced(t3, t4));
+}
+
 HFr mimc7_hash(const HFr &x, const HFr &key) {
     std::call_once(g_once, init_constants);
-    // (lazily reduced products -- no conditional subtraction on the chain -- were measured slower on the GPU
-    //  box's Xeon: 22.1 vs 21.3 us per 3-element multi_hash; the chain is bound by the multiplier latency)
+#if GKR_HASH_CHAIN
+    HFr h = seventh_power_chain(add_plain(x, key));
+    for (int i = 1; i < kRounds; ++i) h = seventh_power_chain(add_plain(h, hfr_add(key, g_constants[i])));
+    if (hf::geq_p(h.l)) hf::sub_p(h.l);              // h < 1.32 p
+    return hfr_add(h, key);
+#else
     HFr h = seventh_power(hfr_add(x, key));
     for (int i = 1; i < kRounds; ++i) h = seventh_power(hfr_add(hfr_add(h, key), g_constants[i]));
     return hfr_add(h, key);
+#endif
 }
 
 bool mimc7_round_constant(unsigned i, HFr *out) {

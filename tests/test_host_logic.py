@@ -68,3 +68,18 @@ def test_proof_pack_unpack_roundtrip():
         back = _unpack_proof(pc)
         for f in ("sumcheck_proofs", "sumcheck_r", "q", "z", "r", "k", "depth", "d_coef", "input_coef"):
             assert getattr(back, f) == getattr(dp, f), f
+
+
+def test_host_square_equals_product():
+    """host_field.hpp: the dedicated Montgomery square (compile-time option GKR_HOST_SQR, off by default: slower on the GPU
+    box) == the general product, bit for bit"""
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = os.path.join(here, "csrc", "host_sqr_check.cpp")
+    exe = os.path.join(here, "csrc", "host_sqr_check")
+    hdr = os.path.join(here, "..", "gkr_b200", "csrc", "host_field.hpp")
+    if not os.path.exists(exe) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(exe):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-DGKR_HOST_SQR=1", src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "bad=0", out.stdout + out.stderr
