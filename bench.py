@@ -341,6 +341,12 @@ def run_ours(args):
     elif rank == 0:
         parity["c3_proof_verified"] = bool(pv.verify(circuit, pv.prove(circuit, witness), pinned_np)[0])
 
+    # ---- proofs made by the reference's own Python prover (committed fixture): the CUDA path must reproduce them -------
+    refpy = os.path.join(ROOT, "tests", "golden", "refpy_vectors.json")
+    if rank == 0 and os.path.exists(refpy):
+        from gkr_b200 import verify as gv_ref
+        parity["reference_python_prover_vectors"] = gv_ref.check_reference_python_vectors(pv, refpy)
+
     # ---- per-kernel-class device timing (library-side CUDA events around every launch) --------------
     pv.profile(1)
     step_resident()

@@ -55,3 +55,63 @@ def check_sumcheck_prod(msgs, chal, fin, claimed_sum: int | None = None, evals=N
         out["final_evals"] = list(evals) == list(fin)
     out["ok"] = all(v for v in out.values())
     return out
+
+
+def check_reference_python_vectors(pv, path: str) -> dict:
+    """Runs the CUDA prover on every circuit of tests/golden/refpy_vectors.json -- proofs made by the reference's own
+    Python prover (python/gkr.py `prove`, python/sumcheck.py `prove_sumcheck`; tests/golden/make_refpy_vectors.py) -- and
+    compares round messages, challenges, q, z, r*, D, the input polynomial and f(r).  Coefficient lists are compared
+    without leading zeros (the prototype always lists four coefficients, the Rust prover uses static lengths).
+    Reads a JSON fixture only; nothing of the oracle is involved.  Used by bench.py (`parity`) and smoke()."""
+    import json
+
+    from .prover import DenseLayer
+
+    def ints(x):
+        return [ints(v) for v in x] if isinstance(x, list) else int(x)
+
+    def strip(c):
+        c = list(c)
+        while len(c) > 1 and c[0] == 0:
+            c = c[1:]
+        return c
+
+    def terms_map(terms):
+        m = {}
+        for t in terms:
+            mask = 0
+            for e in t[1:]:
+                mask = (mask << 1) | e
+            m[mask] = t[0]
+        return m
+
+    with open(path) as f:
+        fx = json.load(f)
+    bad = []
+    for case in fx["gkr"]:
+        layers = [DenseLayer(L["k_out"], L["k_in"], np.array([g[0] for g in L["gates"]], np.uint8),
+                             np.array([g[1] for g in L["gates"]], np.uint32), np.array([g[2] for g in L["gates"]], np.uint32))
+                  for L in case["layers"]]
+        c = pv.circuit(layers)
+        w = pv.witness_eval(c, ints_to_fr(ints(case["input"])))
+        pr = pv.prove(c, w)
+        want = case["proof"]
+        same = (pr.depth == want["depth"] and list(pr.k) == want["k"]
+                and [[strip(m) for m in lay] for lay in pr.sumcheck_proofs] == [[strip(m) for m in lay] for lay in ints(want["sumcheck_proofs"])]
+                and [list(x) for x in pr.sumcheck_r] == ints(want["sumcheck_r"])
+                and [strip(x) for x in pr.q] == [strip(x) for x in ints(want["q"])]
+                and [list(x) for x in pr.z] == ints(want["z"]) and list(pr.r) == ints(want["r"])
+                and {i: v for i, v in enumerate(pr.d_coef) if v} == terms_map(ints(want["D"]))
+                and {i: v for i, v in enumerate(pr.input_coef) if v} == terms_map(ints(want["input_func"]))
+                and [horner_desc(lay[-1], rr[-1]) for lay, rr in zip(pr.sumcheck_proofs, pr.sumcheck_r)] == ints(want["f"]))
+        if not same:
+            bad.append(case["name"])
+        w.close()
+        c.close()
+    n_sc = 0
+    for g in fx.get("sumcheck_prod", []):
+        msgs, chal, _ = pv.sumcheck_prod([ints_to_fr(ints(t)) for t in g["tables"]], g["n_vars"])
+        if [strip(m) for m in msgs] != [strip(m) for m in ints(g["msgs"])] or chal != ints(g["r"]):
+            bad.append("sumcheck_prod_%d" % g["n_vars"])
+        n_sc += 1
+    return {"circuits": len(fx["gkr"]), "product_sumchecks": n_sc, "mismatches": bad, "ok": not bad}
