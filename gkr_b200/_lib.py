@@ -71,7 +71,7 @@ EXPORTS = [
     "gkr_ctx_create", "gkr_ctx_destroy", "gkr_ctx_stream", "gkr_ctx_sync", "gkr_ctx_set_option", "gkr_last_error", "gkr_version", "gkr_mimc7_multi_hash", "gkr_mimc7_hash", "gkr_mimc7_round_constant",
     "gkr_frontend_compile", "gkr_frontend_compile_sym", "gkr_frontend_n_outputs", "gkr_frontend_output", "gkr_frontend_n_circuits", "gkr_frontend_n_public", "gkr_frontend_circuit", "gkr_frontend_destroy",
     "gkr_circuit_create", "gkr_circuit_destroy", "gkr_witness_create", "gkr_witness_eval", "gkr_witness_layer",
-    "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_verify", "gkr_sumcheck_prod", "gkr_dev_table_synth", "gkr_dev_table_synth_strided", "gkr_comm_unique_id", "gkr_comm_init", "gkr_comm_destroy", "gkr_comm_create",
+    "gkr_witness_destroy", "gkr_prove", "gkr_proof_free", "gkr_verify", "gkr_sumcheck_prod", "gkr_dev_table_synth", "gkr_dev_table_synth_strided", "gkr_comm_unique_id", "gkr_comm_init", "gkr_comm_init_shared", "gkr_comm_destroy", "gkr_comm_create",
     "gkr_sumcheck_prod_sharded",
     "gkr_dev_table_upload", "gkr_dev_table_download", "gkr_dev_table_free", "gkr_dev_table_eval", "gkr_fr_binop", "gkr_eq_table",
     "gkr_mobius", "gkr_line_restrict", "gkr_ctx_stats", "gkr_ctx_profile", "gkr_bench_field_mul", "gkr_fold_f64_constants", "gkr_selftest",
@@ -142,6 +142,7 @@ def lib():
     L.gkr_dev_table_synth_strided.argtypes = [vp, u64, u64, u64, u64, u64, C.POINTER(vp)]
     L.gkr_comm_unique_id.argtypes = [vp]
     L.gkr_comm_init.argtypes = [vp, i32, i32, vp]
+    L.gkr_comm_init_shared.argtypes = [vp, i32, i32, C.c_char_p]
     L.gkr_comm_destroy.argtypes = [vp]
     if hasattr(L, "gkr_comm_create"):
         L.gkr_comm_create.argtypes = [i32, C.POINTER(i32), C.POINTER(vp)]

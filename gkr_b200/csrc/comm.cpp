@@ -8,6 +8,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <nccl.h>
 
@@ -205,6 +206,99 @@ extern "C" int gkr_comm_init(gkr_ctx *ctx, int n_ranks, int rank, const uint8_t 
             xchg_release(ctx);
             return xrc;
         }
+    }
+    return GKR_OK;
+}
+
+// One process per rank WITHOUT NCCL: the caller supplies the name of the POSIX shared-memory object (the same string on
+// every rank, unique per job; it travels over whatever the host already uses to start its ranks).  Rank 0 creates the
+// object, the others wait for it to appear, everyone maps it and registers it with CUDA, and the ranks meet on flags
+// inside the block before rank 0 unlinks the name.  Ranks may share a device (a multi-process job on a single-GPU box),
+// which an NCCL communicator does not allow; the per-round exchange and the gather are the ones of gkr_comm_init.
+extern "C" int gkr_comm_init_shared(gkr_ctx *ctx, int n_ranks, int rank, const char *shm_name) {
+    if (!ctx || !shm_name || shm_name[0] != '/' || std::strlen(shm_name) >= sizeof(XchgState{}.shm_name) || n_ranks < 1 ||
+        n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks || (n_ranks & (n_ranks - 1))) {
+        set_last_error("gkr_comm_init_shared: n_ranks must be a power of two <= %d, 0 <= rank < n_ranks, name \"/...\" of < 64 bytes", kMaxRanks);
+        return GKR_ERR_INVALID;
+    }
+    if (ctx->comm_active) {
+        set_last_error("gkr_comm_init_shared: communicator already initialised");
+        return GKR_ERR_INVALID;
+    }
+    GKR_TRY(ctx->bind());
+    ctx->n_ranks = n_ranks;
+    ctx->rank = rank;
+    GKR_TRY(comm_buffers(ctx));
+    ctx->comm_active = true;
+    if (n_ranks == 1) return GKR_OK;
+    auto fail = [&](int rc) {
+        xchg_release(ctx);
+        gkr_comm_destroy(ctx);
+        return rc;
+    };
+    ctx->xchg = new (std::nothrow) XchgState();
+    if (!ctx->xchg) return fail(GKR_ERR_OOM);
+    XchgState *x = ctx->xchg;
+    x->is_shm = true;
+    int fd = -1;
+    if (rank == 0) {
+        fd = shm_open(shm_name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, (off_t)sizeof(XchgBlock)) != 0) {
+            set_last_error("shm_open/ftruncate(%s) failed: %s", shm_name, strerror(errno));
+            if (fd >= 0) { close(fd); shm_unlink(shm_name); }
+            return fail(GKR_ERR_COMM);
+        }
+        x->owner = true;
+        std::memcpy(x->shm_name, shm_name, std::strlen(shm_name) + 1);
+    } else {
+        // wait for rank 0 to create the object and give it its size (up to 60 s)
+        const double t0 = now_seconds();
+        for (;;) {
+            fd = shm_open(shm_name, O_RDWR, 0600);
+            if (fd >= 0) {
+                struct stat st;
+                if (fstat(fd, &st) == 0 && (size_t)st.st_size >= sizeof(XchgBlock)) break;
+                close(fd);
+                fd = -1;
+            }
+            if (now_seconds() - t0 > 60.0) {
+                set_last_error("gkr_comm_init_shared: rank 0 never created %s", shm_name);
+                return fail(GKR_ERR_COMM);
+            }
+            usleep(2000);
+        }
+    }
+    void *p = mmap(nullptr, sizeof(XchgBlock), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) {
+        set_last_error("mmap(%s) failed: %s", shm_name, strerror(errno));
+        if (x->owner) shm_unlink(shm_name);
+        return fail(GKR_ERR_COMM);
+    }
+    x->host = static_cast<XchgBlock *>(p);
+    if (cudaHostRegister(p, sizeof(XchgBlock), cudaHostRegisterMapped | cudaHostRegisterPortable) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&x->dev, p, 0) != cudaSuccess) {
+        set_last_error("cudaHostRegister of the exchange block failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (x->owner) shm_unlink(shm_name);
+        return fail(GKR_ERR_CUDA);
+    }
+    // rendezvous: everyone has mapped the object before the name goes away or the first exchange starts
+    volatile uint32_t *att = x->host->attached;
+    __atomic_store_n(&x->host->attached[rank], 1u, __ATOMIC_RELEASE);
+    const double t1 = now_seconds();
+    for (int r = 0; r < n_ranks; ++r) {
+        while (__atomic_load_n(&att[r], __ATOMIC_ACQUIRE) == 0) {
+            if (now_seconds() - t1 > 60.0) {
+                set_last_error("gkr_comm_init_shared: rank %d never attached to %s", r, shm_name);
+                if (x->owner) shm_unlink(shm_name);
+                return fail(GKR_ERR_COMM);
+            }
+            usleep(500);
+        }
+    }
+    if (x->owner) {
+        shm_unlink(shm_name);                 // the mappings keep it alive; nothing is left behind if a rank crashes
+        x->shm_name[0] = 0;
     }
     return GKR_OK;
 }

@@ -122,6 +122,9 @@ struct XchgBlock {
     // before that peer has finished reading, because gather n+1 waits for the peer's flag, which the peer raises
     // behind its gather-n read in stream order
     Fr stage[2][kMaxRanks][3 * (kGatherEntries / 2)];
+    // host-side rendezvous of gkr_comm_init_shared (processes that have mapped and registered the block); never read
+    // by a kernel
+    uint32_t attached[kMaxRanks];
 };
 // one rank's view of it
 struct XchgState {

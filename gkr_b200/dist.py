@@ -121,10 +121,19 @@ def max_over_ranks(value: float) -> float:
 
 
 def init_comm(prover) -> None:
-    """create the library's NCCL communicator on `prover` (collective over the default process group)"""
+    """create the library's communicator on `prover` (collective over the default process group): through NCCL when the
+    group's backend is NCCL (one GPU per rank), through a named shared-memory block otherwise (`gkr_comm_init_shared`:
+    ranks may then share a device, e.g. a torchrun job over `gloo` on a single-GPU box)"""
     import torch.distributed as dist
     L = _lib.lib()
     rank, ws = dist.get_rank(), dist.get_world_size()
+    if dist.get_backend() != "nccl":
+        import os
+        import time
+        name = ("/gkr_b200_%d_%x" % (os.getpid(), int(time.time() * 1e6) & 0xFFFFFFFFFFFF)).encode() if rank == 0 else None
+        ident = broadcast_bytes(name.ljust(64, b"\0") if rank == 0 else None, 64, 0).rstrip(b"\0")
+        _lib.check(L.gkr_comm_init_shared(prover._ctx, ws, rank, ident))
+        return
     buf = (C.c_uint8 * _lib.GKR_COMM_ID_BYTES)()
     if rank == 0:
         _lib.check(L.gkr_comm_unique_id(buf))

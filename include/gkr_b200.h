@@ -198,6 +198,12 @@ int gkr_sumcheck_prod(gkr_ctx *ctx, uint32_t n_tables, uint32_t n_vars, const vo
 int gkr_comm_unique_id(uint8_t out[GKR_COMM_ID_BYTES]);
 int gkr_comm_init(gkr_ctx *ctx, int n_ranks, int rank, const uint8_t id[GKR_COMM_ID_BYTES]);
 void gkr_comm_destroy(gkr_ctx *ctx);
+/* The same communicator without NCCL: the per-round exchange of this library never goes through NCCL anyway (a block of
+ * pinned host memory shared by the ranks), so all a rank needs is the name of the POSIX shared-memory object -- the same
+ * string "/..." (< 64 bytes, unique per job) on every rank, handed over by whatever starts the ranks.  Rank 0 creates
+ * the object, the others wait for it (60 s), all meet inside the block, rank 0 unlinks the name.  Ranks may share a
+ * device (a multi-process job on a single-GPU box), which an NCCL communicator refuses.  Collective. */
+int gkr_comm_init_shared(gkr_ctx *ctx, int n_ranks, int rank, const char *shm_name);
 /* The same communicator with every rank inside ONE process: creates n_ranks contexts (rank r on device_ids[r]; ranks may
  * share a device) whose mailboxes address each other directly.  Each context is then driven by its own host thread;
  * the sharded entry points are collective over the group.  No NCCL involved.  Destroy every context with

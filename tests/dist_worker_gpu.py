@@ -14,8 +14,14 @@ from oracle import oracle as orc  # noqa: E402
 
 def main():
     rank, ws, local = gd.world()
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_dev = torch.cuda.device_count()
+    if n_dev >= ws:                      # one GPU per rank: NCCL process group, gkr_comm_init
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:                                # fewer GPUs than ranks (a single-GPU box): gloo group, gkr_comm_init_shared,
+        local = local % n_dev            # ranks share devices -- the exchange goes through shared host memory either way
+        torch.cuda.set_device(local)
+        dist.init_process_group("gloo")
     pv = gkr_b200.Prover(local)
     gd.init_comm(pv)
     for v, seed in ((6, 1), (13, 2), (20, 3)):
