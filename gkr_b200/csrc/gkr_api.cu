@@ -461,7 +461,8 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx **out) {
     std::memset((void *)ctx->cmds_host, 0, sizeof(HostCmd) * gkr_ctx::kSlots);
     GKR_CUDA_TRY(cudaHostGetDevicePointer((void **)&ctx->cmds_dev, (void *)ctx->cmds_host, 0));
     ctx->ws.max_blocks = device_sm_count() * 4;
-    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->ws.partials, sizeof(Fr) * 6 * (size_t)ctx->ws.max_blocks));
+    // 6 sums per CTA for max_blocks CTAs; the tiled wiring kernel (3 sums per CTA) runs up to kWiringGridFactor x as many CTAs
+    GKR_CUDA_TRY(cudaMalloc((void **)&ctx->ws.partials, sizeof(Fr) * 6 * (size_t)ctx->ws.max_blocks * (kWiringGridFactor / 2)));
     GKR_CUDA_TRY(cudaMalloc((void **)&ctx->ws.counter, 2 * sizeof(unsigned int)));
     GKR_CUDA_TRY(cudaMemsetAsync(ctx->ws.counter, 0, 2 * sizeof(unsigned int), ctx->stream));
     ctx->ws.tile_counter = ctx->ws.counter + 1;

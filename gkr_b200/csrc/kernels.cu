@@ -389,18 +389,29 @@ __global__ void __launch_bounds__(kThreads, GKR_WIRING_MINB)
     grid_sum_publish<K>(acc, partials, counter, slot, seq, 0u, xa);
 }
 // ------------------------------------------------------------------------------------------------
-// The same computation, tiled per CTA instead of per warp (tables of >= kWiringTiledMin rows).  A tile is 256 row pairs
-// (b, b + N/2); its two contiguous CSR edge ranges are walked edge-parallel by all 256 threads: the two gathers of an edge
+// The same computation, tiled per CTA instead of per warp (tables of >= kWiringTiledMin rows).  A tile is kWTile (128) row pairs
+// (b, b + N/2); its two contiguous CSR edge ranges are walked edge-parallel by all threads of the CTA: the two gathers of an edge
 // go straight into shared memory with cp.async (no registers held while they are in flight, up to 8 per thread
 // outstanding), the products then run back to back from shared memory (full warps, four independent products per
 // thread), and after one barrier every thread adds up the staged segments of its own two rows.  Tiles are handed out
 // by an atomic counter (field sums are exact, so the order cannot change a bit of the result).
 // ------------------------------------------------------------------------------------------------
+// Tile shape, measured on 2^20 x 16 proofs (wiring class per proof / proof, same box back to back; r02 late):
+//   256 threads x 2 CTAs per SM 3.98 ms / 23.92 ms;  128 x 4: 3.75 / 23.78;  96 x 5: 3.95;  64 x 8: 3.93;  32 x 16: 4.47;
+//   128 x 3 (170 registers): 4.12;  512 x 1: 4.48.  Four small CTAs per SM overlap the dependent phases of a tile (row
+//   extents -> edge indices -> gathers -> products -> barrier -> row sums) better than two large ones.
 #ifndef GKR_WTILE_MINB
-#define GKR_WTILE_MINB 2
+#define GKR_WTILE_MINB 4
 #endif
-constexpr int kWTile = 256;
-constexpr int kWCap = 1024;                    // staged edges per pass (2 x 32 KB of shared memory)
+#ifndef GKR_WTILE
+#define GKR_WTILE 128                          // row pairs per tile = threads per CTA
+#endif
+#ifndef GKR_WCAP
+#define GKR_WCAP (4 * GKR_WTILE)               // staged edges per pass: four per thread (2 x 32 B of shared memory each)
+#endif
+constexpr int kWTile = GKR_WTILE;
+constexpr int kWCap = GKR_WCAP;
+static_assert(kWCap % kWTile == 0 && kWTile % 32 == 0 && kWTile <= 32 * kMaxWarps, "tile shape");
 constexpr uint64_t kWiringTiledMin = 1024;
 __device__ __forceinline__ void cp_async_fr(Fr *dst_smem, const Fr *src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
@@ -539,7 +550,7 @@ void launch_wiring_round1(bool phase2, bool full, const uint32_t *rowptr, const 
         const uint32_t n_tiles = (uint32_t)((n / 2 + kWTile - 1) / kWTile);
         int grid = device_sm_count() * GKR_WTILE_MINB;
         if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
-        if (grid > ws.max_blocks) grid = ws.max_blocks;
+        if (grid > ws.max_blocks * kWiringGridFactor) grid = ws.max_blocks * kWiringGridFactor;      // K <= 3 sums per CTA
         const size_t smem = sizeof(Fr) * 2 * kWCap;
         const uint32_t base = ws.tile_base;
         ws.tile_base += n_tiles + (uint32_t)grid;           // every CTA draws one ticket past the end

@@ -32,8 +32,9 @@ struct FrVec {            // up to 32 field elements passed by value as a kernel
 };
 
 // Reduction workspace shared by all reducing kernels of one context (stream-ordered reuse).
+constexpr int kWiringGridFactor = 4;     // the tiled wiring kernel may run up to this many times max_blocks CTAs (small CTAs)
 struct ReduceWs {
-    Fr *partials;         // [max_blocks * 6]
+    Fr *partials;         // [max_blocks * 6 * kWiringGridFactor / 2]
     unsigned int *counter;
     int max_blocks;
     // work distribution of the tiled wiring kernel: a device counter that only ever grows; the host keeps the value it

@@ -45,13 +45,15 @@ def bits(i, k):
     return [(i >> (k - 1 - j)) & 1 for j in range(k)]
 
 
-def run_prototype(ks, gates_per_layer, inputs):
-    """The reference's python/gkr.py prover on the circuit; returns its Proof as plain ints."""
+def run_prototype(ks, gates_per_layer, inputs, native_transcript=False):
+    """The reference's python/gkr.py prover on the circuit; returns its Proof as plain ints.
+    native_transcript: the stub hashes the prototype's coefficient lists exactly as they are (no leading zeros dropped)."""
     for p in (os.path.join(HERE, "refpy_stub"), REF_PY):
         if p not in sys.path:
             sys.path.insert(0, p)
     import gkr as G                      # /root/reference/python/gkr.py
-    from ethsnarks import field          # the stub
+    from ethsnarks import field, mimc    # the stub
+    mimc.STRIP_LEADING_ZEROS = not native_transcript
     FQ = field.FQ
     vals = forward(ks, gates_per_layer, inputs)
     depth = len(ks)
@@ -90,7 +92,8 @@ def run_prototype_sumcheck(tables, v):
             sys.path.insert(0, p)
     import poly as PL                    # /root/reference/python/poly.py
     import sumcheck as SC                # /root/reference/python/sumcheck.py
-    from ethsnarks import field
+    from ethsnarks import field, mimc
+    mimc.STRIP_LEADING_ZEROS = True
     FQ = field.FQ
 
     def index_of(arr):
@@ -145,6 +148,28 @@ def generate():
                     "layers": [{"k_out": ks[i], "k_in": ks[i + 1], "gates": [list(g) for g in gl[i]]} for i in range(len(gl))],
                     "input": S(list(inputs)),
                     "proof": {k: (S(v) if isinstance(v, list) and k != "k" else v) for k, v in pr.items()}})
+    # second regime: the prototype's own serialisation is what gets hashed (its four-coefficient lists, unmodified stub
+    # hash), and the provers under test run with a transcript callback that pads a message to four coefficients.  This
+    # also covers circuits with round messages of lower degree: the four candidates skipped above and circuits that are
+    # degenerate by construction (constant / zero / half-constant inputs, one gate feeding every output).
+    native = []
+    rngn = random.Random(20261019)
+    by_name = {c[0]: c for c in candidate_cases()}
+    deg = [by_name[n] for n in skipped]
+    ks = [2, 3]
+    gl = [rand_gates(rngn, 2, 3)]
+    a, b = rngn.randrange(P), rngn.randrange(P)
+    deg += [("constant_input_2_3", ks, gl, [5] * 8), ("zero_input_2_3", ks, gl, [0] * 8),
+            ("depends_on_x1_only_2_3", ks, gl, [a] * 4 + [b] * 4),
+            ("same_operands_2_2_2", [2, 2, 2], [[(0, 1, 1)] * 4, [(1, 2, 2)] * 4], [rngn.randrange(P) for _ in range(4)]),
+            ("sparse_input_2_3_3", [2, 3, 3], [rand_gates(rngn, 2, 3), rand_gates(rngn, 3, 3)],
+             [rngn.randrange(P) if rngn.random() < 0.4 else 0 for _ in range(8)])]
+    for name, ks_, gl_, inputs in deg:
+        pr = run_prototype(ks_, gl_, inputs, native_transcript=True)
+        native.append({"name": name, "k": ks_,
+                       "layers": [{"k_out": ks_[i], "k_in": ks_[i + 1], "gates": [list(g) for g in gl_[i]]} for i in range(len(gl_))],
+                       "input": S(list(inputs)),
+                       "proof": {k: (S(v) if isinstance(v, list) and k != "k" else v) for k, v in pr.items()}})
     rng = random.Random(20261018)
     prod = []
     for v in (2, 3, 4, 5):
@@ -153,7 +178,7 @@ def generate():
         prod.append({"n_vars": v, "tables": S(tabs), "msgs": S(msgs), "r": S(r)})
     return {"generator": "tests/golden/make_refpy_vectors.py: /root/reference/python/gkr.py `prove` (unmodified) over "
                          "tests/golden/refpy_stub/ethsnarks (MiMC7-91 multi_hash over the message without leading zeros; z_0 = 0)",
-            "skipped_lower_degree_messages": skipped, "gkr": res, "sumcheck_prod": prod}
+            "skipped_lower_degree_messages": skipped, "gkr": res, "gkr_native_transcript": native, "sumcheck_prod": prod}
 
 
 if __name__ == "__main__":

@@ -48,8 +48,9 @@ def assert_matches_reference_python(case, sumcheck_proofs, sumcheck_r, q, z, r, 
     assert [strip(x) for x in q] == [strip(x) for x in gu.I(w["q"])], what
     assert [list(x) for x in z] == gu.I(w["z"]), what
     assert list(r) == gu.I(w["r"]), what
-    assert d_map == gu.terms_map(gu.I(w["D"])), what
-    assert input_map == gu.terms_map(gu.I(w["input_func"])), what
+    # (the prototype writes the zero polynomial as one term with coefficient 0, python/poly.py:331-333)
+    assert d_map == {m: c for m, c in gu.terms_map(gu.I(w["D"])).items() if c}, what
+    assert input_map == {m: c for m, c in gu.terms_map(gu.I(w["input_func"])).items() if c}, what
     # f_i = the layer's last round polynomial at its last challenge (python/gkr.py:176-183)
     assert [horner(layer[-1], rr[-1]) for layer, rr in zip(sumcheck_proofs, sumcheck_r)] == gu.I(w["f"]), what
 
@@ -82,6 +83,31 @@ def test_product_sumcheck_matches_reference_python_prover(idx):
     assert [strip(m) for m in msgs] == want_msgs and r == want_r
     msgs, r, _ = orc.sumcheck_prod([orc.to_bytes(t) for t in tabs], v)
     assert [strip(m) for m in msgs] == want_msgs and r == want_r
+
+
+NATIVE = REFPY["gkr_native_transcript"]
+NATIVE_IDS = [c["name"] for c in NATIVE]
+
+
+def prototype_list(msg):
+    """the coefficient list the prototype hashes for a round message: [constant slot, c2, c1, c0] (python/poly.py:168-178
+    appends the polynomial's constant -- always 0 here -- to the expansion), or [0, 0] for the zero polynomial"""
+    msg = list(msg)
+    if not any(msg):
+        return [0, 0]
+    return [0] * (4 - len(msg)) + msg
+
+
+@pytest.mark.parametrize("case", NATIVE, ids=NATIVE_IDS)
+def test_literal_restatement_matches_reference_python_prover_on_degenerate_circuits(case, monkeypatch):
+    """second regime: the prototype hashes its own lists; the restatement runs with the hash taken over the same list.
+    Covers round messages of lower degree (the Rust prover's two-coefficient messages included) and zero polynomials."""
+    orig = l0.multi_hash
+    monkeypatch.setattr(l0, "multi_hash", lambda msg, key=0: orig(prototype_list(msg), key))
+    pr, _ = run_l0(gu.case_layers(case), gu.I(case["input"]))
+    assert_matches_reference_python(case, pr.sumcheck_proofs, pr.sumcheck_r, pr.q, pr.z, pr.r, pr.depth, pr.k,
+                                    gu.terms_map(pr.d), gu.terms_map(pr.input_func))
+    assert any(len(m) == 2 for c in NATIVE for layer in run_l0(gu.case_layers(c), gu.I(c["input"]))[0].sumcheck_proofs for m in layer)
 
 
 def test_fixture_covers_the_prototype_example_and_mixed_circuits():

@@ -65,6 +65,23 @@ def test_reference_python_prover_vectors(pv, case):
                                        gu.terms_map(got.d), gu.terms_map(got.input_func))
 
 
+def _refpy_native():
+    from tests import test_golden_refpy as rp
+    return rp.NATIVE, rp.NATIVE_IDS
+
+
+@pytest.mark.parametrize("case", _refpy_native()[0], ids=_refpy_native()[1])
+def test_reference_python_prover_vectors_degenerate(pv, case):
+    """circuits with round messages of lower degree: the prototype hashes its own coefficient lists, the CUDA path runs
+    with a transcript callback (gkr_transcript) that hashes the same list"""
+    from tests import test_golden_refpy as rp
+    cb = lambda msg: l0.multi_hash(rp.prototype_list(msg), 0)      # noqa: E731
+    proof = _gpu_prove(pv, gu.case_layers(case), gu.I(case["input"]), challenge=cb)
+    rp.assert_matches_reference_python(case, proof.sumcheck_proofs, proof.sumcheck_r, proof.q, proof.z, proof.r, proof.depth,
+                                       proof.k, {i: c for i, c in enumerate(proof.d_coef) if c},
+                                       {i: c for i, c in enumerate(proof.input_coef) if c})
+
+
 @pytest.mark.parametrize("ks", [[1, 2, 2], [2, 3, 2], [2, 2, 3, 1], [3, 4, 3], [0, 2, 2], [1, 1, 1], [4, 5, 4, 5]])
 @pytest.mark.parametrize("mode", ["mixed", "add", "mult"])
 def test_against_literal_reference_types(pv, ks, mode):
