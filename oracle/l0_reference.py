@@ -11,8 +11,8 @@ The transcript hash is the external `mimc-rs` crate (unpinned, not under /root/r
 MiMC7-91, restated from its published algorithm and pinned by the known answers of SURVEY.md A.3.
 PARITY: pinned against the reference's own PYTHON prover (/root/reference/python/gkr.py + sumcheck.py, run unmodified
 over a stand-in for the absent `ethsnarks`; tests/golden/make_refpy_vectors.py -> tests/golden/refpy_vectors.json,
-tests/test_golden_refpy.py): messages, challenges, q, z, r*, D, input polynomial and f(r) agree on 21 circuits, the
-generic product sumcheck on 4 table sets.  Still UNPINNED against the Rust binary (no Rust toolchain, no golden
+tests/test_golden_refpy.py): messages, challenges, q, z, r*, D, input polynomial and f(r) agree on 30 circuits (9 of them with
+round messages of lower degree, through a transcript callback), the generic product sumcheck on 4 table sets.  Still UNPINNED against the Rust binary (no Rust toolchain, no golden
 vectors in the reference): what only the Rust code defines -- static message lengths, term-list emission -- rests on
 this literal restatement.
 """

@@ -12,7 +12,9 @@ coefficients of every message (and of q) whatever their value (python/poly.py:16
 lengths (rust/src/gkr/poly.rs:388-420).  The transcript hash is taken over that list, so the stub hashes a message
 without its leading zero coefficients; on circuits whose messages have full degree under the Rust rule (every case
 below: each round's leading coefficient is non-zero) both provers then hash the same lists, draw the same challenges,
-and every later value must agree.  tests/test_golden_refpy.py compares the oracle ladder (and, on a GPU, the CUDA path)
+and every later value must agree.  Circuits with messages of lower degree go through a second regime
+("gkr_native_transcript"): the stub hashes the prototype's list exactly as it is, and the provers under test run with a
+transcript callback that hashes the same list.  tests/test_golden_refpy.py compares the oracle ladder (and, on a GPU, the CUDA path)
 with these vectors after the same normalisation (leading zeros of a coefficient list dropped).
 
     python tests/golden/make_refpy_vectors.py          (needs /root/reference; the fixture is committed)
