@@ -116,17 +116,72 @@ inline HFr hfr_mul(const HFr &a, const HFr &b) {
     if (hf::geq_p(r.l)) hf::sub_p(r.l);
     return r;
 }
-// Montgomery square.  The transcript is a serial chain of x^7 = (x^2)^2 * (x^2 * x): half of its products are squares,
-// and on the host the chain is bound by the 64x64 multiplier port (two independent chains interleaved take twice the
-// time of one).  A square needs the six cross products once (doubled by a shift) plus four squares: 10 multiplies
-// instead of 16 before the 20 of the reduction -- 30 instead of 40 per square, 140 instead of 160 per MiMC round.
-// Same value as hfr_mul(a, a), bit for bit (tests/test_host_logic.py::test_host_square_equals_product).
+// Montgomery square.  The transcript is a serial chain of x^7 = (x^2)^2 * (x^2 * x): half of its products are squares.
+// A square needs the six cross products once (doubled) plus four squares: 10 multiplies instead of 16 before the 20 of
+// the reduction.  Two forms, both bit-identical to hfr_mul(a, a) (tests/test_host_logic.py::test_host_square_equals_product):
+//   GKR_HOST_SQR 2 (default): the interleaved row form of hfr_mul -- row i adds a_i * (a_i at limb i, the doubled tail
+//     2 sum_{j>i} a_j B^j above it) and one reduction step; same dependency structure as the product.
+//   GKR_HOST_SQR 1: full 512-bit square first, then four reduction steps.
+//   GKR_HOST_SQR 0: hfr_mul(a, a).
+// Per 3-element multi_hash on the GPU box's Xeon (tools/hash_bench.sh, profiles/r02_hash_bench_late.txt): 21.25 us with
+// form 0, 21.02 us with form 2, 22.06 us with form 1 (on the build container's CPU form 1 is 14 % faster than form 0).
 #ifndef GKR_HOST_SQR
-#define GKR_HOST_SQR 0           // measured slower on the GPU box (transcript.cpp), faster on the build container
+#define GKR_HOST_SQR 2
 #endif
 inline HFr hfr_sqr(const HFr &a) {
 #if !GKR_HOST_SQR
     return hfr_mul(a, a);
+#elif GKR_HOST_SQR == 2
+    // the square in the interleaved row form of hfr_mul: row i adds a_i * (a_i at limb i, 2 a_j at limbs j > i) and one
+    // reduction step; 2a < 2^255 fits four limbs.  10 + 20 multiplies, the dependency structure of the product.
+    using hf::mac;
+    const uint64_t a0 = a.l[0], a1 = a.l[1], a2 = a.l[2], a3 = a.l[3];
+    // doubled tails 2 * sum_{j > i} a_j B^j: the limb right above a_i takes no bit from a_i (a_i is squared, not doubled)
+    const uint64_t d2 = (a2 << 1) | (a1 >> 63), d3 = (a3 << 1) | (a2 >> 63);
+    const uint64_t e1 = a1 << 1, e2 = a2 << 1, e3 = a3 << 1;
+    uint64_t t0, t1, t2, t3, A, C, lo, m;
+    // row 0
+    mac(a0, a0, 0, 0, A, t0);
+    m = t0 * hf::NINV;
+    mac(m, hf::P[0], t0, 0, C, lo);
+    mac(a0, e1, 0, A, A, t1);
+    mac(m, hf::P[1], t1, C, C, t0);
+    mac(a0, d2, 0, A, A, t2);
+    mac(m, hf::P[2], t2, C, C, t1);
+    mac(a0, d3, 0, A, A, t3);
+    mac(m, hf::P[3], t3, C, C, t2);
+    t3 = C + A;
+    // row 1
+    m = t0 * hf::NINV;
+    mac(m, hf::P[0], t0, 0, C, lo);
+    mac(a1, a1, t1, 0, A, t1);
+    mac(m, hf::P[1], t1, C, C, t0);
+    mac(a1, e2, t2, A, A, t2);
+    mac(m, hf::P[2], t2, C, C, t1);
+    mac(a1, d3, t3, A, A, t3);
+    mac(m, hf::P[3], t3, C, C, t2);
+    t3 = C + A;
+    // row 2
+    m = t0 * hf::NINV;
+    mac(m, hf::P[0], t0, 0, C, lo);
+    mac(m, hf::P[1], t1, C, C, t0);
+    mac(a2, a2, t2, 0, A, t2);
+    mac(m, hf::P[2], t2, C, C, t1);
+    mac(a2, e3, t3, A, A, t3);
+    mac(m, hf::P[3], t3, C, C, t2);
+    t3 = C + A;
+    // row 3
+    m = t0 * hf::NINV;
+    mac(m, hf::P[0], t0, 0, C, lo);
+    mac(m, hf::P[1], t1, C, C, t0);
+    mac(m, hf::P[2], t2, C, C, t1);
+    mac(a3, a3, t3, 0, A, t3);
+    mac(m, hf::P[3], t3, C, C, t2);
+    t3 = C + A;
+    (void)lo;
+    HFr r{{t0, t1, t2, t3}};
+    if (hf::geq_p(r.l)) hf::sub_p(r.l);
+    return r;
 #else
     using hf::u128;
     const uint64_t a0 = a.l[0], a1 = a.l[1], a2 = a.l[2], a3 = a.l[3];

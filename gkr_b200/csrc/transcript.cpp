@@ -113,9 +113,8 @@ void keccak256(const uint8_t *data, size_t len, uint8_t out[32]) {
 //   t^3 < 1.89 p, t^7 < 1.63 p < 2^255;  then p is subtracted iff bit 254 is set (t^7 >= 2^254 > p), which leaves
 //   h < max(2^254, 0.63 p) = 1.32 p again.  One plain addition instead of two reduced ones, no data-dependent branch.
 // Same hashes, bit for bit.  Measured per 3-element multi_hash on the GPU box's Xeon (tools/hash_bench.sh,
-// profiles/r02_hash_bench_late.txt): chain 0 21.24 us, chain 1 24.0 us, chain 0 with the dedicated Montgomery square of
-// host_field.hpp (GKR_HOST_SQR, 30 instead of 36 multiplies) 22.06 us -- on the build container's CPU the square is 14 %
-// FASTER (that chain is bound by the multiplier port; the GPU box's is not).  The plain form stays.
+// profiles/r02_hash_bench_late.txt): chain 0 21.24 us, chain 1 24.0 us.  (The squares inside either chain are hfr_sqr,
+// host_field.hpp: its row form brings chain 0 to 21.02 us.)
 #ifndef GKR_HASH_CHAIN
 #define GKR_HASH_CHAIN 0
 #endif

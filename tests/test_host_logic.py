@@ -71,15 +71,16 @@ def test_proof_pack_unpack_roundtrip():
 
 
 def test_host_square_equals_product():
-    """host_field.hpp: the dedicated Montgomery square (compile-time option GKR_HOST_SQR, off by default: slower on the GPU
-    box) == the general product, bit for bit"""
+    """host_field.hpp: both dedicated Montgomery squares (GKR_HOST_SQR 2 = the default row form, 1 = product first, then
+    reduction) == the general product, bit for bit"""
     import os
     import subprocess
     here = os.path.dirname(os.path.abspath(__file__))
     src = os.path.join(here, "csrc", "host_sqr_check.cpp")
-    exe = os.path.join(here, "csrc", "host_sqr_check")
     hdr = os.path.join(here, "..", "gkr_b200", "csrc", "host_field.hpp")
-    if not os.path.exists(exe) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(exe):
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-DGKR_HOST_SQR=1", src, "-o", exe])
-    out = subprocess.run([exe], capture_output=True, text=True)
-    assert out.returncode == 0 and out.stdout.strip() == "bad=0", out.stdout + out.stderr
+    for form in (2, 1):
+        exe = os.path.join(here, "csrc", "host_sqr_check%d" % form)
+        if not os.path.exists(exe) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(exe):
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-DGKR_HOST_SQR=%d" % form, src, "-o", exe])
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0 and out.stdout.strip() == "bad=0", (form, out.stdout + out.stderr)
