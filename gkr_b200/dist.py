@@ -120,6 +120,18 @@ def max_over_ranks(value: float) -> float:
     return float(t.item())
 
 
+def shared_block_name() -> bytes:
+    """name of the job's shared-memory exchange block ("/..." of fewer than 64 bytes): chosen by rank 0, the same on every
+    rank after a broadcast over the default process group (collective)"""
+    import os
+    import time
+    import torch.distributed as dist
+    name = None
+    if dist.get_rank() == 0:
+        name = ("/gkr_b200_%d_%x" % (os.getpid(), int(time.time() * 1e6) & 0xFFFFFFFFFFFF)).encode().ljust(64, b"\0")
+    return broadcast_bytes(name, 64, 0).rstrip(b"\0")
+
+
 def init_comm(prover) -> None:
     """create the library's communicator on `prover` (collective over the default process group): through NCCL when the
     group's backend is NCCL (one GPU per rank), through a named shared-memory block otherwise (`gkr_comm_init_shared`:
@@ -128,11 +140,7 @@ def init_comm(prover) -> None:
     L = _lib.lib()
     rank, ws = dist.get_rank(), dist.get_world_size()
     if dist.get_backend() != "nccl":
-        import os
-        import time
-        name = ("/gkr_b200_%d_%x" % (os.getpid(), int(time.time() * 1e6) & 0xFFFFFFFFFFFF)).encode() if rank == 0 else None
-        ident = broadcast_bytes(name.ljust(64, b"\0") if rank == 0 else None, 64, 0).rstrip(b"\0")
-        _lib.check(L.gkr_comm_init_shared(prover._ctx, ws, rank, ident))
+        _lib.check(L.gkr_comm_init_shared(prover._ctx, ws, rank, shared_block_name()))
         return
     buf = (C.c_uint8 * _lib.GKR_COMM_ID_BYTES)()
     if rank == 0:

@@ -18,6 +18,11 @@ def main():
     payload = bytes((7 * i + 3) % 256 for i in range(256))
     got = gd.broadcast_bytes(payload if rank == 0 else None, 256, 0)
     assert got == payload
+    # the NCCL-free communicator (gkr_comm_init_shared) needs one name on every rank
+    name = gd.shared_block_name()
+    names = [None] * ws
+    dist.all_gather_object(names, name)
+    assert all(n == names[0] for n in names) and name.startswith(b"/gkr_b200_") and 1 < len(name) < 64 and b"\0" not in name
     # independent proofs are dealt round-robin, each exactly once
     mine = gd.assign_round_robin(13, rank, ws)
     gathered = [None] * ws

@@ -44,6 +44,18 @@ def test_no_device_is_a_loud_error():
         Prover(0)
 
 
+def test_communicator_entry_points_reject_bad_arguments_without_a_device():
+    """argument checks come before any CUDA call: GKR_ERR_INVALID, a message, nothing aborts"""
+    L = _lib.lib()
+    assert L.gkr_comm_init_shared(None, 2, 0, b"/gkr_test") == -1
+    assert b"gkr_comm_init_shared" in L.gkr_last_error()
+    assert L.gkr_comm_init(None, 2, 0, None) == -1
+    ctxs = (C.c_void_p * 3)()
+    devs = (C.c_int32 * 3)(0, 0, 0)
+    assert L.gkr_comm_create(3, devs, ctxs) == -1           # not a power of two
+    assert all(not c for c in ctxs)
+
+
 def test_product_does_not_import_oracle():
     """the product package must never route through oracle/"""
     pkg = os.path.join(ROOT, "gkr_b200")
